@@ -1,0 +1,237 @@
+/*
+ * nvbx_c_api.h -- C ABI of libnvbx.so: the B200-native reconstruction hot path behind the
+ * nvblox_torch `Mapper` surface used by mindmap/mapping.
+ *
+ * Every entry point replaces one method of the reference's torch custom class
+ * `pynvblox::Mapper` (TORCH_LIBRARY(pynvblox) in
+ * submodules/nvblox/nvblox_torch/cpp/src/py_nvblox.cu:55-344) or of its layer / mesh holders.
+ * The reference-side file:line each function stands in for is cited next to it.
+ *
+ * Conventions
+ *   - plain C types only: device pointers are passed as `const void*` / `void*`, poses as 16
+ *     row-major floats (T_L_C, camera -> layer/world), intrinsics as fx, fy, cx, cy.
+ *   - `stream` is a cudaStream_t cast to void* (0 = legacy default stream).  All kernels are enqueued
+ *     on it; calls do NOT synchronise unless documented (the reference synchronises after every kernel:
+ *     projective_integrator_impl.cuh:341,443).
+ *   - every function returns NVBX_OK (0) or a negative error code; nvbx_last_error() returns the
+ *     message of the calling thread's last failure.  Nothing aborts the process.
+ *   - a handle is not thread-safe; use one handle per host thread / per GPU.
+ */
+#ifndef NVBX_C_API_H_
+#define NVBX_C_API_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NVBX_OK 0
+#define NVBX_ERR_INVALID_ARGUMENT (-1)
+#define NVBX_ERR_CUDA (-2)
+#define NVBX_ERR_OUT_OF_MEMORY (-3)
+#define NVBX_ERR_NOT_FOUND (-4)
+#define NVBX_ERR_UNSUPPORTED (-5)
+
+/* Layer selectors. */
+#define NVBX_LAYER_TSDF 0
+#define NVBX_LAYER_FEATURE 1
+
+/* WeightingFunctionType, nvblox/integrators/weighting_function.h:11-18 */
+#define NVBX_WEIGHT_CONSTANT 0
+#define NVBX_WEIGHT_CONSTANT_DROPOFF 1
+#define NVBX_WEIGHT_INVERSE_SQUARE 2
+#define NVBX_WEIGHT_INVERSE_SQUARE_DROPOFF 3
+#define NVBX_WEIGHT_INVERSE_SQUARE_TSDF_DISTANCE_PENALTY 4
+#define NVBX_WEIGHT_LINEAR_WITH_MAX 5
+
+/* WorkspaceBoundsType, nvblox/geometry/workspace_bounds.h:24 */
+#define NVBX_WORKSPACE_UNBOUNDED 0
+#define NVBX_WORKSPACE_HEIGHT_BOUNDS 1
+#define NVBX_WORKSPACE_BOUNDING_BOX 2
+
+/*
+ * One POD carrying every reference parameter that reaches the hot path.  Defaults (set by
+ * nvbx_default_params) are the reference's: projective_integrator_params.h:24-73,
+ * view_calculator_params.h:23-59, tsdf_decay_integrator_params.h:22-38,
+ * decay_integrator_base_params.h:22-24, mesh_integrator_params.h:21-26, mesh_integrator.h:126-133,
+ * sphere_tracer.h:216-218, projective_appearance_integrator.cu:61 (ray length frozen at 7 m).
+ */
+typedef struct nvbx_params {
+  /* ProjectiveIntegratorParams */
+  float max_integration_distance_m;          /* 7.0  */
+  float truncation_distance_vox;             /* 4.0  (TSDF integrator) */
+  int32_t weighting_mode;                    /* NVBX_WEIGHT_INVERSE_SQUARE */
+  float max_weight;                          /* 5.0  */
+  float invalid_depth_decay_factor;          /* -1.0 (disabled) */
+  float appearance_measurement_weight;       /* 0.8  (mindmap: 1.0) */
+  /* The appearance integrators keep their own truncation distance; Mapper::setMapperParams
+   * (mapper.cpp:126-141) never forwards projective_integrator_truncation_distance_vox to them, so it
+   * stays at the default unless set directly on the integrator (as the reference's gtests do). */
+  float appearance_truncation_distance_vox;  /* 4.0  */
+  int32_t sphere_tracing_subsampling;        /* 4    */
+  float sphere_tracing_max_ray_length_m;     /* 7.0  */
+  int32_t sphere_tracing_max_steps;          /* 100  */
+  float sphere_tracing_surface_epsilon_vox;  /* 0.1  */
+  /* TsdfDecayIntegratorParams + DecayIntegratorBaseParams */
+  float tsdf_decay_factor;                   /* 0.95 */
+  float tsdf_decayed_weight_threshold;       /* 1e-3 */
+  int32_t tsdf_set_free_distance_on_decayed; /* 0    */
+  float tsdf_decayed_free_distance_vox;      /* 4.0  */
+  int32_t deallocate_decayed_blocks;         /* 1    */
+  /* ViewCalculatorParams */
+  int32_t raycast_subsampling_factor;        /* 4 (mindmap: 1) */
+  int32_t workspace_bounds_type;             /* NVBX_WORKSPACE_UNBOUNDED */
+  float workspace_min[3];                    /* x 0, y 2, z(height) 0 */
+  float workspace_max[3];                    /* x 0, y 2, z(height) 1 */
+  int32_t cache_last_viewpoint;              /* 1    */
+  /* MeshIntegratorParams */
+  float mesh_min_weight;                     /* 1e-4 */
+  int32_t mesh_weld_vertices;                /* 1    */
+  float mesh_cutoff_distance_vox;            /* 5.0  */
+  /* BlockMemoryPoolParams: accepted for drop-in compatibility.  Our pools are slab arenas; these two
+   * only seed the initial slab size. */
+  int32_t num_preallocated_blocks;           /* 2048 */
+  float expansion_factor;                    /* 2.0  */
+  /* Ours.  0 (default): when appearance_measurement_weight == 1 the old feature vector is not
+   * re-read (x_new = x_meas; the reference computes 0*x_old + 1*x_meas in fp16, which differs only
+   * in the sign of zero and in NaN poisoning from non-finite old values).  1: always read + blend. */
+  int32_t strict_blend;
+} nvbx_params;
+
+typedef struct nvbx_mapper nvbx_mapper;
+
+/* Per-map counters that define the algorithmic bytes of SURVEY.md 8(d); accumulated on the device,
+ * read back (with a stream sync) by nvbx_get_counters.  Reset by nvbx_reset_counters. */
+typedef struct nvbx_counters {
+  int64_t depth_frames;        /* nvbx_integrate_depth calls                                   */
+  int64_t feature_frames;      /* nvbx_integrate_features calls                                */
+  int64_t tsdf_blocks_in_view; /* sum over depth frames of blocks handed to the TSDF update    */
+  int64_t tsdf_voxels_updated; /* N_tsdf: voxels whose TSDF value/weight was rewritten         */
+  int64_t tsdf_blocks_allocated;
+  int64_t feature_candidate_blocks; /* N_cand: TSDF blocks read by the truncation-band test    */
+  int64_t feature_band_blocks;      /* blocks handed to the feature update                     */
+  int64_t feature_voxels_updated;   /* N_upd                                                   */
+  int64_t feature_blocks_allocated;
+  int64_t blocks_deallocated;
+  int64_t mesh_blocks_remeshed;
+  int64_t mesh_vertices;            /* N_v of the last update                                  */
+  int64_t reserved[4];
+} nvbx_counters;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------- */
+
+/* Fill `p` with the reference defaults listed above. */
+void nvbx_default_params(nvbx_params* p);
+
+/* pynvblox::Mapper::Mapper(voxel_sizes, integrator_types, params), py_mapper.cu:33-70.  Only TSDF maps
+ * exist on this path.  `feature_channels` is the reference's compile-time
+ * NVBLOX_FEATURE_ARRAY_NUM_ELEMENTS (core/feature_array.h:22-28), a run-time value here; it must be a
+ * multiple of 8 (128-bit vectors).  `device` is the CUDA ordinal (the reference hard-codes 0). */
+int nvbx_create(int n_maps, const float* voxel_sizes_m, const nvbx_params* params, int feature_channels,
+                int device, nvbx_mapper** out);
+void nvbx_destroy(nvbx_mapper* m);
+int nvbx_num_maps(const nvbx_mapper* m);       /* Mapper::getNumMappers, py_mapper.cu:72 */
+int nvbx_feature_channels(const nvbx_mapper* m);
+int nvbx_get_params(const nvbx_mapper* m, nvbx_params* out); /* Mapper::getMapperParams, py_mapper.cu:80 */
+const char* nvbx_last_error(void);
+
+/* ---- frame integration -------------------------------------------------------------------------- */
+
+/* Mapper::integrateDepth, py_mapper.cu:85-113 -> nvblox::Mapper::integrateDepth mapper.cpp:358-407.
+ * depth: device float[H*W] row-major; mask: device uint8[H*W] or NULL (non-zero = active). */
+int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int height, int width,
+                         const void* mask, const float* T_L_C, float fx, float fy, float cx, float cy,
+                         void* stream);
+
+/* Mapper::integrateFeatures, py_mapper.cu:146-174 -> mapper.cpp:452-464 ->
+ * ProjectiveAppearanceIntegrator<FeatureLayer>::integrateFrame projective_appearance_integrator.cu:72-169.
+ * features: device fp16 [H*W*C] (HWC, contiguous, 16-byte aligned); channels must equal
+ * nvbx_feature_channels(); height/width must be multiples of sphere_tracing_subsampling
+ * (sphere_tracer.cu:426-427 CHECKs the same). */
+int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, int height, int width,
+                            int channels, const void* mask, const float* T_L_C, float fx, float fy,
+                            float cx, float cy, void* stream);
+
+/* Mapper::integrateColor, py_mapper.cu:115-144.  SURVEY 8(f) N1 ("next"): arguments are validated,
+ * the planes-viewpoint cache is not touched and no colour layer is kept in this round. */
+int nvbx_integrate_color(nvbx_mapper* m, int map_id, const void* rgb, int height, int width,
+                         const void* mask, const float* T_L_C, float fx, float fy, float cx, float cy,
+                         void* stream);
+
+/* Same as integrate_depth + integrate_features but from HOST buffers (pinned or pageable): the H2D
+ * copies are enqueued on `stream` ahead of the kernels.  This is the end-to-end entry bench.py times. */
+int nvbx_integrate_frame_host(nvbx_mapper* m, int map_id, const float* depth_host, const void* features_host,
+                              int height, int width, int channels, const uint8_t* depth_mask_host,
+                              const uint8_t* feature_mask_host, const float* T_L_C, float fx, float fy,
+                              float cx, float cy, void* stream);
+
+/* Mapper::decayTsdf, py_mapper.cu:264-273 -> mapper.cpp:466-495.  map_id -1 = all maps. */
+int nvbx_decay(nvbx_mapper* m, int map_id, void* stream);
+
+/* Mapper::clear, py_mapper.cu:286-306. */
+int nvbx_clear(nvbx_mapper* m, int map_id, void* stream);
+
+/* ---- surface extraction ------------------------------------------------------------------------- */
+
+/* Mapper::updateFeatureMesh, py_mapper.cu:196-204 -> Mapper::updateMeshTemplate mapper.cpp:580-614
+ * (MeshIntegrator::integrateBlocksGPU mesh_integrator.cu:64-103 + updateAppearance
+ * mesh_integrator_appearance.cu:290-340).  Synchronises `stream` once (the vertex total sizes the
+ * output arena). */
+int nvbx_update_feature_mesh(nvbx_mapper* m, int map_id, void* stream);
+
+/* Mapper::getFeatureMesh, py_mapper.cu:223-239 + PyMesh::vertices/vertex_appearances/triangles
+ * py_mesh.cpp:19-90.  Returns DEVICE pointers owned by the handle, valid until the next
+ * update_feature_mesh / clear / decay of that map: vertices float[n_vertices*3], features
+ * fp16[n_vertices*C], triangles int32[n_triangles*3] (global vertex ids).  No kernel, no copy. */
+int nvbx_get_feature_mesh(nvbx_mapper* m, int map_id, const void** vertices, const void** features,
+                          const void** triangles, int64_t* n_vertices, int64_t* n_triangles);
+
+/* ---- layer views (PyVoxelBlockLayer, py_layer.cpp:24-47,99-198) ---------------------------------- */
+
+int64_t nvbx_num_blocks(nvbx_mapper* m, int map_id, int layer, void* stream);           /* numBlocks            */
+int64_t nvbx_num_allocated_blocks(nvbx_mapper* m, int map_id, int layer, void* stream); /* numAllocatedBlocks   */
+int64_t nvbx_num_allocated_bytes(nvbx_mapper* m, int map_id, int layer, void* stream);  /* numAllocatedBytes    */
+float nvbx_voxel_size(const nvbx_mapper* m, int map_id);
+/* get_all_block_indices: writes up to `capacity` int32 triples to HOST memory `out_xyz`, returns the count. */
+int64_t nvbx_get_block_indices(nvbx_mapper* m, int map_id, int layer, int32_t* out_xyz, int64_t capacity,
+                               void* stream);
+/* get_block_at_index: device pointer of the block's voxel array and its voxel stride in ELEMENTS.
+ * TSDF: float [8][8][8][2], stride 2.  Feature: fp16 [8][8][8][stride], stride = C + 8 (the first C are
+ * the feature, element C is the weight, the rest is padding that keeps rows 16-byte aligned), to be
+ * viewed as [8,8,8,C+1].  NVBX_ERR_NOT_FOUND if the block is not allocated. */
+int nvbx_get_block_ptr(nvbx_mapper* m, int map_id, int layer, int x, int y, int z, void** ptr,
+                       int64_t* voxel_stride_elems, void* stream);
+/* allocate_block_at_index (zero-initialised). */
+int nvbx_allocate_block(nvbx_mapper* m, int map_id, int layer, int x, int y, int z, void* stream);
+/* Layer::clear of one layer is not exposed by mindmap; nvbx_clear drops everything. */
+
+/* ---- point queries (queryTsdf / queryFeatures, py_mapper.cu:596-698; sdf_query.cu:206-270) -------- */
+
+/* xyz: device float[n*3]; out: device float[n*2] = (distance, weight); rows of unallocated positions
+ * are left untouched (the caller pre-fills zeros, mapper.py:352-356). */
+int nvbx_query_tsdf(nvbx_mapper* m, int map_id, const void* xyz, int64_t n, void* out, void* stream);
+/* out: device fp16[n*(C+1)] = (f_0..f_{C-1}, weight). */
+int nvbx_query_features(nvbx_mapper* m, int map_id, const void* xyz, int64_t n, void* out, void* stream);
+
+/* ---- accounting --------------------------------------------------------------------------------- */
+
+int nvbx_get_counters(nvbx_mapper* m, int map_id, nvbx_counters* out, void* stream);
+int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t nvbx_kernel_launch_count(void);
+/* Debug / parity hooks: copy the last frame's intermediate products to HOST memory.
+ *   which = 0: block indices handed to the last TSDF update   (int32 triples)
+ *   which = 1: block indices handed to the last feature update (int32 triples)
+ * returns the count (or a negative error). */
+int64_t nvbx_debug_last_block_list(nvbx_mapper* m, int map_id, int which, int32_t* out_xyz, int64_t capacity,
+                                   void* stream);
+/* last synthetic depth image (device float[rows*cols], sphere_tracer.cu:191-236) */
+int nvbx_debug_last_synthetic_depth(nvbx_mapper* m, int map_id, const void** ptr, int* rows, int* cols);
+
+const char* nvbx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVBX_C_API_H_ */

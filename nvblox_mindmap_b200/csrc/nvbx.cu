@@ -1,0 +1,1117 @@
+// nvbx.cu -- host orchestration and the C ABI of libnvbx.so (include/nvbx_c_api.h).
+//
+// The host side does what cannot be done on the device: argument checks, the viewpoint-cache decision
+// (pose/intrinsics comparison, view_calculator.cu:472-541), the view AABB (8 frustum corners), arena
+// sizing, and enqueueing a FIXED sequence of launches per call.  It never reads a result back during
+// frame integration or decay; the only synchronising calls are update_feature_mesh (vertex total),
+// the layer-view getters and get_counters.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/nvbx_c_api.h"
+#include "nvbx_mesh.cuh"
+
+using namespace nvbx;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fail(_e == cudaErrorMemoryAllocation ? NVBX_ERR_OUT_OF_MEMORY : NVBX_ERR_CUDA,         \
+                  "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);      \
+  } while (0)
+
+#define LAUNCH(kernel, grid, block, smem, stream, ...)                                              \
+  do {                                                                                              \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                     \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                             \
+    CUDA_TRY(cudaPeekAtLastError());                                                                \
+  } while (0)
+
+template <typename T>
+struct DevBuf {  // grow-only device scratch buffer
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n, cudaStream_t stream, bool keep = false) {
+    if (n <= cap) return NVBX_OK;
+    size_t ncap = std::max(n, cap + cap / 2 + 64);
+    T* np = nullptr;
+    CUDA_TRY(cudaMalloc(&np, ncap * sizeof(T)));
+    if (p) {
+      if (keep) CUDA_TRY(cudaMemcpyAsync(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));  // earlier kernels may still use the old buffer
+      cudaFree(p);
+    }
+    p = np;
+    cap = ncap;
+    return NVBX_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+// One viewpoint-cache entry: pose + camera on the host, the block-index list it produced on the device.
+struct CacheEntry {
+  Pose T;
+  Cam cam;
+  DevBuf<int3> idx;
+  int* d_count = nullptr;
+  int bound = 0;  // host upper bound of *d_count (cells of the AABB it was built from)
+};
+
+struct ViewCache {  // deque semantics of ViewpointCache (kMaxCacheSize = 2), view_calculator.cu:519-541
+  std::deque<CacheEntry*> live;
+  std::vector<std::unique_ptr<CacheEntry>> pool;
+  CacheEntry* lookup(const Pose& T, const Cam& cam) {
+    for (CacheEntry* e : live)
+      if (cameras_equal(cam, e->cam, T, e->T)) return e;
+    return nullptr;
+  }
+  // entry to (over)write for a new result: the one that would be evicted, or a fresh one
+  int acquire(CacheEntry** out) {
+    if (live.size() == 2) {
+      *out = live.back();
+      live.pop_back();
+      return NVBX_OK;
+    }
+    pool.emplace_back(new CacheEntry());
+    CacheEntry* e = pool.back().get();
+    CUDA_TRY(cudaMalloc(&e->d_count, sizeof(int)));
+    *out = e;
+    return NVBX_OK;
+  }
+  void store(CacheEntry* e) { live.push_front(e); }
+  void release() {
+    for (auto& e : pool) {
+      e->idx.release();
+      if (e->d_count) cudaFree(e->d_count);
+    }
+    pool.clear();
+    live.clear();
+  }
+};
+
+struct Map {
+  float voxel_size = 0, block_size = 0;
+  MapDev dev{};
+  // slot table + hash (contiguous, re-allocated on growth)
+  int slot_capacity = 0;
+  int feat_capacity = 0;
+  long long slot_used_ub = 0;  // host upper bounds of live ids (pessimistic between syncs)
+  long long feat_used_ub = 0;
+  std::vector<void*> tsdf_slabs, feat_slabs;
+  float2** d_tsdf_table = nullptr;
+  __half** d_feat_table = nullptr;
+  Ctrl* d_ctrl = nullptr;
+  Ctrl* h_ctrl = nullptr;  // pinned mirror
+  ViewCache raycast_cache, planes_cache;
+  CacheEntry scratch_ray, scratch_planes;  // used when the cache is disabled
+  DevBuf<uint8_t> grid;
+  DevBuf<int> view_slots, band_slots, newfeat_slots;
+  DevBuf<float> synth;
+  int synth_rows = 0, synth_cols = 0;
+  CacheEntry* last_depth_entry = nullptr;
+  bool have_band_list = false;
+  // mesh
+  DevBuf<int> cnt_v, cnt_t, off_v, off_t;
+  DevBuf<float> arena_v[2];
+  DevBuf<__half> arena_f[2];
+  DevBuf<int> arena_t[2];
+  int arena_cur = 0;
+  long long mesh_nv = 0, mesh_nt = 0;
+  // host staging for nvbx_integrate_frame_host
+  DevBuf<float> st_depth;
+  DevBuf<__half> st_feat;
+  DevBuf<uint8_t> st_mask_d, st_mask_f;
+  // misc single-value device scratch
+  int* d_tmp_int = nullptr;
+  unsigned long long* d_tmp_ptr = nullptr;
+  DevBuf<int3> idx_out;
+};
+
+}  // namespace
+
+struct nvbx_mapper {
+  int device = 0;
+  int C = 0;
+  int sm_count = 148;
+  nvbx_params params{};
+  std::vector<std::unique_ptr<Map>> maps;
+};
+
+namespace {
+
+int persistent_grid(const nvbx_mapper* m, int ctas_per_sm) { return m->sm_count * ctas_per_sm; }
+
+int upload_slab_tables(Map& mp, cudaStream_t stream) {
+  if (!mp.tsdf_slabs.empty())
+    CUDA_TRY(cudaMemcpyAsync(mp.d_tsdf_table, mp.tsdf_slabs.data(), mp.tsdf_slabs.size() * sizeof(void*),
+                             cudaMemcpyHostToDevice, stream));
+  if (!mp.feat_slabs.empty())
+    CUDA_TRY(cudaMemcpyAsync(mp.d_feat_table, mp.feat_slabs.data(), mp.feat_slabs.size() * sizeof(void*),
+                             cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));  // the host vectors may reallocate later
+  return NVBX_OK;
+}
+
+template <typename T>
+int regrow(T** p, size_t old_n, size_t new_n, cudaStream_t stream) {
+  T* np = nullptr;
+  CUDA_TRY(cudaMalloc(&np, new_n * sizeof(T)));
+  if (*p && old_n) CUDA_TRY(cudaMemcpyAsync(np, *p, old_n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  if (*p) cudaFree(*p);
+  *p = np;
+  return NVBX_OK;
+}
+
+// Grow the slot table (and TSDF slabs, hash) to hold `new_cap` block indices.
+int grow_slots(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  const int old = mp.slot_capacity;
+  new_cap = ((new_cap + (1 << kTsdfSlabShift) - 1) >> kTsdfSlabShift) << kTsdfSlabShift;
+  if ((new_cap >> kTsdfSlabShift) > kMaxSlabs) return fail(NVBX_ERR_OUT_OF_MEMORY, "TSDF arena limit reached");
+  int rc;
+  if ((rc = regrow(&mp.dev.blk_index, old, new_cap, stream))) return rc;
+  if ((rc = regrow(&mp.dev.blk_layers, old, new_cap, stream))) return rc;
+  if ((rc = regrow(&mp.dev.blk_feat, old, new_cap, stream))) return rc;
+  if ((rc = regrow(&mp.dev.blk_dirty, old, new_cap, stream))) return rc;
+  if ((rc = regrow(&mp.dev.blk_mesh, old, new_cap, stream))) return rc;
+  if ((rc = regrow(&mp.dev.slot_free, old, new_cap, stream))) return rc;
+  CUDA_TRY(cudaMemsetAsync(mp.dev.blk_layers + old, 0, new_cap - old, stream));
+  while ((int)mp.tsdf_slabs.size() < (new_cap >> kTsdfSlabShift)) {
+    void* s = nullptr;
+    CUDA_TRY(cudaMalloc(&s, (size_t)(1 << kTsdfSlabShift) * kVoxelsPerBlock * sizeof(float2)));
+    mp.tsdf_slabs.push_back(s);
+  }
+  if ((rc = upload_slab_tables(mp, stream))) return rc;
+  mp.slot_capacity = new_cap;
+  mp.dev.slot_capacity = new_cap;
+  // hash: next pow2 >= 4 * capacity
+  unsigned hcap = 1024;
+  while (hcap < 4u * (unsigned)new_cap) hcap <<= 1;
+  if (hcap != mp.dev.hash_mask + 1 || mp.dev.keys == nullptr) {
+    if (mp.dev.keys) cudaFree(mp.dev.keys);
+    if (mp.dev.vals) cudaFree(mp.dev.vals);
+    mp.dev.keys = nullptr;
+    mp.dev.vals = nullptr;
+    CUDA_TRY(cudaMalloc(&mp.dev.keys, (size_t)hcap * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&mp.dev.vals, (size_t)hcap * sizeof(int)));
+    mp.dev.hash_mask = hcap - 1;
+    LAUNCH(k_hash_clear, persistent_grid(m, 4), 256, 0, stream, mp.dev, 1);
+    LAUNCH(k_hash_reinsert, persistent_grid(m, 4), 256, 0, stream, mp.dev, 1);
+  }
+  return NVBX_OK;
+}
+
+int grow_feats(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  const int old = mp.feat_capacity;
+  new_cap = ((new_cap + (1 << kFeatSlabShift) - 1) >> kFeatSlabShift) << kFeatSlabShift;
+  if ((new_cap >> kFeatSlabShift) > kMaxSlabs) return fail(NVBX_ERR_OUT_OF_MEMORY, "feature arena limit reached");
+  int rc;
+  if ((rc = regrow(&mp.dev.feat_free, old, new_cap, stream))) return rc;
+  const size_t slab_bytes = (size_t)(1 << kFeatSlabShift) * kVoxelsPerBlock * (size_t)mp.dev.row * sizeof(__half);
+  while ((int)mp.feat_slabs.size() < (new_cap >> kFeatSlabShift)) {
+    void* s = nullptr;
+    CUDA_TRY(cudaMalloc(&s, slab_bytes));
+    mp.feat_slabs.push_back(s);
+  }
+  if ((rc = upload_slab_tables(mp, stream))) return rc;
+  mp.feat_capacity = new_cap;
+  mp.dev.feat_capacity = new_cap;
+  return NVBX_OK;
+}
+
+int read_ctrl(Map& mp, cudaStream_t stream) {
+  CUDA_TRY(cudaMemcpyAsync(mp.h_ctrl, mp.d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  if (mp.h_ctrl->overflow) return fail(NVBX_ERR_OUT_OF_MEMORY, "internal: a block arena overflowed on the device");
+  return NVBX_OK;
+}
+
+// Workspace cell count (upper bound of distinct block indices when a bounding box is set), or -1.
+long long workspace_cells(const nvbx_mapper* m, const Map& mp) {
+  if (m->params.workspace_bounds_type != NVBX_WORKSPACE_BOUNDING_BOX) return -1;
+  long long n = 1;
+  for (int i = 0; i < 3; ++i) {
+    const float lo = m->params.workspace_min[i], hi = m->params.workspace_max[i];
+    if (!(hi >= lo)) return 0;
+    const long long c = (long long)std::floor(hi / mp.block_size) - (long long)std::floor(lo / mp.block_size) + 1;
+    n *= std::max(1LL, c);
+    if (n > (1LL << 40)) return -1;
+  }
+  return n;
+}
+
+// Make sure `need` more block indices can be allocated by the next kernel without the host knowing
+// how many really will be (see DESIGN.md "Arena sizing without read-backs").
+int ensure_slots(nvbx_mapper* m, Map& mp, long long need, cudaStream_t stream) {
+  const long long ws = workspace_cells(m, mp);
+  auto bound = [&](long long v) { return ws >= 0 ? std::min(v, ws) : v; };
+  if (bound(mp.slot_used_ub + need) <= mp.slot_capacity) {
+    mp.slot_used_ub = bound(mp.slot_used_ub + need);
+    return NVBX_OK;
+  }
+  int rc = read_ctrl(mp, stream);  // exact figure
+  if (rc) return rc;
+  mp.slot_used_ub = (long long)mp.h_ctrl->slot_high - mp.h_ctrl->slot_free_top;
+  const long long want = bound(mp.slot_used_ub + need);
+  if (want > mp.slot_capacity) {
+    long long ncap = std::max(want, (long long)(mp.slot_capacity * std::max(1.5f, m->params.expansion_factor)));
+    if (ws >= 0) ncap = std::min(ncap, std::max(ws, want));
+    if (ncap > (1LL << 30)) return fail(NVBX_ERR_OUT_OF_MEMORY, "map too large (%lld blocks)", ncap);
+    if ((rc = grow_slots(m, mp, (int)ncap, stream))) return rc;
+  }
+  mp.slot_used_ub = want;
+  return NVBX_OK;
+}
+bool slots_fit(const nvbx_mapper* m, const Map& mp, long long need) {
+  const long long ws = workspace_cells(m, mp);
+  const long long v = mp.slot_used_ub + need;
+  return (ws >= 0 ? std::min(v, ws) : v) <= mp.slot_capacity;
+}
+int ensure_feats(nvbx_mapper* m, Map& mp, long long need, cudaStream_t stream) {
+  need = std::min(need, mp.slot_used_ub);  // a feature block needs a TSDF block
+  auto bound = [&](long long v) { return std::min(v, mp.slot_used_ub); };
+  if (bound(mp.feat_used_ub + need) <= mp.feat_capacity) {
+    mp.feat_used_ub = bound(mp.feat_used_ub + need);
+    return NVBX_OK;
+  }
+  int rc = read_ctrl(mp, stream);
+  if (rc) return rc;
+  mp.feat_used_ub = (long long)mp.h_ctrl->feat_high - mp.h_ctrl->feat_free_top;
+  mp.slot_used_ub = (long long)mp.h_ctrl->slot_high - mp.h_ctrl->slot_free_top;
+  need = std::min(need, mp.slot_used_ub);
+  const long long want = bound(mp.feat_used_ub + need);
+  if (want > mp.feat_capacity) {
+    long long ncap = std::max(want, (long long)(mp.feat_capacity * 1.5f));
+    ncap = std::min(ncap, std::max(want, mp.slot_used_ub));
+    if ((rc = grow_feats(m, mp, (int)ncap, stream))) return rc;
+  }
+  mp.feat_used_ub = want;
+  return NVBX_OK;
+}
+
+struct GridSpec {
+  ViewGrid g;
+  bool empty;
+};
+// AABB -> block grid (view_calculator.cu:283-289); workspace clipping (workspace_bounds.cpp:20-61)
+int make_grid(const nvbx_mapper* m, const Map& mp, Aabb a, GridSpec* out) {
+  const nvbx_params& p = m->params;
+  if (p.workspace_bounds_type == NVBX_WORKSPACE_HEIGHT_BOUNDS) {
+    a.mn[2] = fmaxf(a.mn[2], p.workspace_min[2]);
+    a.mx[2] = fminf(a.mx[2], p.workspace_max[2]);
+  } else if (p.workspace_bounds_type == NVBX_WORKSPACE_BOUNDING_BOX) {
+    for (int i = 0; i < 3; ++i) {
+      a.mn[i] = fmaxf(p.workspace_min[i], a.mn[i]);
+      a.mx[i] = fminf(p.workspace_max[i], a.mx[i]);
+    }
+  }
+  out->empty = a.empty();
+  if (out->empty) return NVBX_OK;
+  V3 lo, hi;
+  lo.x = a.mn[0];
+  lo.y = a.mn[1];
+  lo.z = a.mn[2];
+  hi.x = a.mx[0];
+  hi.y = a.mx[1];
+  hi.z = a.mx[2];
+  const I3 mn = block_index_from_position(mp.block_size, lo);
+  const I3 mx = block_index_from_position(mp.block_size, hi);
+  const long long sx = (long long)mx.x - mn.x + 1, sy = (long long)mx.y - mn.y + 1, sz = (long long)mx.z - mn.z + 1;
+  const long long n = sx * sy * sz;
+  if (sx <= 0 || sy <= 0 || sz <= 0 || n > (1LL << 30))
+    return fail(NVBX_ERR_UNSUPPORTED, "view AABB spans %lld x %lld x %lld blocks; set workspace bounds", sx, sy, sz);
+  out->g.mn = mn;
+  out->g.sx = (int)sx;
+  out->g.sy = (int)sy;
+  out->g.sz = (int)sz;
+  out->g.n_cells = (int)n;
+  return NVBX_OK;
+}
+
+int check_map(nvbx_mapper* m, int map_id) {
+  if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper handle");
+  if (map_id < 0 || map_id >= (int)m->maps.size())
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "mapper_id %d out of range [0, %d)", map_id, (int)m->maps.size());
+  cudaError_t e = cudaSetDevice(m->device);
+  if (e != cudaSuccess) return fail(NVBX_ERR_CUDA, "cudaSetDevice(%d): %s", m->device, cudaGetErrorString(e));
+  return NVBX_OK;
+}
+
+int init_map(nvbx_mapper* m, Map& mp, float voxel_size, cudaStream_t stream) {
+  mp.voxel_size = voxel_size;
+  mp.block_size = voxel_size * 8;  // voxelSizeToBlockSize
+  mp.dev = MapDev{};
+  mp.dev.block_size = mp.block_size;
+  mp.dev.voxel_size = voxel_size;
+  mp.dev.voxel_size_inv = (float)(1.0 / (double)(mp.block_size * (1.0f / 8.0f)));
+  mp.dev.C = m->C;
+  mp.dev.row = m->C + 8;
+  CUDA_TRY(cudaMalloc(&mp.d_ctrl, sizeof(Ctrl)));
+  CUDA_TRY(cudaMemsetAsync(mp.d_ctrl, 0, sizeof(Ctrl), stream));
+  CUDA_TRY(cudaMallocHost(&mp.h_ctrl, sizeof(Ctrl)));
+  std::memset(mp.h_ctrl, 0, sizeof(Ctrl));
+  mp.dev.ctrl = mp.d_ctrl;
+  CUDA_TRY(cudaMalloc(&mp.d_tsdf_table, kMaxSlabs * sizeof(void*)));
+  CUDA_TRY(cudaMalloc(&mp.d_feat_table, kMaxSlabs * sizeof(void*)));
+  mp.dev.tsdf_slabs = mp.d_tsdf_table;
+  mp.dev.feat_slabs = mp.d_feat_table;
+  CUDA_TRY(cudaMalloc(&mp.d_tmp_int, sizeof(int)));
+  CUDA_TRY(cudaMalloc(&mp.d_tmp_ptr, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&mp.scratch_ray.d_count, sizeof(int)));
+  CUDA_TRY(cudaMalloc(&mp.scratch_planes.d_count, sizeof(int)));
+  int rc = grow_slots(m, mp, std::max(1024, m->params.num_preallocated_blocks), stream);
+  if (rc) return rc;
+  return grow_feats(m, mp, 1 << kFeatSlabShift, stream);
+}
+
+void destroy_map(Map& mp) {
+  cudaDeviceSynchronize();
+  auto F = [](auto*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+  };
+  F(mp.dev.keys);
+  F(mp.dev.vals);
+  F(mp.dev.blk_index);
+  F(mp.dev.blk_layers);
+  F(mp.dev.blk_feat);
+  F(mp.dev.blk_dirty);
+  F(mp.dev.blk_mesh);
+  F(mp.dev.slot_free);
+  F(mp.dev.feat_free);
+  for (void* s : mp.tsdf_slabs) cudaFree(s);
+  for (void* s : mp.feat_slabs) cudaFree(s);
+  mp.tsdf_slabs.clear();
+  mp.feat_slabs.clear();
+  F(mp.d_tsdf_table);
+  F(mp.d_feat_table);
+  F(mp.d_ctrl);
+  if (mp.h_ctrl) cudaFreeHost(mp.h_ctrl);
+  mp.h_ctrl = nullptr;
+  F(mp.d_tmp_int);
+  F(mp.d_tmp_ptr);
+  mp.raycast_cache.release();
+  mp.planes_cache.release();
+  mp.scratch_ray.idx.release();
+  mp.scratch_planes.idx.release();
+  F(mp.scratch_ray.d_count);
+  F(mp.scratch_planes.d_count);
+  mp.grid.release();
+  mp.view_slots.release();
+  mp.band_slots.release();
+  mp.newfeat_slots.release();
+  mp.synth.release();
+  mp.cnt_v.release();
+  mp.cnt_t.release();
+  mp.off_v.release();
+  mp.off_t.release();
+  for (int i = 0; i < 2; ++i) {
+    mp.arena_v[i].release();
+    mp.arena_f[i].release();
+    mp.arena_t[i].release();
+  }
+  mp.st_depth.release();
+  mp.st_feat.release();
+  mp.st_mask_d.release();
+  mp.st_mask_f.release();
+  mp.idx_out.release();
+}
+
+Cam make_cam(float fx, float fy, float cx, float cy, int H, int W) {
+  Cam c;
+  c.fu = fx;
+  c.fv = fy;
+  c.cu = cx;
+  c.cv = cy;
+  c.width = W;
+  c.height = H;
+  return c;
+}
+
+template <int VPL>
+int launch_feature(nvbx_mapper* m, Map& mp, const FeatFrame& ff, cudaStream_t stream) {
+  LAUNCH(k_feature_integrate<VPL>, persistent_grid(m, 2), 512, 0, stream, mp.dev, mp.band_slots.p, ff);
+  return NVBX_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* nvbx_version(void) { return "nvbx 0.1.0 (sm_100a)"; }
+const char* nvbx_last_error(void) { return g_last_error.c_str(); }
+int64_t nvbx_kernel_launch_count(void) { return g_launches.load(); }
+
+void nvbx_default_params(nvbx_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->max_integration_distance_m = 7.0f;
+  p->truncation_distance_vox = 4.0f;
+  p->weighting_mode = NVBX_WEIGHT_INVERSE_SQUARE;
+  p->max_weight = 5.0f;
+  p->invalid_depth_decay_factor = -1.0f;
+  p->appearance_measurement_weight = 0.8f;
+  p->appearance_truncation_distance_vox = 4.0f;
+  p->sphere_tracing_subsampling = 4;
+  p->sphere_tracing_max_ray_length_m = 7.0f;
+  p->sphere_tracing_max_steps = 100;
+  p->sphere_tracing_surface_epsilon_vox = 0.1f;
+  p->tsdf_decay_factor = 0.95f;
+  p->tsdf_decayed_weight_threshold = 1e-3f;
+  p->tsdf_set_free_distance_on_decayed = 0;
+  p->tsdf_decayed_free_distance_vox = 4.0f;
+  p->deallocate_decayed_blocks = 1;
+  p->raycast_subsampling_factor = 4;
+  p->workspace_bounds_type = NVBX_WORKSPACE_UNBOUNDED;
+  p->workspace_min[0] = 0.0f;
+  p->workspace_min[1] = 2.0f;
+  p->workspace_min[2] = 0.0f;
+  p->workspace_max[0] = 0.0f;
+  p->workspace_max[1] = 2.0f;
+  p->workspace_max[2] = 1.0f;
+  p->cache_last_viewpoint = 1;
+  p->mesh_min_weight = 1e-4f;
+  p->mesh_weld_vertices = 1;
+  p->mesh_cutoff_distance_vox = 5.0f;
+  p->num_preallocated_blocks = 2048;
+  p->expansion_factor = 2.0f;
+  p->strict_blend = 0;
+}
+
+int nvbx_create(int n_maps, const float* voxel_sizes_m, const nvbx_params* params, int feature_channels, int device,
+                nvbx_mapper** out) {
+  if (!out) return fail(NVBX_ERR_INVALID_ARGUMENT, "out is null");
+  *out = nullptr;
+  if (n_maps <= 0 || !voxel_sizes_m) return fail(NVBX_ERR_INVALID_ARGUMENT, "need at least one map");
+  if (feature_channels <= 0 || feature_channels % 8)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "feature_channels must be a positive multiple of 8 (got %d)",
+                feature_channels);
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(NVBX_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+  if (device < 0 || device >= n_dev) return fail(NVBX_ERR_INVALID_ARGUMENT, "device %d out of range", device);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(NVBX_ERR_UNSUPPORTED, "device %s is sm_%d%d; libnvbx is built for sm_100a only", prop.name, prop.major,
+                prop.minor);
+  std::unique_ptr<nvbx_mapper> m(new nvbx_mapper());
+  m->device = device;
+  m->C = feature_channels;
+  m->sm_count = prop.multiProcessorCount;
+  if (params)
+    m->params = *params;
+  else
+    nvbx_default_params(&m->params);
+  const nvbx_params& p = m->params;
+  if (!(p.appearance_measurement_weight > 0.0f && p.appearance_measurement_weight <= 1.0f))
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "appearance_measurement_weight must be in (0, 1]");
+  if (p.raycast_subsampling_factor <= 0 || p.sphere_tracing_subsampling <= 0)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "subsampling factors must be positive");
+  // the mesh kernels need > 48 KiB of dynamic shared memory
+  CUDA_TRY(cudaFuncSetAttribute(k_mesh_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem)));
+  CUDA_TRY(cudaFuncSetAttribute(k_mesh_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem)));
+  for (int i = 0; i < n_maps; ++i) {
+    if (!(voxel_sizes_m[i] > 0.0f)) return fail(NVBX_ERR_INVALID_ARGUMENT, "voxel size must be positive");
+    m->maps.emplace_back(new Map());
+    int rc = init_map(m.get(), *m->maps[i], voxel_sizes_m[i], 0);
+    if (rc) {
+      for (auto& mp : m->maps) destroy_map(*mp);
+      return rc;
+    }
+  }
+  CUDA_TRY(cudaDeviceSynchronize());
+  *out = m.release();
+  return NVBX_OK;
+}
+
+void nvbx_destroy(nvbx_mapper* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  for (auto& mp : m->maps) destroy_map(*mp);
+  delete m;
+}
+
+int nvbx_num_maps(const nvbx_mapper* m) { return m ? (int)m->maps.size() : 0; }
+int nvbx_feature_channels(const nvbx_mapper* m) { return m ? m->C : 0; }
+int nvbx_get_params(const nvbx_mapper* m, nvbx_params* out) {
+  if (!m || !out) return fail(NVBX_ERR_INVALID_ARGUMENT, "null argument");
+  *out = m->params;
+  return NVBX_OK;
+}
+float nvbx_voxel_size(const nvbx_mapper* m, int map_id) {
+  if (!m || map_id < 0 || map_id >= (int)m->maps.size()) return 0.0f;
+  return m->maps[map_id]->voxel_size;
+}
+
+// ---- depth ---------------------------------------------------------------------------------------
+int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int height, int width, const void* mask,
+                         const float* T_L_C_rm, float fx, float fy, float cx, float cy, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (!depth || !T_L_C_rm || height <= 0 || width <= 0) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad depth frame");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  Map& mp = *m->maps[map_id];
+  const nvbx_params& p = m->params;
+  const Pose T_L_C = pose_from_row_major(T_L_C_rm);
+  const Cam cam = make_cam(fx, fy, cx, cy, height, width);
+  const float trunc = p.truncation_distance_vox * mp.voxel_size;
+
+  CacheEntry* entry = p.cache_last_viewpoint ? mp.raycast_cache.lookup(T_L_C, cam) : nullptr;
+  if (entry) {
+    // cache hit: previous block list, blocks (re-)allocated where required
+    if ((rc = ensure_slots(m, mp, entry->bound, stream))) return rc;
+    if ((rc = mp.view_slots.ensure((size_t)entry->bound, stream))) return rc;
+    LAUNCH(k_view_alloc_from_list, persistent_grid(m, 2), 256, 0, stream, mp.dev, entry->idx.p, entry->d_count,
+           mp.view_slots.p);
+  } else {
+    GridSpec gs;
+    if ((rc = make_grid(m, mp, view_aabb(cam, T_L_C, 0.0f, p.max_integration_distance_m), &gs))) return rc;
+    if (gs.empty) {
+      mp.last_depth_entry = nullptr;
+      return NVBX_OK;  // nothing in view, nothing cached (view_calculator.cu:275-279)
+    }
+    if (p.cache_last_viewpoint) {
+      if ((rc = mp.raycast_cache.acquire(&entry))) return rc;
+    } else {
+      entry = &mp.scratch_ray;
+    }
+    const size_t n = (size_t)gs.g.n_cells;
+    if ((rc = entry->idx.ensure(n, stream))) return rc;
+    if ((rc = mp.grid.ensure(n, stream))) return rc;
+    if ((rc = mp.view_slots.ensure(n, stream))) return rc;
+    entry->T = T_L_C;
+    entry->cam = cam;
+    entry->bound = gs.g.n_cells;
+    CUDA_TRY(cudaMemsetAsync(mp.grid.p, 0, n, stream));
+    CUDA_TRY(cudaMemsetAsync(entry->d_count, 0, sizeof(int), stream));
+    const int s = p.raycast_subsampling_factor;
+    const int n_rows = (int)std::ceil((float)(height + 1) / (float)s);
+    const int n_cols = (int)std::ceil((float)(width + 1) / (float)s);
+    const dim3 rgrid((unsigned)std::ceil(n_cols / 16.0f), (unsigned)std::ceil(n_rows / 16.0f));
+    LAUNCH(k_raycast_mark, rgrid, dim3(16, 16), 0, stream, T_L_C, cam, (const float*)depth, height, width,
+           mp.block_size, p.max_integration_distance_m, trunc, s, gs.g, mp.grid.p);
+    const int cgrid = std::min(persistent_grid(m, 4), (gs.g.n_cells + 255) / 256);
+    if (!slots_fit(m, mp, (long long)n)) {
+      // The pessimistic bound (every cell of the AABB is new) does not fit: count the marked cells and
+      // read that one int back.  Only happens while the arena is still growing (or with an unbounded
+      // workspace); a bounded workspace reaches its cell count and never synchronises again.
+      CUDA_TRY(cudaMemsetAsync(mp.d_tmp_int, 0, sizeof(int), stream));
+      LAUNCH(k_count_marked, cgrid, 256, 0, stream, mp.grid.p, gs.g.n_cells, mp.d_tmp_int);
+      int marked = 0;
+      CUDA_TRY(cudaMemcpyAsync(&marked, mp.d_tmp_int, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      entry->bound = std::max(1, marked);
+    }
+    if ((rc = ensure_slots(m, mp, (long long)entry->bound, stream))) return rc;
+    LAUNCH(k_view_compact_alloc, cgrid, 256, 0, stream, mp.dev, mp.grid.p, gs.g, entry->idx.p, entry->d_count,
+           mp.view_slots.p);
+    if (p.cache_last_viewpoint) mp.raycast_cache.store(entry);
+  }
+  mp.last_depth_entry = entry;
+  DepthFrame f;
+  f.depth = (const float*)depth;
+  f.mask = (const uint8_t*)mask;
+  f.rows = height;
+  f.cols = width;
+  f.cam = cam;
+  f.T_C_L = inverse(T_L_C);
+  f.max_depth = p.max_integration_distance_m;
+  f.trunc = trunc;
+  f.max_weight = p.max_weight;
+  f.invalid_decay = p.invalid_depth_decay_factor;
+  f.weighting_mode = p.weighting_mode;
+  const int tgrid = std::max(1, std::min(persistent_grid(m, 2), entry->bound));
+  LAUNCH(k_tsdf_update, tgrid, 512, 0, stream, mp.dev, mp.view_slots.p, entry->d_count, f);
+  return NVBX_OK;
+}
+
+// ---- features ------------------------------------------------------------------------------------
+int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, int height, int width, int channels,
+                            const void* mask, const float* T_L_C_rm, float fx, float fy, float cx, float cy,
+                            void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (!features || !T_L_C_rm || height <= 0 || width <= 0) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad feature frame");
+  if (channels != m->C)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame has %d channels, the map was created with %d", channels,
+                m->C);
+  if (((uintptr_t)features) & 15) return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame must be 16-byte aligned");
+  const nvbx_params& p = m->params;
+  const int sub = p.sphere_tracing_subsampling;
+  if (width % sub || height % sub)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame %dx%d is not divisible by the sphere-tracing subsampling %d",
+                height, width, sub);
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  Map& mp = *m->maps[map_id];
+  const Pose T_L_C = pose_from_row_major(T_L_C_rm);
+  const Cam cam = make_cam(fx, fy, cx, cy, height, width);
+  const float trunc = p.appearance_truncation_distance_vox * mp.voxel_size;
+  const Pose T_C_L = inverse(T_L_C);
+  mp.have_band_list = false;
+
+  CacheEntry* entry = p.cache_last_viewpoint ? mp.planes_cache.lookup(T_L_C, cam) : nullptr;
+  if (!entry) {
+    GridSpec gs;
+    if ((rc = make_grid(m, mp, view_aabb(cam, T_L_C, 1e-6f, p.max_integration_distance_m + trunc), &gs))) return rc;
+    if (gs.empty) return NVBX_OK;
+    if (p.cache_last_viewpoint) {
+      if ((rc = mp.planes_cache.acquire(&entry))) return rc;
+    } else {
+      entry = &mp.scratch_planes;
+    }
+    if ((rc = entry->idx.ensure((size_t)gs.g.n_cells, stream))) return rc;
+    entry->T = T_L_C;
+    entry->cam = cam;
+    entry->bound = gs.g.n_cells;
+    CUDA_TRY(cudaMemsetAsync(entry->d_count, 0, sizeof(int), stream));
+    const V3 vmin = ray_from_image_plane(cam, -10.0f, -10.0f);
+    const V3 vmax = ray_from_image_plane(cam, (float)cam.width + 10.0f, (float)cam.height + 10.0f);
+    const int pgrid = std::min(persistent_grid(m, 4), (gs.g.n_cells + 255) / 256);
+    LAUNCH(k_planes_view, pgrid, 256, 0, stream, gs.g, mp.block_size, T_C_L, vmin.x, vmin.y, vmax.x, vmax.y,
+           entry->idx.p, entry->d_count);
+    if (p.cache_last_viewpoint) mp.planes_cache.store(entry);
+  }
+  const long long cand_bound = std::min((long long)entry->bound, std::max(1LL, mp.slot_used_ub));
+  if ((rc = ensure_feats(m, mp, cand_bound, stream))) return rc;
+  if ((rc = mp.band_slots.ensure((size_t)cand_bound, stream))) return rc;
+  if ((rc = mp.newfeat_slots.ensure((size_t)cand_bound, stream))) return rc;
+  const int srows = height / sub, scols = width / sub;
+  if ((rc = mp.synth.ensure((size_t)srows * scols, stream))) return rc;
+  mp.synth_rows = srows;
+  mp.synth_cols = scols;
+
+  // band_count and newfeat_count are adjacent ints in Ctrl
+  CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->band_count, 0, 2 * sizeof(int), stream));
+  const int bgrid = std::max(1, std::min(persistent_grid(m, 4), (entry->bound + 7) / 8));
+  LAUNCH(k_band_select, bgrid, 256, 0, stream, mp.dev, entry->idx.p, entry->d_count, trunc, mp.band_slots.p,
+         mp.newfeat_slots.p);
+  LAUNCH(k_zero_feature_blocks, persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.newfeat_slots.p);
+
+  TraceParams tp;
+  tp.cam = cam;
+  tp.T_L_C = T_L_C;
+  tp.trunc = trunc;
+  tp.max_steps = p.sphere_tracing_max_steps;
+  tp.max_ray_length = p.sphere_tracing_max_ray_length_m;
+  tp.eps = p.sphere_tracing_surface_epsilon_vox * mp.voxel_size;
+  tp.sub = sub;
+  tp.rows = srows;
+  tp.cols = scols;
+  LAUNCH(k_sphere_trace, dim3((scols + 7) / 8, (srows + 7) / 8), 64, 0, stream, mp.dev, tp, mp.synth.p);
+
+  FeatFrame ff;
+  ff.img = (const __half*)features;
+  ff.mask = (const uint8_t*)mask;
+  ff.synth = mp.synth.p;
+  ff.rows = height;
+  ff.cols = width;
+  ff.srows = srows;
+  ff.scols = scols;
+  ff.sub = height / srows;  // projective_integrator_impl.cuh:424-425
+  ff.cam = cam;
+  ff.T_C_L = T_C_L;
+  ff.max_depth = p.max_integration_distance_m;
+  ff.trunc = trunc;
+  ff.alpha = p.appearance_measurement_weight;
+  ff.max_weight = p.max_weight;
+  {
+    float w1 = 1.0f - ff.alpha, w2 = ff.alpha;  // blendTwoArrays, projective_appearance_integrator.cu:286-305
+    const float tot = w1 + w2;
+    w1 /= tot;
+    w2 /= tot;
+    const __half h1 = __float2half_rn(w1), h2 = __float2half_rn(w2);
+    std::memcpy(&ff.h_w1, &h1, 2);
+    std::memcpy(&ff.h_w2, &h2, 2);
+  }
+  ff.read_old = (p.strict_blend || ff.alpha != 1.0f) ? 1 : 0;
+  if (m->C % 256 == 0 && m->C / 256 == 3)
+    rc = launch_feature<3>(m, mp, ff, stream);
+  else if (m->C % 256 == 0 && m->C / 256 == 4)
+    rc = launch_feature<4>(m, mp, ff, stream);
+  else if (m->C % 256 == 0 && m->C / 256 == 2)
+    rc = launch_feature<2>(m, mp, ff, stream);
+  else if (m->C % 256 == 0 && m->C / 256 == 1)
+    rc = launch_feature<1>(m, mp, ff, stream);
+  else
+    rc = launch_feature<0>(m, mp, ff, stream);
+  if (rc) return rc;
+  mp.have_band_list = true;
+  return NVBX_OK;
+}
+
+int nvbx_integrate_color(nvbx_mapper* m, int map_id, const void* rgb, int height, int width, const void* mask,
+                         const float* T_L_C, float fx, float fy, float cx, float cy, void* stream) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (!rgb || !T_L_C || height <= 0 || width <= 0) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad colour frame");
+  (void)mask;
+  (void)fx;
+  (void)fy;
+  (void)cx;
+  (void)cy;
+  (void)stream;
+  return NVBX_OK;  // no colour layer in this round (output-neutral for the feature cloud)
+}
+
+int nvbx_integrate_frame_host(nvbx_mapper* m, int map_id, const float* depth_host, const void* features_host,
+                              int height, int width, int channels, const uint8_t* depth_mask_host,
+                              const uint8_t* feature_mask_host, const float* T_L_C, float fx, float fy, float cx,
+                              float cy, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (!depth_host || !features_host) return fail(NVBX_ERR_INVALID_ARGUMENT, "null host frame");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  Map& mp = *m->maps[map_id];
+  const size_t px = (size_t)height * width;
+  if ((rc = mp.st_depth.ensure(px, stream))) return rc;
+  if ((rc = mp.st_feat.ensure(px * channels, stream))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(mp.st_depth.p, depth_host, px * sizeof(float), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(mp.st_feat.p, features_host, px * channels * sizeof(__half), cudaMemcpyHostToDevice, stream));
+  const uint8_t* dm = nullptr;
+  const uint8_t* fm = nullptr;
+  if (depth_mask_host) {
+    if ((rc = mp.st_mask_d.ensure(px, stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(mp.st_mask_d.p, depth_mask_host, px, cudaMemcpyHostToDevice, stream));
+    dm = mp.st_mask_d.p;
+  }
+  if (feature_mask_host) {
+    if ((rc = mp.st_mask_f.ensure(px, stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(mp.st_mask_f.p, feature_mask_host, px, cudaMemcpyHostToDevice, stream));
+    fm = mp.st_mask_f.p;
+  }
+  if ((rc = nvbx_integrate_depth(m, map_id, mp.st_depth.p, height, width, dm, T_L_C, fx, fy, cx, cy, stream_v)))
+    return rc;
+  return nvbx_integrate_features(m, map_id, mp.st_feat.p, height, width, channels, fm, T_L_C, fx, fy, cx, cy,
+                                 stream_v);
+}
+
+// ---- decay / clear -------------------------------------------------------------------------------
+static int decay_one(nvbx_mapper* m, Map& mp, cudaStream_t stream) {
+  DecayParams dp;
+  dp.factor = m->params.tsdf_decay_factor;
+  dp.threshold = m->params.tsdf_decayed_weight_threshold;
+  dp.set_free = m->params.tsdf_set_free_distance_on_decayed;
+  dp.free_distance = m->params.tsdf_decayed_free_distance_vox * mp.voxel_size;
+  dp.deallocate = m->params.deallocate_decayed_blocks;
+  const int grid = std::max(1, (int)std::min<long long>(persistent_grid(m, 8), std::max(1LL, (long long)mp.slot_capacity)));
+  LAUNCH(k_decay, grid, 256, 0, stream, mp.dev, dp);
+  if (dp.deallocate) {
+    LAUNCH(k_hash_clear, persistent_grid(m, 4), 256, 0, stream, mp.dev, 0);
+    LAUNCH(k_hash_reinsert, persistent_grid(m, 4), 256, 0, stream, mp.dev, 0);
+    LAUNCH(k_hash_rebuild_done, 1, 1, 0, stream, mp.dev);
+  }
+  return NVBX_OK;
+}
+
+int nvbx_decay(nvbx_mapper* m, int map_id, void* stream_v) {
+  if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper handle");
+  if (map_id < 0) {
+    for (int i = 0; i < (int)m->maps.size(); ++i) {
+      int rc = nvbx_decay(m, i, stream_v);
+      if (rc) return rc;
+    }
+    return NVBX_OK;
+  }
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  return decay_one(m, *m->maps[map_id], (cudaStream_t)stream_v);
+}
+
+int nvbx_clear(nvbx_mapper* m, int map_id, void* stream_v) {
+  if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper handle");
+  if (map_id < 0) {
+    for (int i = 0; i < (int)m->maps.size(); ++i) {
+      int rc = nvbx_clear(m, i, stream_v);
+      if (rc) return rc;
+    }
+    return NVBX_OK;
+  }
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  Map& mp = *m->maps[map_id];
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  LAUNCH(k_clear_all, persistent_grid(m, 4), 256, 0, stream, mp.dev);
+  mp.slot_used_ub = 0;
+  mp.feat_used_ub = 0;
+  mp.mesh_nv = 0;
+  mp.mesh_nt = 0;
+  // NOTE: the viewpoint caches and the to-update tracker survive, as in the reference
+  // (py_mapper.cu:286-306 clears the layers only).
+  return NVBX_OK;
+}
+
+// ---- mesh ----------------------------------------------------------------------------------------
+static int update_mesh_one(nvbx_mapper* m, Map& mp, cudaStream_t stream) {
+  int rc;
+  const size_t cap = (size_t)mp.slot_capacity;
+  if ((rc = mp.cnt_v.ensure(cap, stream))) return rc;
+  if ((rc = mp.cnt_t.ensure(cap, stream))) return rc;
+  if ((rc = mp.off_v.ensure(cap, stream))) return rc;
+  if ((rc = mp.off_t.ensure(cap, stream))) return rc;
+  MeshParams mpar;
+  mpar.min_weight = m->params.mesh_min_weight;
+  mpar.cutoff = m->params.mesh_cutoff_distance_vox * mp.voxel_size;
+  mpar.weld = m->params.mesh_weld_vertices;
+  const int grid = persistent_grid(m, 2);
+  LAUNCH(k_mesh_count, grid, 512, sizeof(MeshSmem), stream, mp.dev, mpar, mp.cnt_v.p, mp.cnt_t.p);
+  LAUNCH(k_mesh_scan, 1, 1024, 0, stream, mp.dev, mp.cnt_v.p, mp.cnt_t.p, mp.off_v.p, mp.off_t.p);
+  if ((rc = read_ctrl(mp, stream))) return rc;  // the one synchronisation of the export path
+  const long long nv = mp.h_ctrl->mesh_total_v, nt = mp.h_ctrl->mesh_total_t;
+  mp.slot_used_ub = (long long)mp.h_ctrl->slot_high - mp.h_ctrl->slot_free_top;  // free refresh of the bounds
+  mp.feat_used_ub = (long long)mp.h_ctrl->feat_high - mp.h_ctrl->feat_free_top;
+  const int nxt = mp.arena_cur ^ 1;
+  if ((rc = mp.arena_v[nxt].ensure((size_t)std::max(1LL, nv) * 3, stream))) return rc;
+  if ((rc = mp.arena_f[nxt].ensure((size_t)std::max(1LL, nv) * m->C, stream))) return rc;
+  if ((rc = mp.arena_t[nxt].ensure((size_t)std::max(1LL, nt), stream))) return rc;
+  MeshArena prev{mp.arena_v[mp.arena_cur].p, mp.arena_f[mp.arena_cur].p, mp.arena_t[mp.arena_cur].p};
+  MeshArena out{mp.arena_v[nxt].p, mp.arena_f[nxt].p, mp.arena_t[nxt].p};
+  LAUNCH(k_mesh_emit, grid, 512, sizeof(MeshSmem), stream, mp.dev, mpar, mp.off_v.p, mp.off_t.p, prev, out);
+  mp.arena_cur = nxt;
+  mp.mesh_nv = nv;
+  mp.mesh_nt = nt;
+  return NVBX_OK;
+}
+
+int nvbx_update_feature_mesh(nvbx_mapper* m, int map_id, void* stream_v) {
+  if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper handle");
+  if (map_id < 0) {
+    for (int i = 0; i < (int)m->maps.size(); ++i) {
+      int rc = nvbx_update_feature_mesh(m, i, stream_v);
+      if (rc) return rc;
+    }
+    return NVBX_OK;
+  }
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  return update_mesh_one(m, *m->maps[map_id], (cudaStream_t)stream_v);
+}
+
+int nvbx_get_feature_mesh(nvbx_mapper* m, int map_id, const void** vertices, const void** features,
+                          const void** triangles, int64_t* n_vertices, int64_t* n_triangles) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  Map& mp = *m->maps[map_id];
+  if (vertices) *vertices = mp.arena_v[mp.arena_cur].p;
+  if (features) *features = mp.arena_f[mp.arena_cur].p;
+  if (triangles) *triangles = mp.arena_t[mp.arena_cur].p;
+  if (n_vertices) *n_vertices = mp.mesh_nv;
+  if (n_triangles) *n_triangles = mp.mesh_nt / 3;
+  return NVBX_OK;
+}
+
+// ---- layer views ---------------------------------------------------------------------------------
+int64_t nvbx_num_blocks(nvbx_mapper* m, int map_id, int layer, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  Map& mp = *m->maps[map_id];
+  if ((rc = read_ctrl(mp, (cudaStream_t)stream_v))) return rc;
+  return layer == NVBX_LAYER_TSDF ? mp.h_ctrl->n_tsdf : mp.h_ctrl->n_feat;
+}
+int64_t nvbx_num_allocated_blocks(nvbx_mapper* m, int map_id, int layer, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  (void)stream_v;
+  Map& mp = *m->maps[map_id];
+  return layer == NVBX_LAYER_TSDF ? mp.slot_capacity : mp.feat_capacity;
+}
+int64_t nvbx_num_allocated_bytes(nvbx_mapper* m, int map_id, int layer, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  (void)stream_v;
+  Map& mp = *m->maps[map_id];
+  if (layer == NVBX_LAYER_TSDF) return (int64_t)mp.slot_capacity * kVoxelsPerBlock * (int64_t)sizeof(float2);
+  return (int64_t)mp.feat_capacity * kVoxelsPerBlock * (int64_t)mp.dev.row * (int64_t)sizeof(__half);
+}
+
+int64_t nvbx_get_block_indices(nvbx_mapper* m, int map_id, int layer, int32_t* out_xyz, int64_t capacity,
+                               void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  Map& mp = *m->maps[map_id];
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if ((rc = mp.idx_out.ensure((size_t)mp.slot_capacity, stream))) return rc;
+  CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->list_count, 0, sizeof(int), stream));
+  LAUNCH(k_collect_block_indices, persistent_grid(m, 4), 256, 0, stream, mp.dev,
+         (uint8_t)(layer == NVBX_LAYER_TSDF ? kLayerTsdfBit : kLayerFeatBit), mp.idx_out.p, mp.slot_capacity);
+  if ((rc = read_ctrl(mp, stream))) return rc;
+  const int64_t n = mp.h_ctrl->list_count;
+  if (out_xyz && capacity > 0) {
+    const int64_t c = std::min(n, capacity);
+    CUDA_TRY(cudaMemcpyAsync(out_xyz, mp.idx_out.p, (size_t)c * sizeof(int3), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+  }
+  return n;
+}
+
+int nvbx_get_block_ptr(nvbx_mapper* m, int map_id, int layer, int x, int y, int z, void** ptr,
+                       int64_t* voxel_stride_elems, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (!ptr) return fail(NVBX_ERR_INVALID_ARGUMENT, "ptr is null");
+  Map& mp = *m->maps[map_id];
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  LAUNCH(k_find_one, 1, 1, 0, stream, mp.dev, x, y, z, layer, mp.d_tmp_ptr);
+  unsigned long long h = 0;
+  CUDA_TRY(cudaMemcpyAsync(&h, mp.d_tmp_ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  *ptr = (void*)h;
+  if (voxel_stride_elems) *voxel_stride_elems = layer == NVBX_LAYER_TSDF ? 2 : mp.dev.row;
+  if (!h) return fail(NVBX_ERR_NOT_FOUND, "block (%d, %d, %d) is not allocated", x, y, z);
+  return NVBX_OK;
+}
+
+int nvbx_allocate_block(nvbx_mapper* m, int map_id, int layer, int x, int y, int z, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (!key_in_range(x, y, z)) return fail(NVBX_ERR_INVALID_ARGUMENT, "block index out of range");
+  Map& mp = *m->maps[map_id];
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if ((rc = ensure_slots(m, mp, 1, stream))) return rc;
+  if (layer != NVBX_LAYER_TSDF) {
+    // a stand-alone feature block: capacity is bounded by slots, so size it directly
+    if (mp.feat_used_ub + 1 > mp.feat_capacity)
+      if ((rc = grow_feats(m, mp, mp.feat_capacity + (1 << kFeatSlabShift), stream))) return rc;
+    mp.feat_used_ub += 1;
+  }
+  LAUNCH(k_allocate_one, 1, 1, 0, stream, mp.dev, x, y, z, layer, mp.d_tmp_int);
+  if (layer != NVBX_LAYER_TSDF) LAUNCH(k_zero_one_feature_block, 64, 256, 0, stream, mp.dev, mp.d_tmp_int);
+  return NVBX_OK;
+}
+
+// ---- queries -------------------------------------------------------------------------------------
+int nvbx_query_tsdf(nvbx_mapper* m, int map_id, const void* xyz, int64_t n, void* out, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!xyz || !out))) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad query buffers");
+  if (n == 0) return NVBX_OK;
+  Map& mp = *m->maps[map_id];
+  LAUNCH(k_query_tsdf, (unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream_v, mp.dev, (const float*)xyz,
+         (long long)n, (float2*)out);
+  return NVBX_OK;
+}
+int nvbx_query_features(nvbx_mapper* m, int map_id, const void* xyz, int64_t n, void* out, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (n < 0 || (n > 0 && (!xyz || !out))) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad query buffers");
+  if (n == 0) return NVBX_OK;
+  Map& mp = *m->maps[map_id];
+  LAUNCH(k_query_features, (unsigned)((n * 32 + 127) / 128), 128, 0, (cudaStream_t)stream_v, mp.dev,
+         (const float*)xyz, (long long)n, (__half*)out);
+  return NVBX_OK;
+}
+
+// ---- accounting ----------------------------------------------------------------------------------
+int nvbx_get_counters(nvbx_mapper* m, int map_id, nvbx_counters* out, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (!out) return fail(NVBX_ERR_INVALID_ARGUMENT, "out is null");
+  Map& mp = *m->maps[map_id];
+  if ((rc = read_ctrl(mp, (cudaStream_t)stream_v))) return rc;
+  const unsigned long long* c = mp.h_ctrl->counters;
+  std::memset(out, 0, sizeof(*out));
+  out->depth_frames = (int64_t)c[kCntDepthFrames];
+  out->feature_frames = (int64_t)c[kCntFeatureFrames];
+  out->tsdf_blocks_in_view = (int64_t)c[kCntTsdfBlocksInView];
+  out->tsdf_voxels_updated = (int64_t)c[kCntTsdfVoxelsUpdated];
+  out->tsdf_blocks_allocated = (int64_t)c[kCntTsdfBlocksAllocated];
+  out->feature_candidate_blocks = (int64_t)c[kCntFeatCandidateBlocks];
+  out->feature_band_blocks = (int64_t)c[kCntFeatBandBlocks];
+  out->feature_voxels_updated = (int64_t)c[kCntFeatVoxelsUpdated];
+  out->feature_blocks_allocated = (int64_t)c[kCntFeatBlocksAllocated];
+  out->blocks_deallocated = (int64_t)c[kCntBlocksDeallocated];
+  out->mesh_blocks_remeshed = (int64_t)c[kCntMeshBlocksRemeshed];
+  out->mesh_vertices = (int64_t)c[kCntMeshVertices];
+  return NVBX_OK;
+}
+int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  Map& mp = *m->maps[map_id];
+  CUDA_TRY(cudaMemsetAsync(mp.d_ctrl->counters, 0, sizeof(unsigned long long) * kCntNum, (cudaStream_t)stream_v));
+  return NVBX_OK;
+}
+
+int64_t nvbx_debug_last_block_list(nvbx_mapper* m, int map_id, int which, int32_t* out_xyz, int64_t capacity,
+                                   void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  Map& mp = *m->maps[map_id];
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (which == 0) {
+    if (!mp.last_depth_entry) return 0;
+    int n = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n, mp.last_depth_entry->d_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (out_xyz && capacity > 0) {
+      CUDA_TRY(cudaMemcpyAsync(out_xyz, mp.last_depth_entry->idx.p, (size_t)std::min<int64_t>(n, capacity) * sizeof(int3),
+                               cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    return n;
+  }
+  if (!mp.have_band_list) return 0;
+  if ((rc = read_ctrl(mp, stream))) return rc;
+  const int n = mp.h_ctrl->band_count;
+  if (out_xyz && capacity > 0 && n > 0) {
+    std::vector<int> slots((size_t)n);
+    CUDA_TRY(cudaMemcpyAsync(slots.data(), mp.band_slots.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    std::vector<int3> all((size_t)mp.slot_capacity);
+    CUDA_TRY(cudaMemcpyAsync(all.data(), mp.dev.blk_index, all.size() * sizeof(int3), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    for (int64_t i = 0; i < std::min<int64_t>(n, capacity); ++i) {
+      out_xyz[3 * i] = all[slots[i]].x;
+      out_xyz[3 * i + 1] = all[slots[i]].y;
+      out_xyz[3 * i + 2] = all[slots[i]].z;
+    }
+  }
+  return n;
+}
+
+int nvbx_debug_last_synthetic_depth(nvbx_mapper* m, int map_id, const void** ptr, int* rows, int* cols) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  Map& mp = *m->maps[map_id];
+  if (ptr) *ptr = mp.synth.p;
+  if (rows) *rows = mp.synth_rows;
+  if (cols) *cols = mp.synth_cols;
+  return NVBX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,191 @@
+// nvbx_map.cuh -- device-resident sparse map store.
+//
+// Replaces the reference's CPU std::unordered_map<Index3D, unified_ptr<Block>> master + stdgpu mirror +
+// one cudaMallocAsync per block (NB/include/nvblox/map/internal/impl/layer_impl.h:106-305,
+// block_memory_pool_impl.h:22-73, gpu_hash/internal/cuda/impl/gpu_layer_view_impl.cuh:36-174) with ONE
+// structure that lives in HBM and is only ever touched by kernels:
+//
+//   * an open-addressing hash (64-bit packed key -> 32-bit slot), linear probing, load <= 0.25, no
+//     tombstones (the table is rebuilt from the slot table after a decay that freed blocks);
+//   * a slot table (struct-of-arrays): block index, layer bits, feature-slot id, mesh-dirty flag and the
+//     block's extent in the current mesh arena;
+//   * slab arenas for voxel payloads: TSDF float2[512] per slot (slot id == payload id), feature
+//     fp16[512][C+8] per feature slot; slabs are appended, never moved, so block views stay valid;
+//   * free-list stacks + high-water marks for both payload kinds, all driven by atomics on the device.
+//
+// Nothing here needs the host in steady state: allocation, lookup, release all happen inside kernels.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "nvbx_math.cuh"
+
+namespace nvbx {
+
+constexpr int kVoxelsPerBlock = 512;
+constexpr int kTsdfSlabShift = 10;  // 1024 blocks  (4 MiB) per TSDF slab
+constexpr int kFeatSlabShift = 4;   // 16 blocks (12.1 MiB at C=768) per feature slab
+constexpr int kMaxSlabs = 1 << 15;
+constexpr unsigned long long kEmptyKey = ~0ull;
+
+constexpr uint8_t kLayerTsdfBit = 1;
+constexpr uint8_t kLayerFeatBit = 2;
+
+// counter slots (unsigned long long each) -- mirror nvbx_counters
+enum CounterId {
+  kCntDepthFrames = 0,
+  kCntFeatureFrames,
+  kCntTsdfBlocksInView,
+  kCntTsdfVoxelsUpdated,
+  kCntTsdfBlocksAllocated,
+  kCntFeatCandidateBlocks,
+  kCntFeatBandBlocks,
+  kCntFeatVoxelsUpdated,
+  kCntFeatBlocksAllocated,
+  kCntBlocksDeallocated,
+  kCntMeshBlocksRemeshed,
+  kCntMeshVertices,
+  kCntNum = 16
+};
+
+// Device-side control block (one per map).
+struct Ctrl {
+  int slot_free_top;   // number of entries on the slot free stack
+  int slot_high;       // slots [0, slot_high) have been handed out at least once
+  int feat_free_top;
+  int feat_high;
+  int n_tsdf;          // live blocks per layer
+  int n_feat;
+  int overflow;        // set when a pool ran dry (host sizing bug -- reported as an error)
+  int rebuild;         // hash must be rebuilt (blocks were released)
+  int view_count;      // length of the current TSDF view list
+  int cand_count;      // length of the feature candidate list
+  int band_count;      // length of the feature band list
+  int newfeat_count;   // feature blocks allocated this frame (to be zero-filled)
+  int list_count;      // generic compaction counter (block index export)
+  int mesh_total_v;    // totals of the mesh being built
+  int mesh_total_t;
+  int pad;
+  unsigned long long counters[kCntNum];
+};
+
+struct MapDev {
+  // hash
+  unsigned long long* keys;
+  int* vals;
+  unsigned int hash_mask;
+  // slot table
+  int3* blk_index;
+  uint8_t* blk_layers;
+  int* blk_feat;
+  uint8_t* blk_dirty;
+  int4* blk_mesh;  // (vertex offset, vertex count, triangle-index offset, triangle-index count)
+  int slot_capacity;
+  int feat_capacity;
+  // payload arenas
+  float2* const* tsdf_slabs;
+  __half* const* feat_slabs;
+  // free lists
+  int* slot_free;
+  int* feat_free;
+  Ctrl* ctrl;
+  // geometry / layout
+  float block_size;
+  float voxel_size;
+  float voxel_size_inv;
+  int C;    // feature channels
+  int row;  // halves per feature voxel row (C + 8)
+};
+
+__device__ __forceinline__ float2* tsdf_block(const MapDev& m, int slot) {
+  return m.tsdf_slabs[slot >> kTsdfSlabShift] + (size_t)(slot & ((1 << kTsdfSlabShift) - 1)) * kVoxelsPerBlock;
+}
+__device__ __forceinline__ __half* feat_block(const MapDev& m, int fslot) {
+  return m.feat_slabs[fslot >> kFeatSlabShift] +
+         (size_t)(fslot & ((1 << kFeatSlabShift) - 1)) * (size_t)kVoxelsPerBlock * (size_t)m.row;
+}
+
+__host__ __device__ __forceinline__ bool key_in_range(int x, int y, int z) {
+  const int lim = 1 << 20;
+  return x >= -lim && x < lim && y >= -lim && y < lim && z >= -lim && z < lim;
+}
+__host__ __device__ __forceinline__ unsigned long long pack_key(int x, int y, int z) {
+  const unsigned long long bx = (unsigned long long)(unsigned)(x + (1 << 20)) & 0x1fffffull;
+  const unsigned long long by = (unsigned long long)(unsigned)(y + (1 << 20)) & 0x1fffffull;
+  const unsigned long long bz = (unsigned long long)(unsigned)(z + (1 << 20)) & 0x1fffffull;
+  return (bx << 42) | (by << 21) | bz;
+}
+__host__ __device__ __forceinline__ unsigned int mix_key(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (unsigned int)k;
+}
+
+__device__ __forceinline__ int hash_find(const MapDev& m, int x, int y, int z) {
+  if (!key_in_range(x, y, z)) return -1;
+  const unsigned long long key = pack_key(x, y, z);
+  unsigned int h = mix_key(key) & m.hash_mask;
+  while (true) {
+    const unsigned long long k = m.keys[h];
+    if (k == key) return m.vals[h];
+    if (k == kEmptyKey) return -1;
+    h = (h + 1) & m.hash_mask;
+  }
+}
+// Insert a key known to be absent and inserted by exactly one thread.
+__device__ __forceinline__ void hash_insert(const MapDev& m, int x, int y, int z, int slot) {
+  const unsigned long long key = pack_key(x, y, z);
+  unsigned int h = mix_key(key) & m.hash_mask;
+  while (true) {
+    const unsigned long long prev = atomicCAS(&m.keys[h], kEmptyKey, key);
+    if (prev == kEmptyKey) {
+      m.vals[h] = slot;
+      return;
+    }
+    h = (h + 1) & m.hash_mask;
+  }
+}
+
+// Pop a slot id: recycled ids first, then fresh ones.  Returns -1 (and raises ctrl->overflow) when the
+// arena is exhausted -- the host sizes arenas before every launch so this is an internal error.
+__device__ __forceinline__ int pop_id(int* free_top, int* high, const int* free_stack, int capacity, int* overflow) {
+  const int top = atomicSub(free_top, 1);
+  if (top > 0) return free_stack[top - 1];
+  atomicAdd(free_top, 1);
+  const int id = atomicAdd(high, 1);
+  if (id >= capacity) {
+    atomicAdd(high, -1);
+    atomicExch(overflow, 1);
+    return -1;
+  }
+  return id;
+}
+__device__ __forceinline__ void push_id(int* free_top, int* free_stack, int id) {
+  const int top = atomicAdd(free_top, 1);
+  free_stack[top] = id;
+}
+
+// Find-or-create the slot of a block index and make sure the TSDF layer bit is set.  The caller
+// guarantees that no other thread handles the same index concurrently.  *created_tsdf tells the caller
+// to zero the TSDF payload.
+__device__ __forceinline__ int acquire_slot(const MapDev& m, int x, int y, int z, bool* is_new_slot) {
+  *is_new_slot = false;
+  if (!key_in_range(x, y, z)) return -1;  // |index| >= 2^20 blocks: outside the packed-key range
+  int slot = hash_find(m, x, y, z);
+  if (slot >= 0) return slot;
+  slot = pop_id(&m.ctrl->slot_free_top, &m.ctrl->slot_high, m.slot_free, m.slot_capacity, &m.ctrl->overflow);
+  if (slot < 0) return -1;
+  m.blk_index[slot] = make_int3(x, y, z);
+  m.blk_layers[slot] = 0;
+  m.blk_feat[slot] = -1;
+  m.blk_dirty[slot] = 0;
+  m.blk_mesh[slot] = make_int4(0, 0, 0, 0);
+  hash_insert(m, x, y, z, slot);
+  *is_new_slot = true;
+  return slot;
+}
+
+}  // namespace nvbx

@@ -1,0 +1,302 @@
+"""`Mapper`: the surface mindmap/mapping calls (reference: nvblox_torch/mapper.py:34-490).
+
+Same constructor, method names, argument order, assertions and error behaviour as the reference
+wrapper; every method forwards to one C-ABI entry point of libnvbx.so (include/nvbx_c_api.h), passing
+`tensor.data_ptr()` and torch's current CUDA stream, so image tensors cross zero-copy and all kernels
+run stream-ordered with the caller's torch work.  There is no CPU fallback: constructing a Mapper
+without a Blackwell GPU raises.
+"""
+import ctypes as C
+from enum import Enum
+from typing import List, Optional
+
+import torch
+
+from nvblox_mindmap_b200 import _capi
+from nvblox_mindmap_b200.params import NvbxCounters
+from nvblox_mindmap_b200.torch_interop import current_stream_ptr, device_view
+from nvblox_torch.constants import constants
+from nvblox_torch.layer import ColorLayer, FeatureLayer, TsdfLayer
+from nvblox_torch.mapper_params import MapperParams
+from nvblox_torch.mesh import ColorMesh, FeatureMesh
+from nvblox_torch.projective_integrator_types import ProjectiveIntegratorType
+
+
+class QueryType(Enum):
+    """Enum used when querying layers."""
+    TSDF = 'tsdf'
+    FEATURE = 'feature'
+    OCCUPANCY = 'occupancy'
+    ESDF = 'esdf'
+    ESDF_GRAD = 'esdf_with_gradients'
+    COLOR = 'color'
+
+
+def _pose16(t_w_c: torch.Tensor):
+    return (C.c_float * 16)(*t_w_c.reshape(-1).tolist())
+
+
+class Mapper:
+    """Accumulates depth (+ feature) frames into voxel-block-hashed TSDF / feature maps on one GPU.
+
+    Several independent maps (`mapper_id`) can live in one Mapper, e.g. static / dynamic
+    (mindmap/mapping/helpers/nvblox_mapping_helpers.py:72-76).  `mapper_id = -1` addresses all maps
+    where the reference allows it.
+    """
+
+    def __init__(self,
+                 voxel_sizes_m,
+                 integrator_types=ProjectiveIntegratorType.TSDF,
+                 mapper_parameters: Optional[MapperParams] = None,
+                 device: Optional[int] = None) -> None:
+        voxel_sizes = [voxel_sizes_m] if isinstance(voxel_sizes_m, (float, int)) else list(voxel_sizes_m)
+        if isinstance(integrator_types, ProjectiveIntegratorType):
+            integrator_types = [integrator_types] * len(voxel_sizes)
+        assert len(voxel_sizes) == len(integrator_types)
+        for t in integrator_types:
+            if t != ProjectiveIntegratorType.TSDF:
+                raise NotImplementedError('only TSDF maps are on the accelerated path (SURVEY.md 2.3)')
+        self._params = MapperParams(mapper_parameters) if mapper_parameters is not None else MapperParams()
+        self._voxel_sizes = [float(v) for v in voxel_sizes]
+        self._integrator_types = list(integrator_types)
+        self._feature_channels = constants.feature_array_num_elements()
+        if not torch.cuda.is_available():
+            raise RuntimeError('nvblox_torch (B200 back end) needs a CUDA device: there is no CPU fallback')
+        self._device = torch.cuda.current_device() if device is None else int(device)
+        self._lib = _capi.load()
+        nv = self._params.to_nvbx()
+        sizes = (C.c_float * len(voxel_sizes))(*self._voxel_sizes)
+        handle = C.c_void_p()
+        _capi.check(self._lib.nvbx_create(len(voxel_sizes), sizes, C.byref(nv), self._feature_channels, self._device,
+                                          C.byref(handle)))
+        self._handle = handle
+
+    def __del__(self):
+        h = getattr(self, '_handle', None)
+        if h:
+            try:
+                self._lib.nvbx_destroy(h)
+            except Exception:    # interpreter shutdown
+                pass
+            self._handle = None
+
+    # -- helpers ----------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return current_stream_ptr(self._device)
+
+    @staticmethod
+    def _mask_ptr(mask_frame: Optional[torch.Tensor], image: torch.Tensor) -> Optional[int]:
+        if mask_frame is None:
+            return None
+        # py_mapper.cu:90-99: not-on-GPU / size mismatch are logged and the frame is skipped there;
+        # here they raise (ALL_ON_GPU_OR_RETURN, checkImageDimensionsEqual).
+        assert mask_frame.is_cuda, 'Mask frame should be on device.'
+        assert mask_frame.dtype == torch.uint8, 'Mask frame should have type torch.uint8.'
+        assert mask_frame.shape[0] == image.shape[0] and mask_frame.shape[1] == image.shape[1], \
+            'Mask frame size should match the image.'
+        if not mask_frame.is_contiguous():
+            mask_frame = mask_frame.contiguous()
+        return mask_frame.data_ptr()
+
+    def params(self) -> MapperParams:
+        return MapperParams(self._params)
+
+    # -- frame integration --------------------------------------------------------------------------------
+    def add_depth_frame(self,
+                        depth_frame: torch.Tensor,
+                        t_w_c: torch.Tensor,
+                        intrinsics: torch.Tensor,
+                        mask_frame: Optional[torch.Tensor] = None,
+                        mapper_id: int = 0) -> None:
+        """Integrate a (H, W) float32 CUDA depth frame; t_w_c (4,4) and intrinsics (3,3) are CPU tensors."""
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        check_integrator_inputs(depth_frame, t_w_c, intrinsics, 'Depth', 2, torch.float32)
+        depth_frame = depth_frame if depth_frame.is_contiguous() else depth_frame.contiguous()
+        mask_ptr = self._mask_ptr(mask_frame, depth_frame)
+        k = intrinsics
+        _capi.check(self._lib.nvbx_integrate_depth(
+            self._handle, mapper_id, depth_frame.data_ptr(), depth_frame.shape[0], depth_frame.shape[1], mask_ptr,
+            _pose16(t_w_c), float(k[0, 0]), float(k[1, 1]), float(k[0, 2]), float(k[1, 2]), self._stream()))
+
+    def add_color_frame(self,
+                        color_frame: torch.Tensor,
+                        t_w_c: torch.Tensor,
+                        intrinsics: torch.Tensor,
+                        mask_frame: Optional[torch.Tensor] = None,
+                        mapper_id: int = 0) -> None:
+        """(H, W, 3) uint8 colour frame.  Validated and ignored in this round."""
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        check_integrator_inputs(color_frame, t_w_c, intrinsics, 'Color', 3, torch.uint8, 3)
+        mask_ptr = self._mask_ptr(mask_frame, color_frame)
+        k = intrinsics
+        _capi.check(self._lib.nvbx_integrate_color(
+            self._handle, mapper_id, color_frame.data_ptr(), color_frame.shape[0], color_frame.shape[1], mask_ptr,
+            _pose16(t_w_c), float(k[0, 0]), float(k[1, 1]), float(k[0, 2]), float(k[1, 2]), self._stream()))
+
+    def add_feature_frame(self,
+                          feature_frame: torch.Tensor,
+                          t_w_c: torch.Tensor,
+                          intrinsics: torch.Tensor,
+                          mask_frame: Optional[torch.Tensor] = None,
+                          mapper_id: int = 0) -> None:
+        """Integrate a (H, W, C) float16 CUDA feature frame, C == constants.feature_array_num_elements()."""
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        check_integrator_inputs(feature_frame, t_w_c, intrinsics, 'Feature', 3, torch.float16, self._feature_channels)
+        feature_frame = feature_frame if feature_frame.is_contiguous() else feature_frame.contiguous()
+        mask_ptr = self._mask_ptr(mask_frame, feature_frame)
+        k = intrinsics
+        _capi.check(self._lib.nvbx_integrate_features(
+            self._handle, mapper_id, feature_frame.data_ptr(), feature_frame.shape[0], feature_frame.shape[1],
+            feature_frame.shape[2], mask_ptr, _pose16(t_w_c), float(k[0, 0]), float(k[1, 1]), float(k[0, 2]),
+            float(k[1, 2]), self._stream()))
+
+    def integrate_frame_from_host(self, depth, features, t_w_c, intrinsics, depth_mask=None, feature_mask=None,
+                                  mapper_id: int = 0) -> None:
+        """(ours) depth + feature frame from HOST (ideally pinned) tensors; H2D copies ride the stream."""
+        assert depth.dtype == torch.float32 and features.dtype == torch.float16 and not depth.is_cuda
+        k = intrinsics
+        _capi.check(self._lib.nvbx_integrate_frame_host(
+            self._handle, mapper_id, depth.data_ptr(), features.data_ptr(), depth.shape[0], depth.shape[1],
+            features.shape[2], None if depth_mask is None else depth_mask.data_ptr(),
+            None if feature_mask is None else feature_mask.data_ptr(), _pose16(t_w_c), float(k[0, 0]), float(k[1, 1]),
+            float(k[0, 2]), float(k[1, 2]), self._stream()))
+
+    # -- map maintenance ------------------------------------------------------------------------------------
+    def decay(self, mapper_id: int = -1) -> None:
+        """Decay TSDF weights and release fully decayed blocks (with their feature / mesh blocks)."""
+        assert -1 <= mapper_id < len(self._voxel_sizes)
+        _capi.check(self._lib.nvbx_decay(self._handle, mapper_id, self._stream()))
+
+    def clear(self, mapper_id: int = -1) -> None:
+        assert -1 <= mapper_id < len(self._voxel_sizes)
+        _capi.check(self._lib.nvbx_clear(self._handle, mapper_id, self._stream()))
+
+    def update_esdf(self, mapper_id: int = -1) -> None:
+        raise NotImplementedError('ESDF is not on the accelerated path (SURVEY.md 2.3)')
+
+    def update_color_mesh(self, mapper_id: int = -1) -> None:
+        assert -1 <= mapper_id < len(self._voxel_sizes)    # no colour layer yet
+
+    def update_feature_mesh(self, mapper_id: int = -1) -> None:
+        """Re-mesh the blocks touched since the last update and refresh their vertex features."""
+        assert -1 <= mapper_id < len(self._voxel_sizes)
+        _capi.check(self._lib.nvbx_update_feature_mesh(self._handle, mapper_id, self._stream()))
+
+    def get_color_mesh(self, mapper_id: int = 0) -> ColorMesh:
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        return ColorMesh()
+
+    def get_feature_mesh(self, mapper_id: int = 0) -> FeatureMesh:
+        """Serialised feature mesh as zero-copy device views (no kernel, no copy)."""
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        v, f, t = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nv, nt = C.c_int64(), C.c_int64()
+        _capi.check(self._lib.nvbx_get_feature_mesh(self._handle, mapper_id, C.byref(v), C.byref(f), C.byref(t),
+                                                    C.byref(nv), C.byref(nt)))
+        c, d = self._feature_channels, self._device
+        return FeatureMesh(c_mesh={
+            'vertices': device_view(v.value, (nv.value, 3), torch.float32, d, owner=self),
+            'appearances': device_view(f.value, (nv.value, c), torch.float16, d, owner=self),
+            'triangles': device_view(t.value, (nt.value, 3), torch.int32, d, owner=self),
+        })
+
+    # -- layer views ------------------------------------------------------------------------------------------
+    def tsdf_layer_view(self, mapper_id: int = 0) -> TsdfLayer:
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        return TsdfLayer(voxel_size_m=self._voxel_sizes[mapper_id], c_layer=(self, mapper_id))
+
+    def feature_layer_view(self, mapper_id: int = 0) -> FeatureLayer:
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        return FeatureLayer(voxel_size_m=self._voxel_sizes[mapper_id], c_layer=(self, mapper_id))
+
+    def color_layer_view(self, mapper_id: int = 0) -> ColorLayer:
+        raise NotImplementedError('colour layer: SURVEY.md 8(f) N1 (next)')
+
+    def save_map(self, map_fname: str, mapper_id: int) -> None:
+        raise NotImplementedError('.nvblx serialisation: SURVEY.md 8(f) N3 (next)')
+
+    def load_from_file(self, filename: str, mapper_id: int) -> None:
+        raise NotImplementedError('.nvblx serialisation: SURVEY.md 8(f) N3 (next)')
+
+    def num_mappers(self) -> int:
+        return int(self._lib.nvbx_num_maps(self._handle))
+
+    # -- queries ------------------------------------------------------------------------------------------------
+    def _maybe_allocate(self, size, tensor=None, dtype=torch.float32, value=None) -> torch.Tensor:
+        if tensor is None:
+            dev = f'cuda:{self._device}'
+            return torch.zeros(size, dtype=dtype, device=dev) if value is None else \
+                torch.full(size, value, dtype=dtype, device=dev)
+        assert tuple(tensor.shape) == tuple(size), f'Expected preallocated size: {size}.'
+        return tensor
+
+    def query_layer(self,
+                    query_type: QueryType,
+                    query: torch.Tensor,
+                    output: Optional[torch.Tensor] = None,
+                    mapper_id: int = -1) -> torch.Tensor:
+        """Look up N positions: TSDF -> [N,2] (distance, weight); FEATURE -> [N,C+1] fp16 (features, weight).
+
+        Rows whose position falls in no allocated block keep the pre-filled value (zeros).
+        """
+        assert -1 <= mapper_id < len(self._voxel_sizes)
+        num_queries = query.shape[0]
+        ok = query.is_cuda and query.dtype == torch.float32 and query.dim() == 2 and query.shape[1] == 3
+        if query_type == QueryType.TSDF:
+            output = self._maybe_allocate((num_queries, TsdfLayer.num_elements_per_voxel()), output)
+            if mapper_id == -1:
+                raise NotImplementedError('multi-mapper TSDF query is not on the accelerated path')
+            if not (ok and output.is_cuda and output.dtype == torch.float32):
+                raise ValueError(f'Query failed for: {query_type}')
+            q = query if query.is_contiguous() else query.contiguous()
+            assert output.is_contiguous()
+            _capi.check(self._lib.nvbx_query_tsdf(self._handle, mapper_id, q.data_ptr(), num_queries,
+                                                  output.data_ptr(), self._stream()))
+            return output
+        if query_type == QueryType.FEATURE:
+            output = self._maybe_allocate((num_queries, self._feature_channels + 1), output, dtype=torch.float16)
+            assert mapper_id >= 0, 'Only single mapper query is supported for features'
+            if not (ok and output.is_cuda and output.dtype == torch.float16):
+                raise ValueError(f'Query failed for: {query_type}')
+            q = query if query.is_contiguous() else query.contiguous()
+            assert output.is_contiguous()
+            _capi.check(self._lib.nvbx_query_features(self._handle, mapper_id, q.data_ptr(), num_queries,
+                                                      output.data_ptr(), self._stream()))
+            return output
+        raise NotImplementedError(f'Query type {query_type} not implemented')
+
+    # -- accounting (ours) ----------------------------------------------------------------------------------------
+    def counters(self, mapper_id: int = 0) -> dict:
+        """Device-side work counters that define the algorithmic bytes."""
+        c = NvbxCounters()
+        _capi.check(self._lib.nvbx_get_counters(self._handle, mapper_id, C.byref(c), self._stream()))
+        return c.as_dict()
+
+    def reset_counters(self, mapper_id: int = 0) -> None:
+        _capi.check(self._lib.nvbx_reset_counters(self._handle, mapper_id, self._stream()))
+
+    def print_timing(self) -> str:
+        from nvblox_torch.timer import timer_status_string
+        return timer_status_string()
+
+
+def check_integrator_inputs(image: torch.Tensor,
+                            t_w_c: torch.Tensor,
+                            intrinsics: torch.Tensor,
+                            image_type: str,
+                            expected_dim: int,
+                            expected_type: torch.dtype,
+                            expected_num_channels: Optional[int] = None) -> None:
+    """Input contract of the integrators (reference mapper.py:458-490): violations raise AssertionError."""
+    assert image.dim() == expected_dim, f'{image_type} image should have dim == {expected_dim}.'
+    assert image.is_cuda, f'{image_type} image should be on device.'
+    assert image.dtype == expected_type, f'{image_type} image should have type {expected_type}.'
+    assert intrinsics.is_cpu, f'{image_type} intrinsics should be on the CPU.'
+    assert intrinsics.dtype == torch.float32, f'{image_type} intrinsics should have type torch.float32.'
+    assert t_w_c.is_cpu, f'{image_type} t_w_c  should be on the CPU.'
+    assert t_w_c.dtype == torch.float32, f'{image_type} pose should have type torch.float32.'
+    assert tuple(t_w_c.shape) == (4, 4) and tuple(intrinsics.shape) == (3, 3), \
+        f'{image_type}: pose must be 4x4 and intrinsics 3x3.'
+    if expected_num_channels:
+        assert image.shape[2] == expected_num_channels, \
+            f'{image_type} should have {expected_num_channels} channels.'

@@ -1,0 +1,125 @@
+"""GPU parity tests: the CUDA path (through the nvblox_torch surface -> C ABI) against the CPU oracle on
+identical seeded inputs.  Bars (BASELINE.json north_star): allocated block sets and extracted voxel
+indices bit-exact; TSDF distance/weight within 1e-5 relative (we assert bit-exact, which is stronger and
+holds because both sides use the uncontracted IEEE operation sequence); features within 1 fp16 ulp (we
+assert bit-exact for the default non-fused arithmetic)."""
+import numpy as np
+import pytest
+
+from tests import scenes as S
+from tests.parity_utils import Pair, make_params, orbit_frames
+
+pytestmark = pytest.mark.gpu
+
+
+def test_single_frame_plumbing():
+    """BASELINE configs[0] scaled down: one synthetic depth + feature frame into a 2 cm map."""
+    mp, op = make_params(workspace=S.WS_CUBE_STACKING)
+    pair = Pair(0.02, 64, mp, op)
+    K = S.intrinsics(128, 128)
+    T = S.look_at((0.35, 0.0, 0.9), (0.35, 0.0, 0.0), up=(1, 0, 0))
+    depth = S.render_depth(K, 128, 128, T, **S.S_TABLE)
+    pair.depth(depth, T, K)
+    g, c = pair.last_block_list(0)
+    assert np.array_equal(g, c) and len(g) > 0
+    assert pair.check_tsdf() > 0
+    feat = S.feature_frame(128, 128, 64, 7)
+    pair.features(feat, T, K)
+    g, c = pair.last_block_list(1)
+    assert np.array_equal(g, c) and len(g) > 0
+    gs, cs = pair.synthetic_depth()
+    assert np.array_equal(gs.view(np.uint32), cs.view(np.uint32))
+    assert pair.check_features() > 0
+    assert pair.check_mesh() > 0
+    gc, cc = pair.gpu.counters(0), pair.cpu.counters()
+    for k in ('tsdf_voxels_updated', 'feature_voxels_updated', 'feature_band_blocks', 'feature_candidate_blocks',
+              'tsdf_blocks_allocated', 'feature_blocks_allocated', 'mesh_vertices'):
+        assert gc[k] == cc[k], (k, gc[k], cc[k])
+
+
+@pytest.mark.parametrize('alpha,strict', [(1.0, False), (1.0, True), (0.3, False)])
+def test_orbit_sequence(alpha, strict):
+    """Cube-stacking style replay: moving wrist camera, decay every step, mesh every second step."""
+    mp, op = make_params(workspace=S.WS_CUBE_STACKING, alpha=alpha, strict=strict)
+    pair = Pair(0.02, 32, mp, op)
+    for i, T, K, depth, feat in orbit_frames(6, 96, 96, 32, S.S_TABLE):
+        if i:
+            pair.decay()
+        pair.depth(depth, T, K)
+        pair.features(feat, T, K, mask=S.border_lower_half_mask(96, 96) if i % 3 == 2 else None)
+        pair.check_tsdf()
+        # alpha == 1 fast path differs from the reference arithmetic only in the sign of zero
+        pair.check_features(max_ulp=0 if (strict or alpha != 1.0) else 1)
+        if i % 2:
+            pair.check_mesh()
+    assert pair.check_mesh() > 0
+
+
+def test_c768_features_bit_exact():
+    """The benchmark feature length (vectorised 3-vectors-per-lane path)."""
+    mp, op = make_params(workspace=S.WS_CUBE_STACKING)
+    pair = Pair(0.02, 768, mp, op)
+    for i, T, K, depth, feat in orbit_frames(2, 64, 64, 768, S.S_SPHERE_SMALL):
+        pair.depth(depth, T, K)
+        pair.features(feat, T, K)
+    pair.check_tsdf()
+    assert pair.check_features(max_ulp=1) > 0
+    assert pair.check_mesh() > 0
+
+
+def test_decay_until_removed():
+    """test_tsdf_decay.cpp DecayUntilRemoved: repeated decay frees every block (and its feature block)."""
+    mp, op = make_params(workspace=S.WS_CUBE_STACKING, decay=0.5)
+    pair = Pair(0.02, 16, mp, op)
+    for i, T, K, depth, feat in orbit_frames(1, 64, 64, 16, S.S_TABLE):
+        pair.depth(depth, T, K)
+        pair.features(feat, T, K)
+    n0 = pair.check_tsdf()
+    assert n0 > 0
+    for _ in range(16):
+        pair.decay()
+        pair.check_tsdf()
+        pair.check_features(max_ulp=1)
+    assert pair.gpu.tsdf_layer_view(0).num_blocks() == 0 == pair.cpu.num_blocks(0)
+    assert pair.gpu.feature_layer_view(0).num_blocks() == 0
+    # the map is usable again after everything was released (slots recycled, hash rebuilt)
+    for i, T, K, depth, feat in orbit_frames(2, 64, 64, 16, S.S_TABLE, seed0=50):
+        pair.depth(depth, T, K)
+        pair.features(feat, T, K)
+    pair.check_tsdf()
+    pair.check_features(max_ulp=1)
+    pair.check_mesh()
+
+
+def test_viewpoint_cache_static_camera():
+    """Q6: a static camera re-uses the previous block list even though the depth image changed."""
+    mp, op = make_params(workspace=S.WS_CUBE_STACKING)
+    pair = Pair(0.02, 16, mp, op)
+    K = S.intrinsics(96, 96)
+    T = S.look_at((-0.2, 0.0, 0.6), (0.4, 0.0, 0.0))
+    d1 = S.render_depth(K, 96, 96, T, **S.S_TABLE)
+    d2 = S.render_depth(K, 96, 96, T, **S.S_SPHERE_SMALL)
+    pair.depth(d1, T, K)
+    l1 = pair.last_block_list(0)
+    pair.depth(d2, T, K)
+    l2 = pair.last_block_list(0)
+    assert np.array_equal(l1[0], l2[0]) and np.array_equal(l2[0], l2[1])
+    pair.features(S.feature_frame(96, 96, 16, 3), T, K)
+    pair.check_tsdf()
+    pair.check_features(max_ulp=1)
+    pair.clear()
+    pair.depth(d2, T, K)    # cache survives clear(): blocks are re-allocated from the cached list
+    pair.check_tsdf()
+    pair.check_mesh()
+
+
+def test_unbounded_workspace_and_subsampling():
+    """Reference defaults: no workspace box, raycast subsampling 4, 7 m range (arena growth path)."""
+    mp, op = make_params(workspace=None, max_dist=7.0, raycast_sub=4, alpha=0.8)
+    pair = Pair(0.05, 16, mp, op)
+    for i, T, K, depth, feat in orbit_frames(3, 96, 128, 16, S.S_TABLE, radius=1.5, height=1.2):
+        pair.depth(depth, T, K)
+        pair.features(feat, T, K)
+    assert pair.check_tsdf() > 0
+    assert pair.check_features() > 0
+    assert pair.check_mesh() > 0
