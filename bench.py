@@ -1,0 +1,349 @@
+#!/usr/bin/env python3
+"""bench.py -- feature frames integrated / s on the cube-stacking replay (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one camera frame: add_depth_frame + add_feature_frame
+(mindmap's integrate_frame minus colour, nvblox_mapping_helpers.py:207-261) of a 512x512 depth +
+768-channel fp16 feature frame into a 2 cm TSDF/feature map bounded by the cube-stacking workspace box,
+camera on a 64-pose wrist orbit (moves > 1 mm / 0.1 deg per frame, so the viewpoint cache never hits).
+
+  value     device-timed throughput with inputs resident in HBM (CUDA events on the launching stream).
+  e2e       the same metric through the public API with HOST (pinned) frames: the H2D copy of depth +
+            features and a D2H read of the map counters are inside the timed region of every step.
+  roofline  the dominant kernel (k_feature_integrate): algorithmic bytes per launch (SURVEY 8(d) formula,
+            N_upd from the device counters, distinct pixels per voxel from the oracle sample) over its
+            live CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline  the CPU oracle (a port of the reference algorithm, oracle/) timed on a bounded sample.
+
+With N > 1 (torchrun, one process per GPU) every rank integrates its own independent map replica; there
+is no collective on the data path, the timed region is bracketed by barriers and the
+slowest rank's time is used.  `--impl reference` times the reference's CPU algorithm (oracle port, all
+host threads) on rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tests import scenes as S  # noqa: E402
+
+H = W = 512
+C_FEAT = 768
+VOXEL = 0.02
+N_POSES = 64
+N_FEATURE_BUFFERS = 6          # distinct 384 MiB feature frames cycled through (>> L2)
+WORKLOAD = 'cube_stacking_replay: 1 wrist cam 512x512, C=768 fp16, 2 cm voxels, S-table scene, 64-pose orbit'
+
+
+def mapper_params():
+    from tests.parity_utils import make_params
+    return make_params(workspace=S.WS_CUBE_STACKING, max_dist=5.0, alpha=1.0, raycast_sub=1, decay=0.98)
+
+
+def poses_and_depths(n):
+    K = S.intrinsics(W, H)
+    out = []
+    for i in range(n):
+        T = S.orbit_pose(i % N_POSES, N_POSES)
+        out.append((T, S.render_depth(K, H, W, T, **S.S_TABLE)))
+    return K, out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(',')])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'),
+                                   r[2:6]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def oracle_sample(n_frames, threads):
+    """Time the CPU oracle on the first `n_frames` frames of the workload; also returns the per-voxel
+    distinct-pixel ratio that enters the algorithmic-bytes formula."""
+    from oracle import oracle as O
+    O.set_threads(threads)
+    _, op = mapper_params()
+    K, frames = poses_and_depths(n_frames)
+    m = O.OracleMapper(VOXEL, C_FEAT, op)
+    t_total, upd, pix, cand = 0.0, 0, 0, 0
+    for i, (T, depth) in enumerate(frames):
+        feat = S.feature_frame(H, W, C_FEAT, 1000 + i)
+        c0 = m.counters()
+        t0 = time.perf_counter()
+        m.add_depth_frame(depth, T, K)
+        m.add_feature_frame(feat, T, K)
+        t_total += time.perf_counter() - t0
+        c = m.counters()
+        upd += c['last_feature_voxels']
+        pix += c['last_distinct_pixels']
+        cand += c['feature_candidate_blocks'] - c0['feature_candidate_blocks']
+    return {'frames': n_frames, 'seconds': t_total, 'fps': n_frames / t_total, 'n_upd': upd, 'u_px': pix,
+            'n_cand': cand, 'threads': threads}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port) with all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    threads = len(os.sched_getaffinity(0))
+    O.set_threads(threads)
+    _, op = mapper_params()
+    K, frames = poses_and_depths(args.warmup + args.steps)
+    m = O.OracleMapper(VOXEL, C_FEAT, op)
+    feats = [S.feature_frame(H, W, C_FEAT, 1000 + i) for i in range(min(N_FEATURE_BUFFERS, len(frames)))]
+    t_timed = 0.0
+    for i, (T, depth) in enumerate(frames):
+        t0 = time.perf_counter()
+        m.add_depth_frame(depth, T, K)
+        m.add_feature_frame(feats[i % len(feats)], T, K)
+        if i >= args.warmup:
+            t_timed += time.perf_counter() - t0
+    value = args.steps / t_timed
+    line = {
+        'impl': 'reference', 'metric': 'feature frames integrated/s (C=768, 512^2)', 'value': value,
+        'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1000.0 * t_timed / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32 geometry + f16 features', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'voxel_size_m': VOXEL, 'workspace': 'cube_stacking box'},
+        'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
+                         'sample': f'{args.steps} frames of the workload after {args.warmup} warm-up frames; the '
+                                   'reference itself cannot be built offline (Eigen/stdgpu/glog absent), so this is '
+                                   'the oracle port of its algorithm with OpenMP over blocks'},
+        'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from nvblox_mindmap_b200 import _capi
+    from nvblox_torch.constants import constants
+    from nvblox_torch.mapper import Mapper
+
+    torch.cuda.set_device(local_rank)
+    dev = f'cuda:{local_rank}'
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    lib = _capi.load()
+    constants.set_feature_array_num_elements(C_FEAT)
+    mp, _ = mapper_params()
+    mapper = Mapper(voxel_sizes_m=VOXEL, mapper_parameters=mp, device=local_rank)
+
+    n_total = args.warmup + args.steps
+    K, frames = poses_and_depths(max(n_total, 1))
+    K_t = torch.from_numpy(K)
+    poses = [torch.from_numpy(T) for T, _ in frames]
+    depths = [torch.from_numpy(d).to(dev) for _, d in frames]
+    g = torch.Generator(device=dev)
+    feats = []
+    for i in range(N_FEATURE_BUFFERS):       # synthetic N(0,1) features, per-map seed = rank
+        g.manual_seed(1000 + i + 7919 * rank)
+        feats.append(torch.randn((H, W, C_FEAT), generator=g, device=dev, dtype=torch.float32).half())
+    torch.cuda.synchronize()
+
+    def step(i):
+        mapper.add_depth_frame(depths[i], poses[i], K_t)
+        mapper.add_feature_frame(feats[i % N_FEATURE_BUFFERS], poses[i], K_t)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-timed pass: inputs resident in HBM ------------------------------------------------
+    for i in range(args.warmup):
+        step(i)
+    mapper.reset_counters(0)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = int(lib.nvbx_kernel_launch_count())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.warmup, n_total):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(lib.nvbx_kernel_launch_count()) - launches0
+    counters = mapper.counters(0)
+    clocks = sampler.finish()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.steps / (ms / 1000.0)
+
+    # ---- per-kernel time of the dominant kernel, live, with CUDA events around each call ---------------
+    # (separate pass so that the event records do not perturb the number above)
+    feat_ms, ev = [], [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                       for _ in range(args.steps)]
+    for j, i in enumerate(range(args.warmup, n_total)):
+        mapper.add_depth_frame(depths[i], poses[i], K_t)
+        ev[j][0].record()
+        mapper.add_feature_frame(feats[i % N_FEATURE_BUFFERS], poses[i], K_t)
+        ev[j][1].record()
+    torch.cuda.synchronize()
+    feat_call_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
+    # ---- end-to-end pass: HOST frames through the public API ----------------------------------------------
+    n_e2e = max(1, min(args.steps, 16))
+    h_depth = [d.cpu().pin_memory() for d in depths[:n_e2e]]
+    h_feat = [feats[i % N_FEATURE_BUFFERS].cpu().pin_memory() for i in range(min(n_e2e, 3))]
+    for i in range(min(3, n_e2e)):
+        mapper.integrate_frame_from_host(h_depth[i], h_feat[i % len(h_feat)], poses[i], K_t)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for i in range(n_e2e):
+        mapper.integrate_frame_from_host(h_depth[i], h_feat[i % len(h_feat)], poses[i], K_t)
+        c = mapper.counters(0)          # D2H read of the step's result (map counters) + stream sync
+        d2h = 256
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * n_e2e / e2e_s
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        sample = oracle_sample(2, 1)
+        sample_mt = oracle_sample(2, len(os.sched_getaffinity(0)))
+        n_upd = counters['feature_voxels_updated'] / args.steps
+        n_cand = counters['feature_candidate_blocks'] / args.steps
+        px_per_voxel = sample['u_px'] / max(1, sample['n_upd'])
+        # B_feat: 2C*U_px + 2(C+1)*N_upd + 2*N_upd + 4096*N_cand + 8*(H/4)(W/4) + N_upd, alpha = 1
+        b_feat = (2 * C_FEAT * px_per_voxel * n_upd + 2 * (C_FEAT + 1) * n_upd + 2 * n_upd + 4096 * n_cand +
+                  8 * (H // 4) * (W // 4) + n_upd)
+        kms = kernel_time_ms(args, mapper, depths, poses, feats, K_t)
+        achieved = b_feat / (kms * 1e-3) / 1e9 if kms else None
+        line = {
+            'metric': 'feature frames integrated/s (C=768, 512^2)', 'value': value, 'unit': 'frames/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 geometry + f16 features', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'voxel_size_m': VOXEL, 'workspace': 'cube_stacking box',
+                       'maps_per_gpu': 1, 'parallelism': f'{world} independent map replica(s), no collective',
+                       'l2_policy': f'inputs larger than L2: {N_FEATURE_BUFFERS} distinct 384 MiB feature frames '
+                                    'cycled, a different one every step'},
+            'e2e': {'value': e2e_value, 'unit': 'frames/s',
+                    'h2d_bytes_per_step': H * W * 4 + H * W * C_FEAT * 2, 'd2h_bytes_per_step': d2h,
+                    'steps': n_e2e},
+            'gpu_launches': launches,
+            'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'kernel': 'k_feature_integrate<3>', 'achieved': achieved, 'peak': peak,
+                         'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None, 'traffic': None,
+                         'peak_source': peak_src, 'kernel_ms': kms, 'algorithmic_bytes_per_launch': b_feat,
+                         'n_upd_per_frame': n_upd, 'distinct_pixels_per_voxel': px_per_voxel,
+                         'frac_of_nominal_8TBps': (achieved / 8000.0) if achieved else None},
+            'cpu_baseline': {'value': sample['fps'], 'unit': 'frames/s', 'cores': 1, 'kind': 'port',
+                             'sample': 'first 2 frames of the workload through the CPU oracle (1 thread); '
+                                       f"{sample_mt['threads']} threads: {sample_mt['fps']:.3f} frames/s"},
+            'extra': {'feature_call_ms': feat_call_ms, 'counters_per_step': {k: v / args.steps
+                                                                            for k, v in counters.items()}},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_time_ms(args, mapper, depths, poses, feats, K_t):
+    """Average duration of the k_feature_integrate launch, measured live with CUDA events placed by the
+    library around that kernel (nvbx_set_kernel_timing)."""
+    import ctypes as C
+    from nvblox_mindmap_b200 import _capi
+    lib = _capi.load()
+    if not hasattr(lib, 'nvbx_set_kernel_timing'):
+        return None
+    lib.nvbx_set_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.nvbx_get_kernel_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.nvbx_set_kernel_timing(mapper._handle, 1)
+    n_total = args.warmup + args.steps
+    for i in range(args.warmup, n_total):
+        mapper.add_depth_frame(depths[i], poses[i], K_t)
+        mapper.add_feature_frame(feats[i % N_FEATURE_BUFFERS], poses[i], K_t)
+    ms, n = C.c_double(), C.c_int64()
+    lib.nvbx_get_kernel_timing(mapper._handle, 0, C.byref(ms), C.byref(n))
+    lib.nvbx_set_kernel_timing(mapper._handle, 0)
+    return (ms.value / n.value) if n.value else None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=64)
+    ap.add_argument('--warmup', type=int, default=8)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

@@ -218,6 +218,12 @@ int nvbx_query_features(nvbx_mapper* m, int map_id, const void* xyz, int64_t n, 
 
 int nvbx_get_counters(nvbx_mapper* m, int map_id, nvbx_counters* out, void* stream);
 int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream);
+/* Live per-kernel timing for the roofline line of bench.py: while enabled, the library brackets every
+ * launch of the dominant kernel (which = 0: k_feature_integrate, 1: k_tsdf_update) with CUDA events on
+ * the launching stream.  nvbx_get_kernel_timing synchronises, returns the summed milliseconds and the
+ * number of launches since timing was enabled, and resets the accumulators. */
+int nvbx_set_kernel_timing(nvbx_mapper* m, int enabled);
+int nvbx_get_kernel_timing(nvbx_mapper* m, int which, double* total_ms, int64_t* launches);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t nvbx_kernel_launch_count(void);
 /* Debug / parity hooks: copy the last frame's intermediate products to HOST memory.

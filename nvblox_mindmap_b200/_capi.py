@@ -21,7 +21,7 @@ API_SYMBOLS = [
     'nvbx_update_feature_mesh', 'nvbx_get_feature_mesh', 'nvbx_num_blocks', 'nvbx_num_allocated_blocks',
     'nvbx_num_allocated_bytes', 'nvbx_voxel_size', 'nvbx_get_block_indices', 'nvbx_get_block_ptr',
     'nvbx_allocate_block', 'nvbx_query_tsdf', 'nvbx_query_features', 'nvbx_get_counters',
-    'nvbx_reset_counters', 'nvbx_kernel_launch_count', 'nvbx_debug_last_block_list',
+    'nvbx_reset_counters', 'nvbx_set_kernel_timing', 'nvbx_get_kernel_timing', 'nvbx_kernel_launch_count', 'nvbx_debug_last_block_list',
     'nvbx_debug_last_synthetic_depth', 'nvbx_version',
 ]
 
@@ -79,6 +79,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         L.nvbx_query_features.argtypes = [vp, C.c_int, vp, C.c_int64, vp, vp]
         L.nvbx_get_counters.argtypes = [vp, C.c_int, C.POINTER(NvbxCounters), vp]
         L.nvbx_reset_counters.argtypes = [vp, C.c_int, vp]
+        L.nvbx_set_kernel_timing.argtypes = [vp, C.c_int]
+        L.nvbx_get_kernel_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_double), i64p]
         L.nvbx_kernel_launch_count.restype = C.c_int64
         L.nvbx_debug_last_block_list.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64, vp]
         L.nvbx_debug_last_block_list.restype = C.c_int64

@@ -160,6 +160,8 @@ struct Map {
 }  // namespace
 
 struct nvbx_mapper {
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events[2];
   int device = 0;
   int C = 0;
   int sm_count = 148;
@@ -460,10 +462,27 @@ Cam make_cam(float fx, float fy, float cx, float cy, int H, int W) {
   return c;
 }
 
+int timing_begin(nvbx_mapper* m, int which, cudaStream_t stream) {
+  if (!m->timing) return NVBX_OK;
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a));
+  CUDA_TRY(cudaEventCreate(&b));
+  m->timing_events[which].emplace_back(a, b);
+  CUDA_TRY(cudaEventRecord(a, stream));
+  return NVBX_OK;
+}
+int timing_end(nvbx_mapper* m, int which, cudaStream_t stream) {
+  if (!m->timing) return NVBX_OK;
+  CUDA_TRY(cudaEventRecord(m->timing_events[which].back().second, stream));
+  return NVBX_OK;
+}
+
 template <int VPL>
 int launch_feature(nvbx_mapper* m, Map& mp, const FeatFrame& ff, cudaStream_t stream) {
+  int rc;
+  if ((rc = timing_begin(m, 0, stream))) return rc;
   LAUNCH(k_feature_integrate<VPL>, persistent_grid(m, 2), 512, 0, stream, mp.dev, mp.band_slots.p, ff);
-  return NVBX_OK;
+  return timing_end(m, 0, stream);
 }
 
 }  // namespace
@@ -658,8 +677,9 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
   f.invalid_decay = p.invalid_depth_decay_factor;
   f.weighting_mode = p.weighting_mode;
   const int tgrid = std::max(1, std::min(persistent_grid(m, 2), entry->bound));
+  if ((rc = timing_begin(m, 1, stream))) return rc;
   LAUNCH(k_tsdf_update, tgrid, 512, 0, stream, mp.dev, mp.view_slots.p, entry->d_count, f);
-  return NVBX_OK;
+  return timing_end(m, 1, stream);
 }
 
 // ---- features ------------------------------------------------------------------------------------
@@ -1065,6 +1085,31 @@ int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream_v) {
   if (rc) return rc;
   Map& mp = *m->maps[map_id];
   CUDA_TRY(cudaMemsetAsync(mp.d_ctrl->counters, 0, sizeof(unsigned long long) * kCntNum, (cudaStream_t)stream_v));
+  return NVBX_OK;
+}
+
+int nvbx_set_kernel_timing(nvbx_mapper* m, int enabled) {
+  if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper handle");
+  m->timing = enabled != 0;
+  return NVBX_OK;
+}
+int nvbx_get_kernel_timing(nvbx_mapper* m, int which, double* total_ms, int64_t* launches) {
+  if (!m || which < 0 || which > 1) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad timing query");
+  CUDA_TRY(cudaSetDevice(m->device));
+  double sum = 0.0;
+  int64_t n = 0;
+  for (auto& ev : m->timing_events[which]) {
+    CUDA_TRY(cudaEventSynchronize(ev.second));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    sum += ms;
+    ++n;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  m->timing_events[which].clear();
+  if (total_ms) *total_ms = sum;
+  if (launches) *launches = n;
   return NVBX_OK;
 }
 

@@ -37,6 +37,9 @@
 #include <set>
 #include <unordered_set>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../include/nvbx_c_api.h"
 
@@ -597,8 +600,14 @@ void integrate_depth(Oracle& o, const float* depth, int rows, int cols, const ui
   }
   const Pose T_C_L = inverse(T_L_C);
   const float trunc = trunc_tsdf(o);
-  for (const I3& b : blocks) {
-    TsdfBlock& blk = o.tsdf[b];
+  std::vector<TsdfBlock*> blk_ptrs(blocks.size());
+  for (size_t i = 0; i < blocks.size(); ++i) blk_ptrs[i] = &o.tsdf[blocks[i]];
+  int64_t n_updated = 0;
+  // blocks are independent: OpenMP over blocks does not change any result
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : n_updated)
+  for (size_t bi = 0; bi < blocks.size(); ++bi) {
+    const I3 b = blocks[bi];
+    TsdfBlock& blk = *blk_ptrs[bi];
     for (int x = 0; x < 8; ++x)
       for (int y = 0; y < 8; ++y)
         for (int z = 0; z < 8; ++z) {
@@ -630,9 +639,10 @@ void integrate_depth(Oracle& o, const float* depth, int rows, int cols, const ui
           const float w_new = std::fmin(w_m + w_cur, o.p.max_weight);
           blk.d[l] = fused;
           blk.w[l] = w_new;
-          o.cnt.tsdf_voxels_updated++;
+          n_updated++;
         }
   }
+  o.cnt.tsdf_voxels_updated += n_updated;
   o.cnt.tsdf_blocks_in_view += (int64_t)blocks.size();
   for (const I3& b : blocks) o.mesh_dirty.insert(b);  // mapper.cpp:406
 }
@@ -729,6 +739,7 @@ void render_synthetic_depth(Oracle& o, const Cam& cam, const Pose& T_L_C, float 
   o.synth_rows = rows;
   o.synth_cols = cols;
   const V3 origin{T_L_C.t[0], T_L_C.t[1], T_L_C.t[2]};
+#pragma omp parallel for schedule(dynamic, 4)
   for (int r = 0; r < rows; ++r)
     for (int c = 0; c < cols; ++c) {
       const float pu = (float)(c * s) + 0.5f * (float)s * 1.0f;
@@ -787,9 +798,18 @@ void integrate_features(Oracle& o, const uint16_t* img, int rows, int cols, cons
   const int sub = rows / o.synth_rows;  // projective_integrator_impl.cuh:424-425
   const Pose T_C_L = inverse(T_L_C);
   const float alpha = o.p.appearance_measurement_weight;
+  std::vector<std::vector<uint16_t>*> fblk_ptrs(band.size());
+  for (size_t i = 0; i < band.size(); ++i) fblk_ptrs[i] = &o.feat[band[i]];
+  int64_t n_upd = 0;
+  const bool fused_half = g_fused_half;
+#pragma omp parallel reduction(+ : n_upd)
+  {
   std::vector<uint16_t> meas((size_t)C);
-  for (const I3& b : band) {
-    std::vector<uint16_t>& blk = o.feat[b];
+  std::unordered_set<uint64_t> seen_local;
+#pragma omp for schedule(dynamic, 2)
+  for (size_t bi = 0; bi < band.size(); ++bi) {
+    const I3 b = band[bi];
+    std::vector<uint16_t>& blk = *fblk_ptrs[bi];
     for (int x = 0; x < 8; ++x)
       for (int y = 0; y < 8; ++y)
         for (int z = 0; z < 8; ++z) {
@@ -822,10 +842,10 @@ void integrate_features(Oracle& o, const uint16_t* img, int rows, int cols, cons
           const uint16_t* p10 = img + ((size_t)ly * cols + lx + 1) * C;
           const uint16_t* p11 = img + ((size_t)(ly + 1) * cols + lx + 1) * C;
           for (int c = 0; c < C; ++c) meas[c] = interp_half(hx, hy, p00[c], p01[c], p10[c], p11[c]);
-          o.pixel_seen.insert(((uint64_t)ly << 32) | (uint32_t)lx);
-          o.pixel_seen.insert(((uint64_t)(ly + 1) << 32) | (uint32_t)lx);
-          o.pixel_seen.insert(((uint64_t)ly << 32) | (uint32_t)(lx + 1));
-          o.pixel_seen.insert(((uint64_t)(ly + 1) << 32) | (uint32_t)(lx + 1));
+          seen_local.insert(((uint64_t)ly << 32) | (uint32_t)lx);
+          seen_local.insert(((uint64_t)(ly + 1) << 32) | (uint32_t)lx);
+          seen_local.insert(((uint64_t)ly << 32) | (uint32_t)(lx + 1));
+          seen_local.insert(((uint64_t)(ly + 1) << 32) | (uint32_t)(lx + 1));
           uint16_t* vox = blk.data() + (size_t)vlin(x, y, z) * (C + 1);
           const float w_cur = h2f(vox[C]);
           if (w_cur == 0.0f) {
@@ -837,17 +857,21 @@ void integrate_features(Oracle& o, const uint16_t* img, int rows, int cols, cons
             w2 /= tot;
             const uint16_t h1 = f2h(w1), h2 = f2h(w2);
             for (int c = 0; c < C; ++c) {
-              if (!g_fused_half)
+              if (!fused_half)
                 vox[c] = hadd(hmul(vox[c], h1), hmul(meas[c], h2));
               else
                 vox[c] = hfma(vox[c], h1, hmul(meas[c], h2));
             }
           }
           vox[C] = f2h(std::fmin(alpha + w_cur, o.p.max_weight));
-          o.cnt.feature_voxels_updated++;
-          o.last_n_upd++;
+          n_upd++;
         }
   }
+#pragma omp critical
+  o.pixel_seen.insert(seen_local.begin(), seen_local.end());
+  }  // omp parallel
+  o.cnt.feature_voxels_updated += n_upd;
+  o.last_n_upd += n_upd;
   o.cnt.feature_band_blocks += (int64_t)band.size();
   o.last_distinct_pixels = (int64_t)o.pixel_seen.size();
   for (const I3& b : band) o.mesh_dirty.insert(b);  // mapper.cpp:462
@@ -1100,6 +1124,20 @@ void* orc_create(float voxel_size, int C, const nvbx_params* p) {
 }
 void orc_destroy(void* h) { delete (Oracle*)h; }
 void orc_set_fused_half(int v) { g_fused_half = v != 0; }
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n > 0 ? n : 1);
+#else
+  (void)n;
+#endif
+}
 
 static Cam make_cam(float fx, float fy, float cx, float cy, int H, int W) { return Cam{fx, fy, cx, cy, W, H}; }
 

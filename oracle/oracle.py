@@ -35,6 +35,8 @@ def lib() -> C.CDLL:
         L.orc_create.argtypes = [C.c_float, C.c_int, C.POINTER(NvbxParams)]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_set_fused_half.argtypes = [C.c_int]
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_max_threads.restype = C.c_int
         frame = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, fp, C.c_float, C.c_float, C.c_float,
                  C.c_float]
         L.orc_integrate_depth.argtypes = frame
@@ -85,6 +87,14 @@ def lib() -> C.CDLL:
         L.orc_weld_key.argtypes = [fp]
         _lib = L
     return _lib
+
+
+def set_threads(n: int) -> None:
+    lib().orc_set_threads(int(n))
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
 
 
 def default_params() -> NvbxParams:
