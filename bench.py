@@ -232,6 +232,13 @@ def run_ours(args, rank, world, local_rank):
         ms = float(t.item())
     value = world * args.steps / (ms / 1000.0)
 
+    if args.quick:
+        if rank == 0:
+            kms = kernel_time_ms(args, mapper, depths, poses, feats, K_t)
+            print(json.dumps({'quick': True, 'value': value, 'ms_per_step': ms / args.steps, 'kernel_ms': kms,
+                              'gpu_launches': launches, 'profile': counters.get('profile')}), flush=True)
+        return
+
     # ---- per-kernel time of the dominant kernel, live, with CUDA events around each call ---------------
     # (separate pass so that the event records do not perturb the number above)
     feat_ms, ev = [], [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -335,6 +342,7 @@ def main():
     ap.add_argument('--steps', type=int, default=64)
     ap.add_argument('--warmup', type=int, default=8)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--quick', action='store_true', help='tuning aid: device-timed pass + kernel timing only')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

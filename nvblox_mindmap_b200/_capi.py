@@ -31,6 +31,8 @@ class NvbxError(RuntimeError):
 
 
 def library_path() -> str:
+    if os.environ.get('NVBX_PROFILE') == '1':      # tuning aid: in-kernel counters compiled in
+        return _build.PROFILE_LIB_PATH
     return _build.LIB_PATH
 
 
@@ -44,7 +46,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         if not os.path.exists(path):
             if not build_if_missing:
                 raise NvbxError(f'{path} is missing: run `python -m nvblox_mindmap_b200.build` (no CPU fallback)')
-            _build.build()
+            _build.build(profile=path == _build.PROFILE_LIB_PATH)
         L = C.CDLL(path)
         vp, fp, i32p, i64p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
         L.nvbx_default_params.argtypes = [C.POINTER(NvbxParams)]

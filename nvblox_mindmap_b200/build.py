@@ -14,6 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libnvbx.so')
+# tuning aid (NVBX_PROFILE=1): same sources with -DNVBX_PROFILE_COUNTERS (in-kernel step / cycle counters)
+PROFILE_LIB_PATH = os.path.join(LIB_DIR, 'libnvbx_prof.so')
 SOURCES = ['nvbx.cu']
 DEPS = ['nvbx.cu', 'nvbx_kernels.cuh', 'nvbx_mesh.cuh', 'nvbx_map.cuh', 'nvbx_math.cuh', 'mc_tables.h',
         os.path.join('..', '..', 'include', 'nvbx_c_api.h')]
@@ -41,19 +43,21 @@ def needs_build() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB_PATH
+def build(force: bool = False, verbose: bool = False, profile: bool = False) -> str:
+    out = PROFILE_LIB_PATH if profile else LIB_PATH
+    if not force and not needs_build() and os.path.exists(out) and \
+            os.path.getmtime(out) >= max(os.path.getmtime(os.path.join(CSRC, d)) for d in DEPS):
+        return out
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
-        ['-o', LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+        (['-DNVBX_PROFILE_COUNTERS'] if profile else []) + ['-o', out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout)
     if verbose:
         print(res.stdout)
-    return LIB_PATH
+    return out
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, profile='--profile' in sys.argv))

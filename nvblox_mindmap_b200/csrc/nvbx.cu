@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -82,9 +83,10 @@ struct DevBuf {  // grow-only device scratch buffer
 struct CacheEntry {
   Pose T;
   Cam cam;
-  DevBuf<int3> idx;
+  DevBuf<int3> idx;     // raycast cache only: the block-index list (depends on the depth image)
   int* d_count = nullptr;
-  int bound = 0;  // host upper bound of *d_count (cells of the AABB it was built from)
+  int bound = 0;        // host upper bound of *d_count (cells of the AABB it was built from)
+  ViewGrid grid{};      // planes cache only: the frustum AABB the in-view test enumerates
 };
 
 struct ViewCache {  // deque semantics of ViewpointCache (kMaxCacheSize = 2), view_calculator.cu:519-541
@@ -96,7 +98,7 @@ struct ViewCache {  // deque semantics of ViewpointCache (kMaxCacheSize = 2), vi
     return nullptr;
   }
   // entry to (over)write for a new result: the one that would be evicted, or a fresh one
-  int acquire(CacheEntry** out) {
+  int acquire(CacheEntry** out, bool device_list = true) {
     if (live.size() == 2) {
       *out = live.back();
       live.pop_back();
@@ -104,7 +106,7 @@ struct ViewCache {  // deque semantics of ViewpointCache (kMaxCacheSize = 2), vi
     }
     pool.emplace_back(new CacheEntry());
     CacheEntry* e = pool.back().get();
-    CUDA_TRY(cudaMalloc(&e->d_count, sizeof(int)));
+    if (device_list) CUDA_TRY(cudaMalloc(&e->d_count, sizeof(int)));
     *out = e;
     return NVBX_OK;
   }
@@ -134,8 +136,10 @@ struct Map {
   Ctrl* h_ctrl = nullptr;  // pinned mirror
   ViewCache raycast_cache, planes_cache;
   CacheEntry scratch_ray, scratch_planes;  // used when the cache is disabled
-  DevBuf<uint8_t> grid;
-  DevBuf<int> view_slots, band_slots, newfeat_slots;
+  DevBuf<unsigned> grid;   // view bitmap; all-zero between frames (k_view_compact_alloc cleans it)
+  bool grid_dirty = false;  // a frame failed between marking and compaction
+  DevBuf<int> view_slots, band_slots;
+  DevBuf<FeatItem> items;
   DevBuf<float> synth;
   int synth_rows = 0, synth_cols = 0;
   CacheEntry* last_depth_entry = nullptr;
@@ -170,6 +174,9 @@ struct nvbx_mapper {
 };
 
 namespace {
+
+constexpr long long kMaxWorkspaceGridCells = 1LL << 24;  // 64 MiB of slot ids
+constexpr int kFeatureChunkBlocks = 8192;                // band blocks per geometry/gather pass (64 MiB of items)
 
 int persistent_grid(const nvbx_mapper* m, int ctas_per_sm) { return m->sm_count * ctas_per_sm; }
 
@@ -220,6 +227,8 @@ int grow_slots(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
   // hash: next pow2 >= 4 * capacity
   unsigned hcap = 1024;
   while (hcap < 4u * (unsigned)new_cap) hcap <<= 1;
+  if (mp.dev.ws_cells > 0 && hcap > (1u << 16) && mp.slot_capacity <= mp.dev.ws_cells)
+    hcap = mp.dev.hash_mask ? mp.dev.hash_mask + 1 : (1u << 16);  // grid-indexed map: the hash only holds strays
   if (hcap != mp.dev.hash_mask + 1 || mp.dev.keys == nullptr) {
     if (mp.dev.keys) cudaFree(mp.dev.keys);
     if (mp.dev.vals) cudaFree(mp.dev.vals);
@@ -392,7 +401,31 @@ int init_map(nvbx_mapper* m, Map& mp, float voxel_size, cudaStream_t stream) {
   CUDA_TRY(cudaMalloc(&mp.d_tmp_int, sizeof(int)));
   CUDA_TRY(cudaMalloc(&mp.d_tmp_ptr, sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc(&mp.scratch_ray.d_count, sizeof(int)));
-  CUDA_TRY(cudaMalloc(&mp.scratch_planes.d_count, sizeof(int)));
+  // level-1 index: direct-mapped grid over the workspace box (same rounding as make_grid)
+  if (m->params.workspace_bounds_type == NVBX_WORKSPACE_BOUNDING_BOX) {
+    Aabb a;
+    for (int i = 0; i < 3; ++i) {
+      a.mn[i] = m->params.workspace_min[i];
+      a.mx[i] = m->params.workspace_max[i];
+    }
+    if (!a.empty()) {
+      V3 lo = {a.mn[0], a.mn[1], a.mn[2]}, hi = {a.mx[0], a.mx[1], a.mx[2]};
+      const I3 mn = block_index_from_position(mp.block_size, lo);
+      const I3 mx = block_index_from_position(mp.block_size, hi);
+      const long long sx = (long long)mx.x - mn.x + 1, sy = (long long)mx.y - mn.y + 1, sz = (long long)mx.z - mn.z + 1;
+      if (sx > 0 && sy > 0 && sz > 0 && sx * sy * sz <= kMaxWorkspaceGridCells && key_in_range(mn.x, mn.y, mn.z) &&
+          key_in_range(mx.x, mx.y, mx.z)) {
+        const int cells = (int)(sx * sy * sz);
+        CUDA_TRY(cudaMalloc(&mp.dev.ws_slot, (size_t)cells * sizeof(int)));
+        CUDA_TRY(cudaMemsetAsync(mp.dev.ws_slot, 0xff, (size_t)cells * sizeof(int), stream));  // -1
+        mp.dev.ws_mn = mn;
+        mp.dev.ws_sx = (int)sx;
+        mp.dev.ws_sy = (int)sy;
+        mp.dev.ws_sz = (int)sz;
+        mp.dev.ws_cells = cells;
+      }
+    }
+  }
   int rc = grow_slots(m, mp, std::max(1024, m->params.num_preallocated_blocks), stream);
   if (rc) return rc;
   return grow_feats(m, mp, 1 << kFeatSlabShift, stream);
@@ -404,6 +437,7 @@ void destroy_map(Map& mp) {
     if (p) cudaFree(p);
     p = nullptr;
   };
+  F(mp.dev.ws_slot);
   F(mp.dev.keys);
   F(mp.dev.vals);
   F(mp.dev.blk_index);
@@ -429,11 +463,10 @@ void destroy_map(Map& mp) {
   mp.scratch_ray.idx.release();
   mp.scratch_planes.idx.release();
   F(mp.scratch_ray.d_count);
-  F(mp.scratch_planes.d_count);
   mp.grid.release();
   mp.view_slots.release();
   mp.band_slots.release();
-  mp.newfeat_slots.release();
+  mp.items.release();
   mp.synth.release();
   mp.cnt_v.release();
   mp.cnt_t.release();
@@ -477,11 +510,31 @@ int timing_end(nvbx_mapper* m, int which, cudaStream_t stream) {
   return NVBX_OK;
 }
 
-template <int VPL>
-int launch_feature(nvbx_mapper* m, Map& mp, const FeatFrame& ff, cudaStream_t stream) {
+int gather_variant() {  // tuning hook: NVBX_GATHER_VARIANT=0..3 (default 1)
+  static const int v = [] {
+    const char* e = getenv("NVBX_GATHER_VARIANT");
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
+
+template <int CH>
+int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, cudaStream_t stream) {
   int rc;
   if ((rc = timing_begin(m, 0, stream))) return rc;
-  LAUNCH(k_feature_integrate<VPL>, persistent_grid(m, 2), 512, 0, stream, mp.dev, mp.band_slots.p, ff);
+  switch (gather_variant()) {
+    case 0:
+      LAUNCH((k_feature_gather<CH, 1, 4>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
+      break;
+    case 2:
+      LAUNCH((k_feature_gather<CH, 1, 6>), persistent_grid(m, 6), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
+      break;
+    case 3:
+      LAUNCH((k_feature_gather<CH, 1, 8>), persistent_grid(m, 8), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
+      break;
+    default:
+      LAUNCH((k_feature_gather<CH, 2, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
+  }
   return timing_end(m, 0, stream);
 }
 
@@ -632,27 +685,38 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
       entry = &mp.scratch_ray;
     }
     const size_t n = (size_t)gs.g.n_cells;
+    const size_t n_words = (n + 31) / 32;
     if ((rc = entry->idx.ensure(n, stream))) return rc;
-    if ((rc = mp.grid.ensure(n, stream))) return rc;
+    const unsigned* old_grid = mp.grid.p;
+    if ((rc = mp.grid.ensure(n_words, stream))) return rc;
+    if (mp.grid.p != old_grid || mp.grid_dirty)  // a fresh (or abandoned) bitmap starts all-zero
+      CUDA_TRY(cudaMemsetAsync(mp.grid.p, 0, mp.grid.cap * sizeof(unsigned), stream));
     if ((rc = mp.view_slots.ensure(n, stream))) return rc;
     entry->T = T_L_C;
     entry->cam = cam;
     entry->bound = gs.g.n_cells;
-    CUDA_TRY(cudaMemsetAsync(mp.grid.p, 0, n, stream));
-    CUDA_TRY(cudaMemsetAsync(entry->d_count, 0, sizeof(int), stream));
     const int s = p.raycast_subsampling_factor;
     const int n_rows = (int)std::ceil((float)(height + 1) / (float)s);
     const int n_cols = (int)std::ceil((float)(width + 1) / (float)s);
-    const dim3 rgrid((unsigned)std::ceil(n_cols / 16.0f), (unsigned)std::ceil(n_rows / 16.0f));
-    LAUNCH(k_raycast_mark, rgrid, dim3(16, 16), 0, stream, T_L_C, cam, (const float*)depth, height, width,
-           mp.block_size, p.max_integration_distance_m, trunc, s, gs.g, mp.grid.p);
-    const int cgrid = std::min(persistent_grid(m, 4), (gs.g.n_cells + 255) / 256);
+    const int tiles_x = (n_cols + 15) / 16, n_tiles = tiles_x * ((n_rows + 15) / 16);
+    const int rgrid = std::max(1, std::min(n_tiles, persistent_grid(m, 4)));
+    mp.grid_dirty = true;
+    if (n_words <= (size_t)kRayBitmapWords) {
+      LAUNCH(k_raycast_mark<true>, rgrid, 256, n_words * sizeof(unsigned), stream, T_L_C, cam, (const float*)depth,
+             height, width, mp.block_size, p.max_integration_distance_m, trunc, s, gs.g, mp.grid.p, tiles_x, n_tiles,
+             entry->d_count);
+    } else {
+      LAUNCH(k_raycast_mark<false>, rgrid, 256, 0, stream, T_L_C, cam, (const float*)depth, height, width,
+             mp.block_size, p.max_integration_distance_m, trunc, s, gs.g, mp.grid.p, tiles_x, n_tiles,
+             entry->d_count);
+    }
+    const int cgrid = std::max(1, std::min(persistent_grid(m, 4), (int)((n_words + 7) / 8)));  // warp per word
     if (!slots_fit(m, mp, (long long)n)) {
       // The pessimistic bound (every cell of the AABB is new) does not fit: count the marked cells and
       // read that one int back.  Only happens while the arena is still growing (or with an unbounded
       // workspace); a bounded workspace reaches its cell count and never synchronises again.
       CUDA_TRY(cudaMemsetAsync(mp.d_tmp_int, 0, sizeof(int), stream));
-      LAUNCH(k_count_marked, cgrid, 256, 0, stream, mp.grid.p, gs.g.n_cells, mp.d_tmp_int);
+      LAUNCH(k_count_marked, cgrid, 256, 0, stream, mp.grid.p, (int)n_words, mp.d_tmp_int);
       int marked = 0;
       CUDA_TRY(cudaMemcpyAsync(&marked, mp.d_tmp_int, sizeof(int), cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(cudaStreamSynchronize(stream));
@@ -661,6 +725,7 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
     if ((rc = ensure_slots(m, mp, (long long)entry->bound, stream))) return rc;
     LAUNCH(k_view_compact_alloc, cgrid, 256, 0, stream, mp.dev, mp.grid.p, gs.g, entry->idx.p, entry->d_count,
            mp.view_slots.p);
+    mp.grid_dirty = false;
     if (p.cache_last_viewpoint) mp.raycast_cache.store(entry);
   }
   mp.last_depth_entry = entry;
@@ -712,37 +777,38 @@ int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, in
     if ((rc = make_grid(m, mp, view_aabb(cam, T_L_C, 1e-6f, p.max_integration_distance_m + trunc), &gs))) return rc;
     if (gs.empty) return NVBX_OK;
     if (p.cache_last_viewpoint) {
-      if ((rc = mp.planes_cache.acquire(&entry))) return rc;
+      if ((rc = mp.planes_cache.acquire(&entry, false))) return rc;
     } else {
       entry = &mp.scratch_planes;
     }
-    if ((rc = entry->idx.ensure((size_t)gs.g.n_cells, stream))) return rc;
     entry->T = T_L_C;
     entry->cam = cam;
+    entry->grid = gs.g;
     entry->bound = gs.g.n_cells;
-    CUDA_TRY(cudaMemsetAsync(entry->d_count, 0, sizeof(int), stream));
-    const V3 vmin = ray_from_image_plane(cam, -10.0f, -10.0f);
-    const V3 vmax = ray_from_image_plane(cam, (float)cam.width + 10.0f, (float)cam.height + 10.0f);
-    const int pgrid = std::min(persistent_grid(m, 4), (gs.g.n_cells + 255) / 256);
-    LAUNCH(k_planes_view, pgrid, 256, 0, stream, gs.g, mp.block_size, T_C_L, vmin.x, vmin.y, vmax.x, vmax.y,
-           entry->idx.p, entry->d_count);
     if (p.cache_last_viewpoint) mp.planes_cache.store(entry);
+  }
+  // The in-view test runs with the pose / camera / AABB of the cache entry: on a hit these are the
+  // cached ones, i.e. the block list the reference would have re-used (view_calculator.cu:401-405).
+  PlanesView pv;
+  pv.g = entry->grid;
+  pv.T_C_L = inverse(entry->T);
+  {
+    const V3 vmin = ray_from_image_plane(entry->cam, -10.0f, -10.0f);
+    const V3 vmax = ray_from_image_plane(entry->cam, (float)entry->cam.width + 10.0f, (float)entry->cam.height + 10.0f);
+    pv.vmin_x = vmin.x;
+    pv.vmin_y = vmin.y;
+    pv.vmax_x = vmax.x;
+    pv.vmax_y = vmax.y;
   }
   const long long cand_bound = std::min((long long)entry->bound, std::max(1LL, mp.slot_used_ub));
   if ((rc = ensure_feats(m, mp, cand_bound, stream))) return rc;
   if ((rc = mp.band_slots.ensure((size_t)cand_bound, stream))) return rc;
-  if ((rc = mp.newfeat_slots.ensure((size_t)cand_bound, stream))) return rc;
+  const long long chunk_blocks = std::min<long long>(cand_bound, kFeatureChunkBlocks);
+  if ((rc = mp.items.ensure((size_t)chunk_blocks * kVoxelsPerBlock, stream))) return rc;
   const int srows = height / sub, scols = width / sub;
   if ((rc = mp.synth.ensure((size_t)srows * scols, stream))) return rc;
   mp.synth_rows = srows;
   mp.synth_cols = scols;
-
-  // band_count and newfeat_count are adjacent ints in Ctrl
-  CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->band_count, 0, 2 * sizeof(int), stream));
-  const int bgrid = std::max(1, std::min(persistent_grid(m, 4), (entry->bound + 7) / 8));
-  LAUNCH(k_band_select, bgrid, 256, 0, stream, mp.dev, entry->idx.p, entry->d_count, trunc, mp.band_slots.p,
-         mp.newfeat_slots.p);
-  LAUNCH(k_zero_feature_blocks, persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.newfeat_slots.p);
 
   TraceParams tp;
   tp.cam = cam;
@@ -754,7 +820,17 @@ int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, in
   tp.sub = sub;
   tp.rows = srows;
   tp.cols = scols;
-  LAUNCH(k_sphere_trace, dim3((scols + 7) / 8, (srows + 7) / 8), 64, 0, stream, mp.dev, tp, mp.synth.p);
+  {
+    // band-select tiles: small enough that a mindmap-sized AABB (a few hundred cells) spreads over many SMs
+    int tile_cells = 32;
+    while (tile_cells < 256 && (entry->bound + tile_cells - 1) / tile_cells > 2 * m->sm_count) tile_cells <<= 1;
+    const int n_tiles = (entry->bound + tile_cells - 1) / tile_cells;
+    const int trace_tiles_x = (scols + 15) / 16;
+    const int n_trace = trace_tiles_x * ((srows + 15) / 16);
+    const int n_band = std::max(1, std::min(n_tiles, persistent_grid(m, 4)));
+    LAUNCH(k_trace_and_band, n_trace + n_band, 256, 0, stream, mp.dev, tp, mp.synth.p, trace_tiles_x, n_trace, pv,
+           trunc, mp.band_slots.p, tile_cells, n_tiles);
+  }
 
   FeatFrame ff;
   ff.img = (const __half*)features;
@@ -781,17 +857,24 @@ int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, in
     std::memcpy(&ff.h_w2, &h2, 2);
   }
   ff.read_old = (p.strict_blend || ff.alpha != 1.0f) ? 1 : 0;
-  if (m->C % 256 == 0 && m->C / 256 == 3)
-    rc = launch_feature<3>(m, mp, ff, stream);
-  else if (m->C % 256 == 0 && m->C / 256 == 4)
-    rc = launch_feature<4>(m, mp, ff, stream);
-  else if (m->C % 256 == 0 && m->C / 256 == 2)
-    rc = launch_feature<2>(m, mp, ff, stream);
-  else if (m->C % 256 == 0 && m->C / 256 == 1)
-    rc = launch_feature<1>(m, mp, ff, stream);
-  else
-    rc = launch_feature<0>(m, mp, ff, stream);
-  if (rc) return rc;
+  for (long long begin = 0; begin < cand_bound; begin += chunk_blocks) {
+    const long long end = std::min(cand_bound, begin + chunk_blocks);
+    const int last = end >= cand_bound ? 1 : 0;
+    if (begin > 0) CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->item_count, 0, sizeof(int), stream));
+    const int ggrid = (int)std::max<long long>(1, std::min<long long>(persistent_grid(m, 2), end - begin));
+    LAUNCH(k_feature_geometry, ggrid, 512, 0, stream, mp.dev, mp.band_slots.p, ff, mp.items.p, (int)begin, (int)end);
+    if (m->C % 256 == 0 && m->C / 256 == 3)
+      rc = launch_gather<3>(m, mp, ff, last, stream);
+    else if (m->C % 256 == 0 && m->C / 256 == 4)
+      rc = launch_gather<4>(m, mp, ff, last, stream);
+    else if (m->C % 256 == 0 && m->C / 256 == 2)
+      rc = launch_gather<2>(m, mp, ff, last, stream);
+    else if (m->C % 256 == 0 && m->C / 256 == 1)
+      rc = launch_gather<1>(m, mp, ff, last, stream);
+    else
+      rc = launch_gather<0>(m, mp, ff, last, stream);
+    if (rc) return rc;
+  }
   mp.have_band_list = true;
   return NVBX_OK;
 }
@@ -1078,6 +1161,7 @@ int nvbx_get_counters(nvbx_mapper* m, int map_id, nvbx_counters* out, void* stre
   out->blocks_deallocated = (int64_t)c[kCntBlocksDeallocated];
   out->mesh_blocks_remeshed = (int64_t)c[kCntMeshBlocksRemeshed];
   out->mesh_vertices = (int64_t)c[kCntMeshVertices];
+  for (int i = 0; i < 4; ++i) out->reserved[i] = (int64_t)c[12 + i];  // NVBX_PROFILE_COUNTERS builds only
   return NVBX_OK;
 }
 int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream_v) {
@@ -1133,7 +1217,7 @@ int64_t nvbx_debug_last_block_list(nvbx_mapper* m, int map_id, int which, int32_
   }
   if (!mp.have_band_list) return 0;
   if ((rc = read_ctrl(mp, stream))) return rc;
-  const int n = mp.h_ctrl->band_count;
+  const int n = mp.h_ctrl->last_band_count;
   if (out_xyz && capacity > 0 && n > 0) {
     std::vector<int> slots((size_t)n);
     CUDA_TRY(cudaMemcpyAsync(slots.data(), mp.band_slots.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -1141,9 +1225,10 @@ int64_t nvbx_debug_last_block_list(nvbx_mapper* m, int map_id, int which, int32_
     CUDA_TRY(cudaMemcpyAsync(all.data(), mp.dev.blk_index, all.size() * sizeof(int3), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     for (int64_t i = 0; i < std::min<int64_t>(n, capacity); ++i) {
-      out_xyz[3 * i] = all[slots[i]].x;
-      out_xyz[3 * i + 1] = all[slots[i]].y;
-      out_xyz[3 * i + 2] = all[slots[i]].z;
+      const int3 b = all[slots[i] & kSlotMask];
+      out_xyz[3 * i] = b.x;
+      out_xyz[3 * i + 1] = b.y;
+      out_xyz[3 * i + 2] = b.z;
     }
   }
   return n;

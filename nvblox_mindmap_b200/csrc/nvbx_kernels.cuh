@@ -29,10 +29,15 @@ __device__ __forceinline__ void count_add(const MapDev& m, int id, unsigned long
 }
 
 // ================================================================================================
-// a2. Blocks in view by ray casting -- one thread per (subsampled) depth pixel, 3-D DDA into a dense
-// byte grid over the view AABB.  Follows combinedBlockIndicesInImageKernel
-// (NB/src/integrators/view_calculator.cu:196-248) and RayCaster (ray_caster_impl.h:26-75), including
-// the linear-index alias of setIndexUpdated (:171-180).
+// a2. Blocks in view by ray casting -- one thread per (subsampled) depth pixel, 3-D DDA over the view
+// AABB.  Follows combinedBlockIndicesInImageKernel (NB/src/integrators/view_calculator.cu:196-248) and
+// RayCaster (ray_caster_impl.h:26-75), including the linear-index alias of setIndexUpdated (:171-180).
+//
+// The reference marks a dense bool grid in global memory: 263 k rays hammer a few hundred bytes, and
+// the same-address traffic serialises in L2.  Here the grid is a BITMAP; every CTA marks a private
+// copy in shared memory (read-before-atomicOr, so a set bit costs one broadcast load) and ORs its
+// non-zero words into the global bitmap once, at the end of its persistent tile loop.  Views whose
+// AABB has more cells than the shared bitmap holds mark the global bitmap directly.
 // ================================================================================================
 struct ViewGrid {
   I3 mn;
@@ -40,98 +45,119 @@ struct ViewGrid {
   int n_cells;
 };
 
-__device__ __forceinline__ void mark_cell(uint8_t* grid, const ViewGrid& g, int x, int y, int z) {
+constexpr int kRayBitmapWords = 8192;  // 32 KiB of shared memory = 262 144 cells
+
+template <bool SMEM>
+__device__ __forceinline__ void mark_cell(unsigned* bm, const ViewGrid& g, int x, int y, int z) {
   const int lx = x - g.mn.x, ly = y - g.mn.y, lz = z - g.mn.z;
   const size_t lin = (size_t)(int)(lx + ly * g.sx + lz * g.sx * g.sy);
   if (lin < (size_t)g.n_cells) {
-    if (!grid[lin]) grid[lin] = 1;  // benign same-value race, as in the reference
+    const unsigned w = (unsigned)lin >> 5, bit = 1u << ((unsigned)lin & 31u);
+    if (SMEM) {
+      if (!(bm[w] & bit)) atomicOr(&bm[w], bit);
+    } else {
+      if (!(__ldcg(&bm[w]) & bit)) atomicOr(&bm[w], bit);
+    }
   }
 }
 
+template <bool SMEM>
 __global__ void __launch_bounds__(256) k_raycast_mark(Pose T_L_C, Cam cam, const float* __restrict__ depth, int rows,
                                                       int cols, float block_size, float max_dist, float behind,
-                                                      int sub, ViewGrid g, uint8_t* grid) {
-  const int ray_col = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ray_row = blockIdx.y * blockDim.y + threadIdx.y;
-  int prow = ray_row * sub, pcol = ray_col * sub;
-  if (prow >= rows + sub - 1 || pcol >= cols + sub - 1) return;
-  if (prow >= rows) prow = rows - 1;
-  if (pcol >= cols) pcol = cols - 1;
-  float d = depth[(size_t)prow * cols + pcol];
-  if (d <= 0.0f) return;
-  if (max_dist > 0.0f && d > max_dist) d = max_dist;
-  const V3 ray = ray_from_image_plane(cam, (float)pcol + 0.5f, (float)prow + 0.5f);
-  const float len = d + behind;
-  V3 p_C;
-  p_C.x = len * ray.x;
-  p_C.y = len * ray.y;
-  p_C.z = len * ray.z;
-  const V3 p_L = xform(T_L_C, p_C);
-  const I3 b = block_index_from_position(block_size, p_L);
-  mark_cell(grid, g, b.x, b.y, b.z);
-
-  // RayCaster(origin / bs, p_L / bs), scale 1
-  const float s[3] = {(T_L_C.t[0] / block_size) / 1.0f, (T_L_C.t[1] / block_size) / 1.0f,
-                      (T_L_C.t[2] / block_size) / 1.0f};
-  const float e[3] = {(p_L.x / block_size) / 1.0f, (p_L.y / block_size) / 1.0f, (p_L.z / block_size) / 1.0f};
-  int cur[3], sign[3];
-  float t_next[3], t_step[3];
-  int steps = 0;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    cur[i] = (int)floorf(s[i]);
-    const int end = (int)floorf(e[i]);
-    steps += abs(end - cur[i]);
-    const float r = e[i] - s[i];
-    sign[i] = (r > 0.0f) ? 1 : ((r < 0.0f) ? -1 : 0);
-    const int corrected = max(sign[i], 0);
-    const float shifted = s[i] - (float)cur[i];
-    const float dist = (float)corrected - shifted;
-    t_next[i] = dist / r;
-    t_step[i] = (float)sign[i] / r;
+                                                      int sub, ViewGrid g, unsigned* gbits, int tiles_x, int n_tiles,
+                                                      int* entry_count) {
+  extern __shared__ unsigned s_bits[];
+  const int n_words = (g.n_cells + 31) >> 5;
+  unsigned* bm = SMEM ? s_bits : gbits;
+  if (SMEM) {
+    for (int w = threadIdx.x; w < n_words; w += 256) s_bits[w] = 0u;
+    __syncthreads();
   }
-  for (int step = 0; step <= steps; ++step) {
-    mark_cell(grid, g, cur[0], cur[1], cur[2]);
-    int mi = 0;
-    float mv = t_next[0];
-    if (t_next[1] < mv) {
-      mi = 1;
-      mv = t_next[1];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *entry_count = 0;  // consumed by k_view_compact_alloc (next launch)
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int ray_col = (tile % tiles_x) * 16 + (threadIdx.x & 15);
+    const int ray_row = (tile / tiles_x) * 16 + (threadIdx.x >> 4);
+    int prow = ray_row * sub, pcol = ray_col * sub;
+    if (prow >= rows + sub - 1 || pcol >= cols + sub - 1) continue;
+    if (prow >= rows) prow = rows - 1;
+    if (pcol >= cols) pcol = cols - 1;
+    float d = __ldg(depth + (size_t)prow * cols + pcol);
+    if (d <= 0.0f) continue;
+    if (max_dist > 0.0f && d > max_dist) d = max_dist;
+    const V3 ray = ray_from_image_plane(cam, (float)pcol + 0.5f, (float)prow + 0.5f);
+    const float len = d + behind;
+    V3 p_C;
+    p_C.x = len * ray.x;
+    p_C.y = len * ray.y;
+    p_C.z = len * ray.z;
+    const V3 p_L = xform(T_L_C, p_C);
+    const I3 b = block_index_from_position(block_size, p_L);
+    mark_cell<SMEM>(bm, g, b.x, b.y, b.z);
+
+    // RayCaster(origin / bs, p_L / bs), scale 1
+    const float s[3] = {(T_L_C.t[0] / block_size) / 1.0f, (T_L_C.t[1] / block_size) / 1.0f,
+                        (T_L_C.t[2] / block_size) / 1.0f};
+    const float e[3] = {(p_L.x / block_size) / 1.0f, (p_L.y / block_size) / 1.0f, (p_L.z / block_size) / 1.0f};
+    int cur[3], sign[3];
+    float t_next[3], t_step[3];
+    int steps = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      cur[i] = (int)floorf(s[i]);
+      const int end = (int)floorf(e[i]);
+      steps += abs(end - cur[i]);
+      const float r = e[i] - s[i];
+      sign[i] = (r > 0.0f) ? 1 : ((r < 0.0f) ? -1 : 0);
+      const int corrected = max(sign[i], 0);
+      const float shifted = s[i] - (float)cur[i];
+      const float dist = (float)corrected - shifted;
+      t_next[i] = dist / r;
+      t_step[i] = (float)sign[i] / r;
     }
-    if (t_next[2] < mv) {
-      mi = 2;
+    for (int step = 0; step <= steps; ++step) {
+      mark_cell<SMEM>(bm, g, cur[0], cur[1], cur[2]);
+      int mi = 0;
+      float mv = t_next[0];
+      if (t_next[1] < mv) {
+        mi = 1;
+        mv = t_next[1];
+      }
+      if (t_next[2] < mv) {
+        mi = 2;
+      }
+      // if-chain (not cur[mi]) keeps cur/t_next in registers
+      if (mi == 0) {
+        cur[0] += sign[0];
+        t_next[0] += t_step[0];
+      } else if (mi == 1) {
+        cur[1] += sign[1];
+        t_next[1] += t_step[1];
+      } else {
+        cur[2] += sign[2];
+        t_next[2] += t_step[2];
+      }
     }
-    // branch-free select keeps cur/t_next in registers
-    if (mi == 0) {
-      cur[0] += sign[0];
-      t_next[0] += t_step[0];
-    } else if (mi == 1) {
-      cur[1] += sign[1];
-      t_next[1] += t_step[1];
-    } else {
-      cur[2] += sign[2];
-      t_next[2] += t_step[2];
+  }
+  if (SMEM) {
+    __syncthreads();
+    for (int w = threadIdx.x; w < n_words; w += 256) {
+      const unsigned v = s_bits[w];
+      if (v && (__ldcg(&gbits[w]) & v) != v) atomicOr(&gbits[w], v);
     }
   }
 }
 
 // Number of marked cells (only launched while the block arena is still growing, see ensure_slots()).
-__global__ void __launch_bounds__(256) k_count_marked(const uint8_t* __restrict__ grid, int n_cells, int* out) {
+__global__ void __launch_bounds__(256) k_count_marked(const unsigned* __restrict__ gbits, int n_words, int* out) {
   int c = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += gridDim.x * blockDim.x) c += grid[i] ? 1 : 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) c += __popc(gbits[i]);
   for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if (lane_id() == 0 && c) atomicAdd(out, c);
 }
 
-// Zero one TSDF payload with the whole warp (4 KiB = 8 x 32 x 16 B).
-__device__ __forceinline__ void warp_zero_tsdf(const MapDev& m, int slot) {
-  uint4* p = reinterpret_cast<uint4*>(tsdf_block(m, slot));
-  const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) p[i * 32 + lane_id()] = z;
-}
-
-// Give `slot` a TSDF layer if it has none; returns true if the payload must be zeroed.
+// Give `slot` a TSDF layer if it has none; returns true if the payload is uninitialised (the TSDF update
+// that follows in stream order writes all 512 voxels of such a block, see k_tsdf_update).
 __device__ __forceinline__ bool ensure_tsdf_layer(const MapDev& m, int slot) {
   const uint8_t layers = m.blk_layers[slot];
   if (layers & kLayerTsdfBit) return false;
@@ -140,43 +166,41 @@ __device__ __forceinline__ bool ensure_tsdf_layer(const MapDev& m, int slot) {
   return true;
 }
 
-// Scan the marked grid -> block indices (appended to the viewpoint-cache entry), find-or-allocate each
-// block in the map, emit the slot list for the TSDF update.  Replaces the D2H copy + CPU scan + CPU
-// allocation + H2D pointer tables of view_calculator.cu:313-323 / layer_impl.h:130-162 /
-// integrators_common_impl.h:60-121.
-__global__ void __launch_bounds__(256) k_view_compact_alloc(MapDev m, const uint8_t* __restrict__ grid, ViewGrid g,
-                                                            int3* entry_idx, int* entry_count, int* view_slots) {
+// Scan the marked bitmap -> block indices (appended to the viewpoint-cache entry), find-or-allocate each
+// block in the map, emit the slot list for the TSDF update, and clear the bitmap for the next frame.
+// Replaces the D2H copy + CPU scan + CPU allocation + H2D pointer tables of view_calculator.cu:313-323 /
+// layer_impl.h:130-162 / integrators_common_impl.h:60-121.  One 32-cell word per warp, one cell per lane.
+__global__ void __launch_bounds__(256) k_view_compact_alloc(MapDev m, unsigned* gbits, ViewGrid g, int3* entry_idx,
+                                                            int* entry_count, int* view_slots) {
+  const int n_words = (g.n_cells + 31) >> 5;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = lane_id();
-  for (int base = warp * 32; base < g.n_cells; base += warps_total * 32) {
-    const int i = base + lane;
-    const bool marked = (i < g.n_cells) && grid[i];
-    const unsigned ballot = __ballot_sync(0xffffffffu, marked);
-    if (!ballot) continue;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps_total) {
+    const unsigned bits = gbits[w];
+    if (!bits) continue;
+    __syncwarp();
+    if (lane == 0) gbits[w] = 0u;  // self-cleaning: the bitmap is all-zero again when this kernel ends
     int pos0 = 0;
-    if (lane == 0) pos0 = atomicAdd(entry_count, __popc(ballot));
+    if (lane == 0) pos0 = atomicAdd(entry_count, __popc(bits));
     pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-    int slot = -1;
-    bool zero = false;
-    if (marked) {
+    bool fresh = false;
+    if ((bits >> lane) & 1u) {
+      const int i = (w << 5) + lane;
       const int x = i % g.sx + g.mn.x;
       const int y = (i / g.sx) % g.sy + g.mn.y;
       const int z = i / (g.sx * g.sy) + g.mn.z;
-      const int pos = pos0 + __popc(ballot & ((1u << lane) - 1u));
+      const int pos = pos0 + __popc(bits & ((1u << lane) - 1u));
       entry_idx[pos] = make_int3(x, y, z);
       bool is_new;
-      slot = acquire_slot(m, x, y, z, &is_new);
-      if (slot >= 0) zero = ensure_tsdf_layer(m, slot);
+      int slot = acquire_slot(m, x, y, z, &is_new);
+      if (slot >= 0 && ensure_tsdf_layer(m, slot)) {
+        slot |= kNewFlag;
+        fresh = true;
+      }
       view_slots[pos] = slot;
     }
-    unsigned zb = __ballot_sync(0xffffffffu, zero);
-    if (zb && lane == 0) count_add(m, kCntTsdfBlocksAllocated, __popc(zb));
-    while (zb) {
-      const int src = __ffs(zb) - 1;
-      zb &= zb - 1;
-      warp_zero_tsdf(m, __shfl_sync(0xffffffffu, slot, src));
-    }
+    const unsigned fb = __ballot_sync(0xffffffffu, fresh);
+    if (fb && lane == 0) count_add(m, kCntTsdfBlocksAllocated, __popc(fb));
   }
 }
 
@@ -185,34 +209,26 @@ __global__ void __launch_bounds__(256) k_view_compact_alloc(MapDev m, const uint
 __global__ void __launch_bounds__(256) k_view_alloc_from_list(MapDev m, const int3* __restrict__ entry_idx,
                                                               const int* __restrict__ entry_count, int* view_slots) {
   const int n = *entry_count;
-  const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = lane_id();
-  for (int base = warp * 32; base < n; base += warps_total * 32) {
-    const int i = base + lane;
-    int slot = -1;
-    bool zero = false;
-    if (i < n) {
-      const int3 b = entry_idx[i];
-      bool is_new;
-      slot = acquire_slot(m, b.x, b.y, b.z, &is_new);
-      if (slot >= 0) zero = ensure_tsdf_layer(m, slot);
-      view_slots[i] = slot;
+  unsigned n_new = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int3 b = entry_idx[i];
+    bool is_new;
+    int slot = acquire_slot(m, b.x, b.y, b.z, &is_new);
+    if (slot >= 0 && ensure_tsdf_layer(m, slot)) {
+      slot |= kNewFlag;
+      ++n_new;
     }
-    unsigned zb = __ballot_sync(0xffffffffu, zero);
-    if (zb && lane == 0) count_add(m, kCntTsdfBlocksAllocated, __popc(zb));
-    while (zb) {
-      const int src = __ffs(zb) - 1;
-      zb &= zb - 1;
-      warp_zero_tsdf(m, __shfl_sync(0xffffffffu, slot, src));
-    }
+    view_slots[i] = slot;
   }
+  if (n_new) count_add(m, kCntTsdfBlocksAllocated, n_new);
 }
 
 // ================================================================================================
 // a4. TSDF update.  integrateBlocksKernel<TsdfVoxel> (projective_integrator_impl.cuh:58-103) +
 // UpdateTsdfVoxelFunctor (projective_tsdf_integrator.cu:25-99).  One CTA of 512 threads per block,
 // thread t owns voxel t of the [x][y][z] array (z fastest -> 32 lanes read 256 contiguous bytes).
+// A block allocated by this frame (kNewFlag) is never read: its voxels start from (0, 0) and all 512
+// are written, which replaces the reference's per-block cudaMemset (blox_impl.h:92-97).
 // ================================================================================================
 struct DepthFrame {
   const float* depth;
@@ -248,35 +264,46 @@ __global__ void __launch_bounds__(512, 2) k_tsdf_update(MapDev m, const int* __r
   const int vx = t >> 6, vy = (t >> 3) & 7, vz = t & 7;
   unsigned updated = 0;
   for (int bi = blockIdx.x; bi < n; bi += gridDim.x) {
-    const int slot = view_slots[bi];
-    if (slot < 0) continue;
+    const int raw = view_slots[bi];
+    if (raw < 0) continue;
+    const bool is_new = (raw & kNewFlag) != 0;
+    const int slot = raw & kSlotMask;
     if (t == 0) m.blk_dirty[slot] = 1;  // blocks_to_update_tracker_.addBlocksToUpdate (mapper.cpp:406)
     const int3 b = m.blk_index[slot];
-    float u, v, vd;
-    if (!project_voxel(f.cam, f.T_C_L, m.block_size, f.max_depth, b, vx, vy, vz, &u, &v, &vd)) continue;
-    const int ui = (int)floorf(u), vi = (int)floorf(v);
-    if (ui < 0 || vi < 0 || ui >= f.cols || vi >= f.rows) continue;
-    const float meas = __ldg(f.depth + (size_t)vi * f.cols + ui);
-    if (isnan(meas)) continue;
-    const bool active = (f.mask == nullptr) || __ldg(f.mask + (size_t)vi * f.cols + ui);
     float2* vox = tsdf_block(m, slot) + t;
-    if (meas <= 0.0f) {
-      if (f.invalid_decay >= 0.0f) vox->y *= f.invalid_decay;
-      continue;
-    }
-    const float sdf = meas - vd;
-    if (sdf < -f.trunc) continue;
-    if (!active && sdf < f.trunc) continue;
-    const float2 cur = *vox;
-    const float w_m = weighting(f.weighting_mode, meas, vd, f.trunc);
-    float fused = (sdf * w_m + cur.x * cur.y) / (w_m + cur.y);
-    if (fused > 0.0f)
-      fused = fminf(f.trunc, fused);
-    else
-      fused = fmaxf(-f.trunc, fused);
-    const float w_new = fminf(w_m + cur.y, f.max_weight);
-    *vox = make_float2(fused, w_new);
-    ++updated;
+    bool write = is_new;
+    float2 out = make_float2(0.0f, 0.0f);
+    do {
+      float u, v, vd;
+      if (!project_voxel(f.cam, f.T_C_L, m.block_size, f.max_depth, b, vx, vy, vz, &u, &v, &vd)) break;
+      const int ui = (int)floorf(u), vi = (int)floorf(v);
+      if (ui < 0 || vi < 0 || ui >= f.cols || vi >= f.rows) break;
+      const float meas = __ldg(f.depth + (size_t)vi * f.cols + ui);
+      if (isnan(meas)) break;
+      const bool active = (f.mask == nullptr) || __ldg(f.mask + (size_t)vi * f.cols + ui);
+      if (meas <= 0.0f) {
+        if (f.invalid_decay >= 0.0f && !is_new) {
+          out = *vox;
+          out.y *= f.invalid_decay;
+          write = true;
+        }
+        break;
+      }
+      const float sdf = meas - vd;
+      if (sdf < -f.trunc) break;
+      if (!active && sdf < f.trunc) break;
+      const float2 cur = is_new ? make_float2(0.0f, 0.0f) : *vox;
+      const float w_m = weighting(f.weighting_mode, meas, vd, f.trunc);
+      float fused = (sdf * w_m + cur.x * cur.y) / (w_m + cur.y);
+      if (fused > 0.0f)
+        fused = fminf(f.trunc, fused);
+      else
+        fused = fmaxf(-f.trunc, fused);
+      out = make_float2(fused, fminf(w_m + cur.y, f.max_weight));
+      write = true;
+      ++updated;
+    } while (false);
+    if (write) *vox = out;
   }
   // accounting: one atomic per warp
   for (int o = 16; o; o >>= 1) updated += __shfl_xor_sync(0xffffffffu, updated, o);
@@ -288,109 +315,98 @@ __global__ void __launch_bounds__(512, 2) k_tsdf_update(MapDev m, const int* __r
 }
 
 // ================================================================================================
-// a6. Feature candidates.  getBlocksInViewPlanes (view_calculator.cu:392-470) on the device: one thread
-// per block of the frustum AABB, block-centre test against the normalised viewport (+10 px margin).
-// The reference enumerates x-outer / z-inner; the order of the list is irrelevant here.
-// ================================================================================================
-__global__ void __launch_bounds__(256) k_planes_view(ViewGrid g, float block_size, Pose T_C_L, float vmin_x,
-                                                     float vmin_y, float vmax_x, float vmax_y, int3* entry_idx,
-                                                     int* entry_count) {
-  const int stride = gridDim.x * blockDim.x;
-  for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < g.n_cells; base += stride) {
-    const int i = base + lane_id();
-    bool in_view = false;
-    int x = 0, y = 0, z = 0;
-    if (i < g.n_cells) {
-      x = i % g.sx + g.mn.x;
-      y = (i / g.sx) % g.sy + g.mn.y;
-      z = i / (g.sx * g.sy) + g.mn.z;
-      V3 c;
-      c.x = block_size * ((float)x + 0.5f);
-      c.y = block_size * ((float)y + 0.5f);
-      c.z = block_size * ((float)z + 0.5f);
-      const V3 r = rotate(T_C_L, c);
-      const float px = r.x + T_C_L.t[0], py = r.y + T_C_L.t[1], pz = r.z + T_C_L.t[2];
-      if (pz > 1e-6f) {
-        const float un = px / pz, vn = py / pz;
-        in_view = (vmin_x <= un) && (vmin_y <= vn) && (un <= vmax_x) && (vn <= vmax_y);
-      }
-    }
-    const unsigned ballot = __ballot_sync(0xffffffffu, in_view);
-    if (!ballot) continue;
-    int pos0 = 0;
-    if (lane_id() == 0) pos0 = atomicAdd(entry_count, __popc(ballot));
-    pos0 = __shfl_sync(0xffffffffu, pos0, 0);
-    if (in_view) entry_idx[pos0 + __popc(ballot & ((1u << lane_id()) - 1u))] = make_int3(x, y, z);
-  }
-}
-
+// a6. Feature candidates.  getBlocksInViewPlanes (view_calculator.cu:392-470) +
 // reduceBlocksToThoseInTruncationBand (projective_appearance_integrator.cu:374-477) + feature block
-// allocation (:120-123), one warp per candidate: hash probe, 4 KiB band scan with early exit,
-// feature-slot pop.  Emits the band list and the list of freshly allocated feature slots.
-__global__ void __launch_bounds__(256) k_band_select(MapDev m, const int3* __restrict__ entry_idx,
-                                                     const int* __restrict__ entry_count, float trunc,
-                                                     int* band_slots, int* newfeat_slots) {
-  const int n = *entry_count;
-  const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = lane_id();
-  unsigned cand = 0;
-  for (int i = warp; i < n; i += warps_total) {
-    int slot = -1;
-    if (lane == 0) {
-      const int3 b = entry_idx[i];
-      slot = hash_find(m, b.x, b.y, b.z);
-      if (slot >= 0 && !(m.blk_layers[slot] & kLayerTsdfBit)) slot = -1;
-    }
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    if (slot < 0) continue;
-    ++cand;
-    const float4* p = reinterpret_cast<const float4*>(tsdf_block(m, slot));
-    bool in_band = false;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float4 q = p[k * 32 + lane];  // two voxels: (d, w, d, w)
-      const bool hit = (q.y > 0.0f && fabsf(q.x) < trunc) || (q.w > 0.0f && fabsf(q.z) < trunc);
-      if (__any_sync(0xffffffffu, hit)) {
-        in_band = true;
-        break;
+// allocation (:120-123) in ONE kernel.  Lanes test 32 cells of the frustum AABB in parallel (block
+// centre against the normalised viewport widened by 10 px, then one index lookup); the warp then scans
+// each surviving TSDF block (4 KiB, all eight 128-bit loads of a lane in flight at once) for a voxel
+// with w > 0 and |d| < trunc, and pops a feature slot for band blocks that have none.
+// `view` carries the pose / camera / AABB the viewpoint cache holds for this call (Q6): on a cache hit
+// those are the CACHED ones, which reproduces the reference re-using its cached index list.
+// ================================================================================================
+struct PlanesView {
+  ViewGrid g;
+  Pose T_C_L;
+  float vmin_x, vmin_y, vmax_x, vmax_y;
+};
+
+// One tile = `tile_cells` consecutive cells of the AABB (a multiple of 32, <= 256): phase 1 tests one cell
+// per thread and compacts the surviving slots into shared memory, phase 2 deals them to the CTA's warps.
+// Small tiles spread the few hundred candidates of a mindmap workspace over many SMs.
+__device__ __forceinline__ void band_select_tile(const MapDev& m, const PlanesView& view, float trunc,
+                                                 int* band_slots, int tile, int tile_cells, int* s_cand,
+                                                 int* s_ncand) {
+  const ViewGrid& g = view.g;
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) *s_ncand = 0;
+  __syncthreads();
+  const int i = tile * tile_cells + threadIdx.x;
+  int slot = -1;
+  if (threadIdx.x < tile_cells && i < g.n_cells) {
+    const int x = i % g.sx + g.mn.x;
+    const int y = (i / g.sx) % g.sy + g.mn.y;
+    const int z = i / (g.sx * g.sy) + g.mn.z;
+    V3 c;
+    c.x = m.block_size * ((float)x + 0.5f);
+    c.y = m.block_size * ((float)y + 0.5f);
+    c.z = m.block_size * ((float)z + 0.5f);
+    const V3 r = rotate(view.T_C_L, c);
+    const float px = r.x + view.T_C_L.t[0], py = r.y + view.T_C_L.t[1], pz = r.z + view.T_C_L.t[2];
+    if (pz > 1e-6f) {
+      const float un = px / pz, vn = py / pz;
+      if ((view.vmin_x <= un) && (view.vmin_y <= vn) && (un <= view.vmax_x) && (vn <= view.vmax_y)) {
+        slot = find_slot(m, x, y, z);
+        if (slot >= 0 && !(m.blk_layers[slot] & kLayerTsdfBit)) slot = -1;
       }
     }
-    if (!in_band) continue;
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, slot >= 0);
+  if (ballot) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(s_ncand, __popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (slot >= 0) s_cand[base + __popc(ballot & ((1u << lane) - 1u))] = slot;
+  }
+  __syncthreads();
+  const int n_cand = *s_ncand;
+  for (int k = warp; k < n_cand; k += (blockDim.x >> 5)) {
+    const int s = s_cand[k];
+    const float4* p = reinterpret_cast<const float4*>(tsdf_block(m, s));
+    float4 q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q[j] = p[j * 32 + lane];  // two voxels each: (d, w, d, w)
+    bool hit = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      hit |= (q[j].y > 0.0f && fabsf(q[j].x) < trunc) || (q[j].w > 0.0f && fabsf(q[j].z) < trunc);
+    if (!__any_sync(0xffffffffu, hit)) continue;
     if (lane == 0) {
-      if (m.blk_feat[slot] < 0) {
-        const int fs = pop_id(&m.ctrl->feat_free_top, &m.ctrl->feat_high, m.feat_free, m.feat_capacity,
-                              &m.ctrl->overflow);
+      int flag = 0;
+      if (m.blk_feat[s] < 0) {
+        const int fs =
+            pop_id(&m.ctrl->feat_free_top, &m.ctrl->feat_high, m.feat_free, m.feat_capacity, &m.ctrl->overflow);
         if (fs >= 0) {
-          m.blk_feat[slot] = fs;
-          m.blk_layers[slot] |= kLayerFeatBit;
+          m.blk_feat[s] = fs;
+          m.blk_layers[s] |= kLayerFeatBit;
           atomicAdd(&m.ctrl->n_feat, 1);
-          newfeat_slots[atomicAdd(&m.ctrl->newfeat_count, 1)] = fs;
           count_add(m, kCntFeatBlocksAllocated, 1);
+          flag = kNewFlag;  // zero-filled by k_feature_geometry
         }
       }
-      if (m.blk_feat[slot] >= 0) band_slots[atomicAdd(&m.ctrl->band_count, 1)] = slot;
+      if (m.blk_feat[s] >= 0) band_slots[atomicAdd(&m.ctrl->band_count, 1)] = s | flag;
     }
   }
-  if (lane == 0 && cand) count_add(m, kCntFeatCandidateBlocks, cand);
-}
-
-// Zero-fill freshly allocated feature blocks (the reference memsets every new block:
-// NB/include/nvblox/map/internal/impl/blox_impl.h:92-97).
-__global__ void __launch_bounds__(256) k_zero_feature_blocks(MapDev m, const int* __restrict__ newfeat_slots) {
-  const int n = m.ctrl->newfeat_count;
-  const int vec_per_block = (kVoxelsPerBlock * m.row) / 8;
-  const uint4 z = make_uint4(0, 0, 0, 0);
-  for (int i = blockIdx.x; i < n; i += gridDim.x) {
-    uint4* p = reinterpret_cast<uint4*>(feat_block(m, newfeat_slots[i]));
-    for (int k = threadIdx.x; k < vec_per_block; k += blockDim.x) p[k] = z;
-  }
+  if (threadIdx.x == 0 && n_cand) count_add(m, kCntFeatCandidateBlocks, (unsigned)n_cand);
+  __syncthreads();  // s_cand / s_ncand are reused by the CTA's next tile
 }
 
 // ================================================================================================
 // a7. Synthetic depth by sphere tracing.  sphereTracingKernel + cast (sphere_tracer.cu:31-131,191-236).
-// One thread per ray; the last block hit is cached in registers so consecutive samples inside one
-// block cost no hash probe.
+// One thread per ray.  Block lookups go through the direct-mapped workspace grid (one L1-resident load);
+// the last block is cached in registers so consecutive samples inside one block cost no lookup; a ray
+// that has left the workspace grid moving away from it can never see a valid sample again, so it is
+// terminated at once (the reference keeps stepping by the truncation distance until 7 m / 100 steps and
+// then reports the same miss).
 // ================================================================================================
 struct TraceParams {
   Cam cam;
@@ -403,10 +419,19 @@ struct TraceParams {
   int rows, cols;  // synthetic image size
 };
 
-__global__ void __launch_bounds__(64) k_sphere_trace(MapDev m, TraceParams tp, float* __restrict__ image) {
-  const int c = threadIdx.x % 8 + blockIdx.x * 8;
-  const int r = threadIdx.x / 8 + blockIdx.y * 8;
-  if (r >= tp.rows || c >= tp.cols) return;
+// floor(p / block_size) exactly as block_index_from_position computes it, without the IEEE division on
+// the common path: q = p * (1/bs) is within |q| * 2^-22 of the true quotient, so when q sits farther than
+// 1e-4 from an integer (and |q| < 256) its floor is the floor of the correctly rounded quotient too.
+__device__ __forceinline__ int floor_div_exact(float p, float bs, float bs_inv) {
+  const float q = p * bs_inv;
+  const float fl = floorf(q);
+  const float fr = q - fl;
+  if (fr > 1e-4f && fr < 1.0f - 1e-4f && fabsf(q) < 256.0f) return (int)fl;
+  return (int)floorf(p / bs);
+}
+
+__device__ __forceinline__ void sphere_trace_ray(const MapDev& m, const TraceParams& tp, int r, int c,
+                                                 float* __restrict__ image) {
   const float pu = (float)(c * tp.sub) + 0.5f * (float)tp.sub * 1.0f;
   const float pv = (float)(r * tp.sub) + 0.5f * (float)tp.sub * 1.0f;
   const V3 ray = ray_from_image_plane(tp.cam, pu, pv);
@@ -420,6 +445,11 @@ __global__ void __launch_bounds__(64) k_sphere_trace(MapDev m, TraceParams tp, f
   }
   const V3 dl = rotate(tp.T_L_C, dc);
   const float ox = tp.T_L_C.t[0], oy = tp.T_L_C.t[1], oz = tp.T_L_C.t[2];
+  // every block lives inside the workspace grid: leaving it for good ends the march
+  const bool closed_world = (m.ws_sx > 0) && (m.ctrl->n_hash == 0);
+  const I3 ws_mx = {m.ws_mn.x + m.ws_sx - 1, m.ws_mn.y + m.ws_sy - 1, m.ws_mn.z + m.ws_sz - 1};
+  const float bs = m.block_size, bs_inv = 1.0f / m.block_size;
+  float2* const slab0 = m.tsdf_slabs[0];
 
   int first = 0;
   float t = 0.0f;
@@ -427,17 +457,36 @@ __global__ void __launch_bounds__(64) k_sphere_trace(MapDev m, TraceParams tp, f
   I3 cached_b;
   cached_b.x = cached_b.y = cached_b.z = 0x7fffffff;
   const float2* cached_ptr = nullptr;
+  int n_steps = 0;
   for (int i = 0; (i < tp.max_steps) && (t < tp.max_ray_length); ++i) {
+    n_steps = i + 1;
     V3 p;
     p.x = ox + t * dl.x;
     p.y = oy + t * dl.y;
     p.z = oz + t * dl.z;
+    // getBlockAndVoxelIndexFromPositionInLayer (indexing_impl.h:37-49)
     I3 b, v;
-    block_and_voxel_from_position(m.block_size, m.voxel_size_inv, p, &b, &v);
+    b.x = floor_div_exact(p.x, bs, bs_inv);
+    b.y = floor_div_exact(p.y, bs, bs_inv);
+    b.z = floor_div_exact(p.z, bs, bs_inv);
+    v.x = min((int)((p.x - bs * (float)b.x) * m.voxel_size_inv), 7);
+    v.y = min((int)((p.y - bs * (float)b.y) * m.voxel_size_inv), 7);
+    v.z = min((int)((p.z - bs * (float)b.z) * m.voxel_size_inv), 7);
     if (b.x != cached_b.x || b.y != cached_b.y || b.z != cached_b.z) {
       cached_b = b;
-      const int slot = hash_find(m, b.x, b.y, b.z);
-      cached_ptr = (slot >= 0 && (m.blk_layers[slot] & kLayerTsdfBit)) ? tsdf_block(m, slot) : nullptr;
+      // A slot without a TSDF layer has an all-zero TSDF payload (k_allocate_one), i.e. reads as
+      // unobserved, so the layer bits need not be consulted here.
+      const int slot = find_slot(m, b.x, b.y, b.z);
+      cached_ptr = nullptr;
+      if (slot >= 0)
+        cached_ptr = (slot < (1 << kTsdfSlabShift)) ? slab0 + (size_t)slot * kVoxelsPerBlock : tsdf_block(m, slot);
+      if (closed_world && slot < 0) {
+        // t only grows (steps are >= 0), so each coordinate of p moves monotonically along sign(dl)
+        const bool gone = (b.x > ws_mx.x && dl.x >= 0.0f) || (b.x < m.ws_mn.x && dl.x <= 0.0f) ||
+                          (b.y > ws_mx.y && dl.y >= 0.0f) || (b.y < m.ws_mn.y && dl.y <= 0.0f) ||
+                          (b.z > ws_mx.z && dl.z >= 0.0f) || (b.z < m.ws_mn.z && dl.z <= 0.0f);
+        if (gone) break;  // miss
+      }
     }
     bool valid = false;
     float dist = 0.0f;
@@ -476,23 +525,59 @@ __global__ void __launch_bounds__(64) k_sphere_trace(MapDev m, TraceParams tp, f
     t += step;
   }
   image[(size_t)r * tp.cols + c] = ok ? t * dc.z : -1.0f;
+#ifdef NVBX_PROFILE_COUNTERS
+  atomicAdd(&m.ctrl->counters[12], (unsigned long long)n_steps);
+  atomicMax(&m.ctrl->counters[13], (unsigned long long)n_steps);
+#endif
+}
+
+// The two independent, latency-bound preparations of a feature frame in ONE launch: CTAs
+// [0, n_trace_ctas) sphere-trace 16x16 tiles of the synthetic depth image, the remaining CTAs run
+// band_select_tile.  Both only read the TSDF layer; they overlap instead of queueing.
+__global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp, float* __restrict__ image,
+                                                        int trace_tiles_x, int n_trace_ctas, PlanesView view,
+                                                        float trunc, int* band_slots, int tile_cells, int n_tiles) {
+  __shared__ int s_cand[256];
+  __shared__ int s_ncand;
+#ifdef NVBX_PROFILE_COUNTERS
+  const long long t0 = clock64();
+#endif
+  if ((int)blockIdx.x < n_trace_ctas) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) m.ctrl->item_count = 0;  // consumed by k_feature_geometry
+    const int c = (blockIdx.x % trace_tiles_x) * 16 + (threadIdx.x & 7) + ((threadIdx.x >> 7) << 3);
+    const int r = (blockIdx.x / trace_tiles_x) * 16 + ((threadIdx.x >> 3) & 15);
+    if (r < tp.rows && c < tp.cols) sphere_trace_ray(m, tp, r, c, image);
+#ifdef NVBX_PROFILE_COUNTERS
+    atomicMax(&m.ctrl->counters[14], (unsigned long long)(clock64() - t0));
+#endif
+    return;
+  }
+  for (int tile = (int)blockIdx.x - n_trace_ctas; tile < n_tiles; tile += (int)gridDim.x - n_trace_ctas)
+    band_select_tile(m, view, trunc, band_slots, tile, tile_cells, s_cand, &s_ncand);
+#ifdef NVBX_PROFILE_COUNTERS
+  if (threadIdx.x == 0) atomicMax(&m.ctrl->counters[15], (unsigned long long)(clock64() - t0));
+#endif
 }
 
 // ================================================================================================
-// a8. Feature integration -- THE hot kernel.
+// a8. Feature integration -- THE hot path, in two kernels.
 //
 // Reference: integrateBlocksKernel<UpdateAppearanceVoxelFunctor<FeatureVoxel>> (projective_integrator_
 // impl.cuh:156-214) runs one THREAD per voxel that serially walks all C channels through three
-// 1.5 KB per-thread arrays and a 2-byte-aligned 1538-byte AoS record.  Here one CTA owns one voxel
-// block:
-//   phase 1 (thread = voxel): geometry only -- project, bilinear synthetic depth, band test, image
-//     bounds, mask, old weight -> a compacted list of work items in shared memory;
-//   phase 2 (warp = work item): the 32 lanes sweep the C channels as 16-byte vectors: four 128-bit
-//     read-only loads per vector (the 4 bilinear neighbours, each C contiguous halves in the HWC
-//     image), fp16 interpolation/blend in the reference's operation order on half2 lanes, one 128-bit
-//     store into the voxel's 16-byte-aligned row.  Voxels adjacent in z are consecutive work items and
-//     mostly share pixel rows, so re-reads hit L1/L2, not HBM.
-// Algorithmic bytes per updated voxel: 2C x (distinct pixels, <= 4) read + 2(C+8) written
+// 1.5 KB per-thread arrays and a 2-byte-aligned 1538-byte AoS record.  Here:
+//
+//   k_feature_geometry (thread = voxel, CTA = band block; fp32 geometry only): project, bilinear
+//     synthetic depth, band test, image bounds, mask, old weight -> 16-byte work items appended to ONE
+//     global list (one atomicAdd per block).  Only ~1/3 of a band block's voxels survive and there are
+//     fewer band blocks than SMs on the mindmap tasks, so doing the byte-moving per block would leave
+//     most of the machine idle; the list is what balances it.
+//   k_feature_gather (warp = 512-byte chunk of one item's channel vector; persistent, grid = SMs x 4):
+//     four 128-bit read-only loads per lane (the 4 bilinear neighbours, each C contiguous halves in the
+//     HWC image), fp16 interpolation / blend in the reference's operation order on half2 lanes, one
+//     128-bit store into the voxel's 16-byte-aligned row.  Units are dealt round-robin over all warps
+//     of the grid and every lane keeps two units (eight loads) in flight.
+//
+// Algorithmic bytes per updated voxel: 2C x (distinct pixels, <= 4) read + 2(C+1) written
 // (+ 2C read when the old feature must be blended).
 // ================================================================================================
 struct FeatFrame {
@@ -543,39 +628,47 @@ __device__ __forceinline__ uint4 blend_vec(uint4 oldv, uint4 meas, __half2 w1, _
 }
 __device__ __forceinline__ uint4 ldg_nc(const uint4* p) { return __ldg(p); }
 
-struct FeatItem {
+// One voxel to update (16 bytes, moved as one uint4).
+struct __align__(16) FeatItem {
   int pix;                // (ly * cols + lx): offset of the top-left neighbour in pixels
   unsigned short hx, hy;  // half bits of the interpolation offsets
   unsigned short wnew;    // half bits of the new weight
-  unsigned short vox;     // voxel linear id | (first-observation flag << 15)
+  unsigned short first;   // 1: first observation (copy, no blend)
+  int row;                // feature voxel row: feature_slot * 512 + voxel
 };
 
-template <int VPL>  // 16-byte vectors per lane (C = 256 * VPL); 0 = any C (multiple of 8)
-__global__ void __launch_bounds__(512, 2) k_feature_integrate(MapDev m, const int* __restrict__ band_slots,
-                                                              FeatFrame f) {
-  __shared__ FeatItem s_items[kVoxelsPerBlock];
+__global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* __restrict__ band_slots, FeatFrame f,
+                                                          FeatItem* __restrict__ items, int block_begin,
+                                                          int block_end) {
   __shared__ int s_warp_base[17];
-  const int n = m.ctrl->band_count;
+  __shared__ int s_base;
+  const int n = min(m.ctrl->band_count, block_end);
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
   const int vx = t >> 6, vy = (t >> 3) & 7, vz = t & 7;
   const int C = m.C;
-  const int nvec = C >> 3;
-  const __half2 w1 = __half2half2(__ushort_as_half(f.h_w1));
-  const __half2 w2 = __half2half2(__ushort_as_half(f.h_w2));
   unsigned long long n_updated = 0;
 
-  for (int bi = blockIdx.x; bi < n; bi += gridDim.x) {
-    const int slot = band_slots[bi];
+  for (int bi = block_begin + blockIdx.x; bi < n; bi += gridDim.x) {
+    const int raw = band_slots[bi];
+    const bool is_new = (raw & kNewFlag) != 0;
+    const int slot = raw & kSlotMask;
     const int3 b = m.blk_index[slot];
-    __half* blk = feat_block(m, m.blk_feat[slot]);
+    const int fs = m.blk_feat[slot];
+    __half* blk = feat_block(m, fs);
     if (t == 0) m.blk_dirty[slot] = 1;  // mapper.cpp:462
+    if (is_new) {                       // zero-fill (blox_impl.h:92-97); the gather kernel runs after us
+      uint4* p = reinterpret_cast<uint4*>(blk);
+      const int vec_per_block = (kVoxelsPerBlock * m.row) / 8;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      for (int k = t; k < vec_per_block; k += 512) p[k] = z;
+    }
 
-    // ---- phase 1: geometry, one thread per voxel -------------------------------------------------
     bool active = false;
     FeatItem it;
     it.pix = 0;
-    it.hx = it.hy = it.wnew = it.vox = 0;
+    it.hx = it.hy = it.wnew = it.first = 0;
+    it.row = fs * kVoxelsPerBlock + t;
     do {
       float u, v, vd;
       if (!project_voxel(f.cam, f.T_C_L, m.block_size, f.max_depth, b, vx, vy, vz, &u, &v, &vd)) break;
@@ -591,17 +684,16 @@ __global__ void __launch_bounds__(512, 2) k_feature_integrate(MapDev m, const in
       const int px = (int)floorf(fu), py = (int)floorf(fv);
       if (px < 0 || py < 0 || (px + 1) > (f.cols - 1) || (py + 1) > (f.rows - 1)) break;
       if (f.mask != nullptr && !__ldg(f.mask + (size_t)((int)v) * f.cols + (int)u)) break;
-      const __half w_cur_h = blk[(size_t)t * m.row + C];
-      const float w_cur = __half2float(w_cur_h);
+      const float w_cur = is_new ? 0.0f : __half2float(blk[(size_t)t * m.row + C]);
       it.pix = py * f.cols + px;
       it.hx = __half_as_ushort(__float2half_rn(fu - (float)px));
       it.hy = __half_as_ushort(__float2half_rn(fv - (float)py));
       it.wnew = __half_as_ushort(__float2half_rn(fminf(f.alpha + w_cur, f.max_weight)));
-      it.vox = (unsigned short)(t | ((w_cur == 0.0f) ? 0x8000 : 0));
+      it.first = (w_cur == 0.0f) ? 1 : 0;
       active = true;
     } while (false);
 
-    // ---- compaction (ballot + 16-entry scan) ----------------------------------------------------
+    // block-level compaction: ballot + 16-entry scan, one atomicAdd per block on the global list
     const unsigned ballot = __ballot_sync(0xffffffffu, active);
     if (lane == 0) s_warp_base[warp + 1] = __popc(ballot);
     __syncthreads();
@@ -613,60 +705,84 @@ __global__ void __launch_bounds__(512, 2) k_feature_integrate(MapDev m, const in
         acc += s_warp_base[w];
         s_warp_base[w] = acc;
       }
+      s_base = acc ? atomicAdd(&m.ctrl->item_count, acc) : 0;
+      n_updated += (unsigned long long)acc;
     }
     __syncthreads();
-    if (active) s_items[s_warp_base[warp] + __popc(ballot & ((1u << lane) - 1u))] = it;
-    const int n_items = s_warp_base[16];
-    __syncthreads();
-
-    // ---- phase 2: one warp per work item, lanes sweep the channels ----------------------------------
-    for (int i = warp; i < n_items; i += 16) {
-      const FeatItem w = s_items[i];
-      const int vox = w.vox & 0x1ff;
-      const bool first = (w.vox & 0x8000) != 0;
-      const __half hx = __ushort_as_half(w.hx), hy = __ushort_as_half(w.hy);
-      const __half2 x2 = __half2half2(hx), y2 = __half2half2(hy), xy2 = __half2half2(__hmul_rn(hx, hy));
-      const uint4* p00 = reinterpret_cast<const uint4*>(f.img + (size_t)w.pix * C);
-      const uint4* p10 = p00 + nvec;
-      const uint4* p01 = p00 + (size_t)f.cols * nvec;
-      const uint4* p11 = p01 + nvec;
-      uint4* dst = reinterpret_cast<uint4*>(blk + (size_t)vox * m.row);
-      const bool blend = (!first) && f.read_old;
-      if (VPL > 0) {
-        uint4 a00[VPL > 0 ? VPL : 1], a01[VPL > 0 ? VPL : 1], a10[VPL > 0 ? VPL : 1], a11[VPL > 0 ? VPL : 1];
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) {  // all loads first: 4*VPL 128-bit requests in flight per lane
-          const int c = lane + 32 * k;
-          a00[k] = ldg_nc(p00 + c);
-          a10[k] = ldg_nc(p10 + c);
-          a01[k] = ldg_nc(p01 + c);
-          a11[k] = ldg_nc(p11 + c);
-        }
-#pragma unroll
-        for (int k = 0; k < VPL; ++k) {
-          const int c = lane + 32 * k;
-          uint4 o = interp_vec(x2, y2, xy2, a00[k], a01[k], a10[k], a11[k]);
-          if (blend) o = blend_vec(dst[c], o, w1, w2);
-          dst[c] = o;
-        }
-      } else {
-        for (int c = lane; c < nvec; c += 32) {
-          uint4 o = interp_vec(x2, y2, xy2, ldg_nc(p00 + c), ldg_nc(p01 + c), ldg_nc(p10 + c), ldg_nc(p11 + c));
-          if (blend) o = blend_vec(dst[c], o, w1, w2);
-          dst[c] = o;
-        }
-      }
-      if (lane == 0) dst[nvec] = make_uint4((unsigned)w.wnew, 0u, 0u, 0u);  // weight + zero padding
-    }
-    if (t == 0) n_updated += (unsigned long long)n_items;
-    __syncthreads();  // s_items / s_warp_base are reused by the next block
+    if (active)
+      *reinterpret_cast<uint4*>(&items[s_base + s_warp_base[warp] + __popc(ballot & ((1u << lane) - 1u))]) =
+          *reinterpret_cast<const uint4*>(&it);
+    __syncthreads();  // s_warp_base / s_base are reused by the next block
   }
   if (t == 0) {
     if (n_updated) count_add(m, kCntFeatVoxelsUpdated, n_updated);
-    if (blockIdx.x == 0) {
-      count_add(m, kCntFeatBandBlocks, (unsigned long long)n);
+    if (blockIdx.x == 0 && block_begin == 0) {
+      count_add(m, kCntFeatBandBlocks, (unsigned long long)m.ctrl->band_count);
       count_add(m, kCntFeatureFrames, 1);
     }
+  }
+}
+
+// CH: 512-byte chunks (32 lanes x 16 B) per channel vector, C = 256 * CH; 0 = any C (multiple of 8).
+template <int CH, int U, int CTAS>  // U: units in flight per warp; CTAS: resident CTAs per SM (register budget)
+__global__ void __launch_bounds__(256, CTAS) k_feature_gather(MapDev m, const FeatItem* __restrict__ items,
+                                                              FeatFrame f, int last_chunk) {
+  const int n_items = m.ctrl->item_count;
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int C = m.C;
+  const int nvec = C >> 3;
+  const int ch_per_item = CH > 0 ? CH : ((nvec + 31) >> 5);
+  const long long n_units = (long long)n_items * ch_per_item;
+  const __half2 w1 = __half2half2(__ushort_as_half(f.h_w1));
+  const __half2 w2 = __half2half2(__ushort_as_half(f.h_w2));
+  const size_t row_vecs = (size_t)(m.row >> 3);
+
+  for (long long q0 = warp; q0 < n_units; q0 += (long long)U * warps_total) {
+    uint4 a00[U], a01[U], a10[U], a11[U], old[U];
+    FeatItem it[U];
+    int cvec[U];
+    bool live[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const long long q = q0 + (long long)k * warps_total;
+      live[k] = q < n_units;
+      const int item = live[k] ? (int)(q / ch_per_item) : 0;
+      cvec[k] = (int)(q - (long long)item * ch_per_item) * 32 + lane;
+      if (CH == 0 && cvec[k] >= nvec) live[k] = false;
+      *reinterpret_cast<uint4*>(&it[k]) = __ldg(reinterpret_cast<const uint4*>(items + item));
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      if (live[k]) {
+        const uint4* p00 = reinterpret_cast<const uint4*>(f.img + (size_t)it[k].pix * C) + cvec[k];
+        const uint4* p01 = p00 + (size_t)f.cols * nvec;
+        a00[k] = ldg_nc(p00);
+        a10[k] = ldg_nc(p00 + nvec);
+        a01[k] = ldg_nc(p01);
+        a11[k] = ldg_nc(p01 + nvec);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      if (live[k]) {
+        const int fslot = it[k].row >> 9, vox = it[k].row & 511;
+        uint4* dst = reinterpret_cast<uint4*>(feat_block(m, fslot)) + (size_t)vox * row_vecs;
+        const bool blend = (!it[k].first) && f.read_old;
+        if (blend) old[k] = dst[cvec[k]];
+        const __half hx = __ushort_as_half(it[k].hx), hy = __ushort_as_half(it[k].hy);
+        uint4 o = interp_vec(__half2half2(hx), __half2half2(hy), __half2half2(__hmul_rn(hx, hy)), a00[k], a01[k],
+                             a10[k], a11[k]);
+        if (blend) o = blend_vec(old[k], o, w1, w2);
+        dst[cvec[k]] = o;
+        if (cvec[k] == 0) dst[nvec] = make_uint4((unsigned)it[k].wnew, 0u, 0u, 0u);  // weight + zero padding
+      }
+    }
+  }
+  if (last_chunk && blockIdx.x == 0 && threadIdx.x == 0) {
+    m.ctrl->last_band_count = m.ctrl->band_count;
+    m.ctrl->band_count = 0;  // ready for the next frame's k_band_select
   }
 }
 
@@ -720,8 +836,8 @@ __global__ void __launch_bounds__(256) k_decay(MapDev m, DecayParams dp) {
         }
         m.blk_mesh[slot] = make_int4(0, 0, 0, 0);
         m.blk_dirty[slot] = 0;
+        unindex_slot(m, slot);
         push_id(&m.ctrl->slot_free_top, m.slot_free, slot);
-        m.ctrl->rebuild = 1;
         count_add(m, kCntBlocksDeallocated, 1);
       } else {
         m.blk_dirty[slot] = 1;  // decayTsdf marks every TSDF block "to update" (mapper.cpp:469-471)
@@ -730,7 +846,8 @@ __global__ void __launch_bounds__(256) k_decay(MapDev m, DecayParams dp) {
   }
 }
 
-// Hash rebuild after releases (three tiny launches, all no-ops unless ctrl->rebuild is set).
+// Overflow-hash rebuild after releases of hash-resident blocks (three tiny launches, all no-ops unless
+// ctrl->rebuild is set; blocks inside the workspace grid never set it).
 __global__ void __launch_bounds__(256) k_hash_clear(MapDev m, int force) {
   if (!force && !m.ctrl->rebuild) return;
   const unsigned n = m.hash_mask + 1;
@@ -742,7 +859,7 @@ __global__ void __launch_bounds__(256) k_hash_reinsert(MapDev m, int force) {
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     if (m.blk_layers[s]) {
       const int3 b = m.blk_index[s];
-      hash_insert(m, b.x, b.y, b.z, s);
+      if (ws_cell(m, b.x, b.y, b.z) < 0) hash_insert(m, b.x, b.y, b.z, s);
     }
   }
 }
@@ -752,8 +869,12 @@ __global__ void k_hash_rebuild_done(MapDev m) { m.ctrl->rebuild = 0; }
 __global__ void __launch_bounds__(256) k_clear_all(MapDev m) {
   const unsigned n = m.hash_mask + 1;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m.keys[i] = kEmptyKey;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.ws_cells; i += gridDim.x * blockDim.x) m.ws_slot[i] = -1;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     Ctrl* c = m.ctrl;
+    c->n_hash = 0;
+    c->band_count = 0;
+    c->item_count = 0;
     c->slot_free_top = 0;
     c->slot_high = 0;
     c->feat_free_top = 0;
@@ -785,11 +906,13 @@ __global__ void k_allocate_one(MapDev m, int x, int y, int z, int layer, int* ne
   const int slot = acquire_slot(m, x, y, z, &is_new);
   *newfeat_slot_out = -1;
   if (slot < 0) return;
+  // invariant relied on by k_sphere_trace: a slot's TSDF payload is zero unless it holds a TSDF layer
+  if (is_new || (layer == 0 && !(m.blk_layers[slot] & kLayerTsdfBit))) {
+    float2* p = tsdf_block(m, slot);
+    for (int i = 0; i < kVoxelsPerBlock; ++i) p[i] = make_float2(0.f, 0.f);
+  }
   if (layer == 0) {
-    if (ensure_tsdf_layer(m, slot)) {
-      float2* p = tsdf_block(m, slot);
-      for (int i = 0; i < kVoxelsPerBlock; ++i) p[i] = make_float2(0.f, 0.f);
-    }
+    ensure_tsdf_layer(m, slot);
   } else if (m.blk_feat[slot] < 0) {
     const int fs =
         pop_id(&m.ctrl->feat_free_top, &m.ctrl->feat_high, m.feat_free, m.feat_capacity, &m.ctrl->overflow);
@@ -809,7 +932,7 @@ __global__ void k_zero_one_feature_block(MapDev m, const int* fslot) {
     p[k] = make_uint4(0, 0, 0, 0);
 }
 __global__ void k_find_one(MapDev m, int x, int y, int z, int layer, unsigned long long* ptr_out) {
-  const int slot = hash_find(m, x, y, z);
+  const int slot = find_slot(m, x, y, z);
   *ptr_out = 0ull;
   if (slot < 0) return;
   if (layer == 0) {
@@ -830,7 +953,7 @@ __global__ void __launch_bounds__(128) k_query_tsdf(MapDev m, const float* __res
   p.z = xyz[3 * i + 2];
   I3 b, v;
   block_and_voxel_from_position(m.block_size, m.voxel_size_inv, p, &b, &v);
-  const int slot = hash_find(m, b.x, b.y, b.z);
+  const int slot = find_slot(m, b.x, b.y, b.z);
   if (slot < 0 || !(m.blk_layers[slot] & kLayerTsdfBit)) return;
   out[i] = tsdf_block(m, slot)[(v.x * 8 + v.y) * 8 + v.z];
 }
@@ -846,7 +969,7 @@ __global__ void __launch_bounds__(128) k_query_features(MapDev m, const float* _
   p.z = xyz[3 * q + 2];
   I3 b, v;
   block_and_voxel_from_position(m.block_size, m.voxel_size_inv, p, &b, &v);
-  const int slot = hash_find(m, b.x, b.y, b.z);
+  const int slot = find_slot(m, b.x, b.y, b.z);
   if (slot < 0 || m.blk_feat[slot] < 0) return;
   const __half* row = feat_block(m, m.blk_feat[slot]) + (size_t)((v.x * 8 + v.y) * 8 + v.z) * m.row;
   __half* o = out + q * (long long)(m.C + 1);

@@ -5,8 +5,11 @@
 // block_memory_pool_impl.h:22-73, gpu_hash/internal/cuda/impl/gpu_layer_view_impl.cuh:36-174) with ONE
 // structure that lives in HBM and is only ever touched by kernels:
 //
-//   * an open-addressing hash (64-bit packed key -> 32-bit slot), linear probing, load <= 0.25, no
-//     tombstones (the table is rebuilt from the slot table after a decay that freed blocks);
+//   * a two-level block index.  Level 1 is a DIRECT-MAPPED grid over the workspace bounding box (mindmap
+//     always sets one: nvblox_mapping_helpers.py:53-61; <= 405 / 3 740 cells for its tasks): block index
+//     -> slot in ONE load, no probing, release = one store.  Level 2 is an open-addressing hash (64-bit
+//     packed key -> 32-bit slot, linear probing, load <= 0.25, no tombstones: rebuilt from the slot table
+//     after a decay that freed hash-resident blocks) for indices outside the box and for unbounded maps;
 //   * a slot table (struct-of-arrays): block index, layer bits, feature-slot id, mesh-dirty flag and the
 //     block's extent in the current mesh arena;
 //   * slab arenas for voxel payloads: TSDF float2[512] per slot (slot id == payload id), feature
@@ -30,6 +33,9 @@ constexpr unsigned long long kEmptyKey = ~0ull;
 
 constexpr uint8_t kLayerTsdfBit = 1;
 constexpr uint8_t kLayerFeatBit = 2;
+// slot lists carry "freshly allocated, payload not initialised yet" in bit 30 (slot ids are < 2^30)
+constexpr int kNewFlag = 0x40000000;
+constexpr int kSlotMask = 0x3fffffff;
 
 // counter slots (unsigned long long each) -- mirror nvbx_counters
 enum CounterId {
@@ -65,12 +71,20 @@ struct Ctrl {
   int list_count;      // generic compaction counter (block index export)
   int mesh_total_v;    // totals of the mesh being built
   int mesh_total_t;
-  int pad;
+  int item_count;      // length of the feature work-item list of the current chunk
+  int last_band_count; // band_count of the last completed feature frame (debug / parity hook)
+  int n_hash;          // blocks resident in the overflow hash (0: every block is in the workspace grid)
+  int pad[2];
   unsigned long long counters[kCntNum];
 };
 
 struct MapDev {
-  // hash
+  // level-1 index: direct-mapped workspace grid (ws_slot == nullptr / ws_sx == 0: disabled)
+  int* ws_slot;
+  I3 ws_mn;
+  int ws_sx, ws_sy, ws_sz;
+  int ws_cells;
+  // level-2 index: overflow hash
   unsigned long long* keys;
   int* vals;
   unsigned int hash_mask;
@@ -149,6 +163,21 @@ __device__ __forceinline__ void hash_insert(const MapDev& m, int x, int y, int z
   }
 }
 
+// Cell of the workspace grid holding block (x, y, z), or -1 when the index lies outside the box (or the
+// grid is disabled: ws_sx == 0 makes the unsigned comparison fail).
+__device__ __forceinline__ int ws_cell(const MapDev& m, int x, int y, int z) {
+  const unsigned lx = (unsigned)(x - m.ws_mn.x), ly = (unsigned)(y - m.ws_mn.y), lz = (unsigned)(z - m.ws_mn.z);
+  if (lx < (unsigned)m.ws_sx && ly < (unsigned)m.ws_sy && lz < (unsigned)m.ws_sz)
+    return (int)(lx + (unsigned)m.ws_sx * (ly + (unsigned)m.ws_sy * lz));
+  return -1;
+}
+// Block index -> slot (or -1): one load inside the workspace grid, a hash probe outside.
+__device__ __forceinline__ int find_slot(const MapDev& m, int x, int y, int z) {
+  const int cell = ws_cell(m, x, y, z);
+  if (cell >= 0) return m.ws_slot[cell];
+  return hash_find(m, x, y, z);
+}
+
 // Pop a slot id: recycled ids first, then fresh ones.  Returns -1 (and raises ctrl->overflow) when the
 // arena is exhausted -- the host sizes arenas before every launch so this is an internal error.
 __device__ __forceinline__ int pop_id(int* free_top, int* high, const int* free_stack, int capacity, int* overflow) {
@@ -173,8 +202,14 @@ __device__ __forceinline__ void push_id(int* free_top, int* free_stack, int id) 
 // to zero the TSDF payload.
 __device__ __forceinline__ int acquire_slot(const MapDev& m, int x, int y, int z, bool* is_new_slot) {
   *is_new_slot = false;
-  if (!key_in_range(x, y, z)) return -1;  // |index| >= 2^20 blocks: outside the packed-key range
-  int slot = hash_find(m, x, y, z);
+  const int cell = ws_cell(m, x, y, z);
+  int slot;
+  if (cell >= 0) {
+    slot = m.ws_slot[cell];
+  } else {
+    if (!key_in_range(x, y, z)) return -1;  // |index| >= 2^20 blocks: outside the packed-key range
+    slot = hash_find(m, x, y, z);
+  }
   if (slot >= 0) return slot;
   slot = pop_id(&m.ctrl->slot_free_top, &m.ctrl->slot_high, m.slot_free, m.slot_capacity, &m.ctrl->overflow);
   if (slot < 0) return -1;
@@ -183,9 +218,27 @@ __device__ __forceinline__ int acquire_slot(const MapDev& m, int x, int y, int z
   m.blk_feat[slot] = -1;
   m.blk_dirty[slot] = 0;
   m.blk_mesh[slot] = make_int4(0, 0, 0, 0);
-  hash_insert(m, x, y, z, slot);
+  if (cell >= 0) {
+    m.ws_slot[cell] = slot;
+  } else {
+    hash_insert(m, x, y, z, slot);
+    atomicAdd(&m.ctrl->n_hash, 1);
+  }
   *is_new_slot = true;
   return slot;
+}
+
+// Drop a block index from the index (its slot id is pushed back by the caller).  Grid-resident blocks
+// cost one store; hash-resident ones raise ctrl->rebuild (no tombstones).
+__device__ __forceinline__ void unindex_slot(const MapDev& m, int slot) {
+  const int3 b = m.blk_index[slot];
+  const int cell = ws_cell(m, b.x, b.y, b.z);
+  if (cell >= 0) {
+    m.ws_slot[cell] = -1;
+  } else {
+    atomicAdd(&m.ctrl->n_hash, -1);
+    m.ctrl->rebuild = 1;
+  }
 }
 
 }  // namespace nvbx

@@ -128,7 +128,7 @@ __device__ void mesh_one_block(const MapDev& m, const MeshParams& mp, MeshSmem& 
 
   // neighbour slots (+x,+y,+z directions), directionFromNeighborIndex: j -> ((j>>2)&1, (j>>1)&1, j&1)
   if (t < 8) {
-    int ns = (t == 0) ? slot : hash_find(m, b.x + ((t >> 2) & 1), b.y + ((t >> 1) & 1), b.z + (t & 1));
+    int ns = (t == 0) ? slot : find_slot(m, b.x + ((t >> 2) & 1), b.y + ((t >> 1) & 1), b.z + (t & 1));
     if (ns >= 0 && !(m.blk_layers[ns] & kLayerTsdfBit)) ns = -1;
     s.nb_slot[t] = ns;
   }

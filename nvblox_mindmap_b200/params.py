@@ -59,7 +59,10 @@ class NvbxCounters(C.Structure):
     ]
 
     def as_dict(self) -> dict:
-        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != 'reserved'}
+        d = {n: int(getattr(self, n)) for n, _ in self._fields_ if n != 'reserved'}
+        if any(self.reserved):                     # libnvbx_prof.so only (NVBX_PROFILE=1)
+            d['profile'] = [int(v) for v in self.reserved]
+        return d
 
 
 WEIGHTING_MODES = {

@@ -463,6 +463,7 @@ struct Oracle {
   nvbx_counters cnt;
   std::unordered_set<uint64_t> pixel_seen;  // distinct feature pixels of the last feature frame
   int64_t last_distinct_pixels = 0;
+  int64_t last_trace_steps = 0, last_trace_max_steps = 0;  // sphere-tracing work of the last feature frame
   int64_t last_n_upd = 0;
 };
 
@@ -684,11 +685,13 @@ std::vector<I3> blocks_in_view_planes(Oracle& o, const Pose& T_L_C, const Cam& c
 // ------------------------------------------------------------------------------------------------
 // a7: sphere tracing.  NB/src/rays/sphere_tracer.cu:26-131,191-236,421-480
 // ------------------------------------------------------------------------------------------------
-inline bool sphere_cast(const Oracle& o, const V3& origin, const V3& dir, float trunc, float* t_out) {
+inline bool sphere_cast(const Oracle& o, const V3& origin, const V3& dir, float trunc, float* t_out,
+                        int* steps_out) {
   const float eps = o.p.sphere_tracing_surface_epsilon_vox * o.voxel_size;
   int first = 0;  // 0 unknown, 1 positive, -1 negative
   float t = 0.0f;
   for (int i = 0; (i < o.p.sphere_tracing_max_steps) && (t < o.p.sphere_tracing_max_ray_length_m); ++i) {
+    *steps_out = i + 1;
     const V3 p{origin.x + t * dir.x, origin.y + t * dir.y, origin.z + t * dir.z};
     I3 b, v;
     block_and_voxel_from_position(o.block_size, p, &b, &v);
@@ -739,7 +742,8 @@ void render_synthetic_depth(Oracle& o, const Cam& cam, const Pose& T_L_C, float 
   o.synth_rows = rows;
   o.synth_cols = cols;
   const V3 origin{T_L_C.t[0], T_L_C.t[1], T_L_C.t[2]};
-#pragma omp parallel for schedule(dynamic, 4)
+  int64_t steps_total = 0, steps_max = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : steps_total) reduction(max : steps_max)
   for (int r = 0; r < rows; ++r)
     for (int c = 0; c < cols; ++c) {
       const float pu = (float)(c * s) + 0.5f * (float)s * 1.0f;
@@ -754,11 +758,16 @@ void render_synthetic_depth(Oracle& o, const Cam& cam, const Pose& T_L_C, float 
       }
       const V3 dl = rotate(T_L_C, dc);
       float t;
-      if (sphere_cast(o, origin, dl, trunc, &t))
+      int steps = 0;
+      if (sphere_cast(o, origin, dl, trunc, &t, &steps))
         o.synth[(size_t)r * cols + c] = t * dc.z;
       else
         o.synth[(size_t)r * cols + c] = -1.0f;
+      steps_total += steps;
+      steps_max = std::max<int64_t>(steps_max, steps);
     }
+  o.last_trace_steps = steps_total;
+  o.last_trace_max_steps = steps_max;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1292,6 +1301,8 @@ void orc_get_counters(void* h, nvbx_counters* out) { *out = ((Oracle*)h)->cnt; }
 void orc_reset_counters(void* h) { std::memset(&((Oracle*)h)->cnt, 0, sizeof(nvbx_counters)); }
 int64_t orc_last_distinct_pixels(void* h) { return ((Oracle*)h)->last_distinct_pixels; }
 int64_t orc_last_feature_voxels(void* h) { return ((Oracle*)h)->last_n_upd; }
+int64_t orc_last_trace_steps(void* h) { return ((Oracle*)h)->last_trace_steps; }
+int64_t orc_last_trace_max_steps(void* h) { return ((Oracle*)h)->last_trace_max_steps; }
 int64_t orc_last_block_list(void* h, int which, int32_t* out, int64_t cap) {
   Oracle& o = *(Oracle*)h;
   const std::vector<I3>& l = which == 0 ? o.last_tsdf_list : o.last_feat_list;

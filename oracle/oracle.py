@@ -58,6 +58,8 @@ def lib() -> C.CDLL:
         L.orc_last_distinct_pixels.argtypes = [C.c_void_p]
         L.orc_last_feature_voxels.restype = C.c_int64
         L.orc_last_feature_voxels.argtypes = [C.c_void_p]
+        for fn in (L.orc_last_trace_steps, L.orc_last_trace_max_steps):
+            fn.restype, fn.argtypes = C.c_int64, [C.c_void_p]
         L.orc_last_block_list.restype = C.c_int64
         L.orc_last_block_list.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
         L.orc_last_synthetic_depth.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -209,6 +211,8 @@ class OracleMapper:
         d = c.as_dict()
         d['last_distinct_pixels'] = int(self.L.orc_last_distinct_pixels(self.h))
         d['last_feature_voxels'] = int(self.L.orc_last_feature_voxels(self.h))
+        d['last_trace_steps'] = int(self.L.orc_last_trace_steps(self.h))
+        d['last_trace_max_steps'] = int(self.L.orc_last_trace_max_steps(self.h))
         return d
 
     def reset_counters(self):

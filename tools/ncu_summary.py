@@ -28,7 +28,10 @@ def launches(src, dst):
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
         agg.setdefault(row['Kernel Name'], []).append(float(row['Metric Value'].replace(',', '')))
-    ours = {k: v for k, v in agg.items() if 'nvbx::' in k}
+    def is_ours(k):
+        n = k.replace('void ', '')
+        return 'nvbx::' in k or n.startswith('k_')
+    ours = {k: v for k, v in agg.items() if is_ours(k)}
     tot = sum(sum(v) for v in ours.values())
     with open(dst, 'w') as f:
         f.write(f'# ncu launch list: `{src}`\n\n')
@@ -39,7 +42,7 @@ def launches(src, dst):
             name = k.split('(')[0].replace('void ', '')
             f.write(f'| `{name}` | {len(v)} | {sum(v) / len(v) / 1e3:.2f} | {min(v) / 1e3:.2f} | {max(v) / 1e3:.2f} | '
                     f'{100 * sum(v) / tot:.1f}% |\n')
-        other = {k: v for k, v in agg.items() if 'nvbx::' not in k}
+        other = {k: v for k, v in agg.items() if not is_ours(k)}
         if other:
             f.write('\nOther kernels in the capture (input generation by torch): ' +
                     ', '.join(f'`{k.split("(")[0][:60]}` x{len(v)}' for k, v in other.items()) + '\n')
