@@ -218,8 +218,10 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host = time.perf_counter()
     for i in range(args.warmup, n_total):
         step(i)
+    t_host = time.perf_counter() - t_host      # host time to ENQUEUE the steps (no sync inside)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -235,7 +237,9 @@ def run_ours(args, rank, world, local_rank):
     if args.quick:
         if rank == 0:
             kms = kernel_time_ms(args, mapper, depths, poses, feats, K_t)
+            print(json.dumps({'per_kernel_us': per_kernel_us(args, mapper, depths, poses, feats, K_t)}), flush=True)
             print(json.dumps({'quick': True, 'value': value, 'ms_per_step': ms / args.steps, 'kernel_ms': kms,
+                              'host_enqueue_ms_per_step': 1000.0 * t_host / args.steps,
                               'gpu_launches': launches, 'profile': counters.get('profile')}), flush=True)
         return
 
@@ -334,6 +338,23 @@ def kernel_time_ms(args, mapper, depths, poses, feats, K_t):
     lib.nvbx_get_kernel_timing(mapper._handle, 0, C.byref(ms), C.byref(n))
     lib.nvbx_set_kernel_timing(mapper._handle, 0)
     return (ms.value / n.value) if n.value else None
+
+
+def per_kernel_us(args, mapper, depths, poses, feats, K_t):
+    """In-pipeline duration of every kernel (event pair around each launch; includes the launch gap)."""
+    import ctypes as C
+    from nvblox_mindmap_b200 import _capi
+    lib = _capi.load()
+    lib.nvbx_set_kernel_timing(mapper._handle, 2)
+    n_total = args.warmup + args.steps
+    for i in range(args.warmup, n_total):
+        mapper.add_depth_frame(depths[i], poses[i], K_t)
+        mapper.add_feature_frame(feats[i % N_FEATURE_BUFFERS], poses[i], K_t)
+    buf = C.create_string_buffer(1 << 16)
+    n = lib.nvbx_kernel_timing_report(mapper._handle, buf, len(buf))
+    lib.nvbx_set_kernel_timing(mapper._handle, 0)
+    rep = json.loads(buf.value.decode()) if n > 0 else {}
+    return {k: round(1000.0 * v[0] / max(1, v[1]), 2) for k, v in rep.items()}
 
 
 def main():

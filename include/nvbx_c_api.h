@@ -223,6 +223,11 @@ int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream);
  * the launching stream.  nvbx_get_kernel_timing synchronises, returns the summed milliseconds and the
  * number of launches since timing was enabled, and resets the accumulators. */
 int nvbx_set_kernel_timing(nvbx_mapper* m, int enabled);
+/* enabled = 2: bracket EVERY kernel launch of the library with an event pair (tuning aid; perturbs the
+ * pipeline).  nvbx_kernel_timing_report synchronises and writes a JSON object
+ * {"kernel name": [total_ms, launches], ...} into `json` (returns its length or a negative error) and
+ * resets the records. */
+int64_t nvbx_kernel_timing_report(nvbx_mapper* m, char* json, int64_t capacity);
 int nvbx_get_kernel_timing(nvbx_mapper* m, int which, double* total_ms, int64_t* launches);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t nvbx_kernel_launch_count(void);

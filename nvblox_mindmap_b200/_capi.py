@@ -21,7 +21,7 @@ API_SYMBOLS = [
     'nvbx_update_feature_mesh', 'nvbx_get_feature_mesh', 'nvbx_num_blocks', 'nvbx_num_allocated_blocks',
     'nvbx_num_allocated_bytes', 'nvbx_voxel_size', 'nvbx_get_block_indices', 'nvbx_get_block_ptr',
     'nvbx_allocate_block', 'nvbx_query_tsdf', 'nvbx_query_features', 'nvbx_get_counters',
-    'nvbx_reset_counters', 'nvbx_set_kernel_timing', 'nvbx_get_kernel_timing', 'nvbx_kernel_launch_count', 'nvbx_debug_last_block_list',
+    'nvbx_reset_counters', 'nvbx_set_kernel_timing', 'nvbx_get_kernel_timing', 'nvbx_kernel_timing_report', 'nvbx_kernel_launch_count', 'nvbx_debug_last_block_list',
     'nvbx_debug_last_synthetic_depth', 'nvbx_version',
 ]
 
@@ -58,12 +58,13 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         L.nvbx_feature_channels.argtypes = [vp]
         L.nvbx_get_params.argtypes = [vp, C.POINTER(NvbxParams)]
         L.nvbx_last_error.restype = C.c_char_p
-        frame = [vp, C.c_int, vp, C.c_int, C.c_int, vp, fp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
+        # poses are passed as the address of 16 row-major floats (a CPU tensor's data_ptr())
+        frame = [vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp]
         L.nvbx_integrate_depth.argtypes = frame
         L.nvbx_integrate_color.argtypes = frame
-        L.nvbx_integrate_features.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, fp, C.c_float,
+        L.nvbx_integrate_features.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_float,
                                               C.c_float, C.c_float, C.c_float, vp]
-        L.nvbx_integrate_frame_host.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, fp,
+        L.nvbx_integrate_frame_host.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp,
                                                 C.c_float, C.c_float, C.c_float, C.c_float, vp]
         for n in ('nvbx_decay', 'nvbx_clear', 'nvbx_update_feature_mesh'):
             getattr(L, n).argtypes = [vp, C.c_int, vp]
@@ -83,6 +84,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         L.nvbx_reset_counters.argtypes = [vp, C.c_int, vp]
         L.nvbx_set_kernel_timing.argtypes = [vp, C.c_int]
         L.nvbx_get_kernel_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_double), i64p]
+        L.nvbx_kernel_timing_report.argtypes = [vp, C.c_char_p, C.c_int64]
+        L.nvbx_kernel_timing_report.restype = C.c_int64
         L.nvbx_kernel_launch_count.restype = C.c_int64
         L.nvbx_debug_last_block_list.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64, vp]
         L.nvbx_debug_last_block_list.restype = C.c_int64

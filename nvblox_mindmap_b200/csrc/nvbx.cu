@@ -17,6 +17,7 @@
 #include <deque>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/nvbx_c_api.h"
@@ -47,11 +48,60 @@ int fail(int code, const char* fmt, ...) {
                   "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);      \
   } while (0)
 
+// Per-kernel live timing (tuning / profiles): mode 2 brackets EVERY launch with a CUDA event pair on the
+// launching stream; nvbx_kernel_timing_report() sums them per kernel name.  Off (0) in normal operation.
+struct LaunchRec {
+  const char* name;
+  cudaEvent_t a, b;
+};
+int g_timing_mode = 0;
+std::vector<LaunchRec> g_launch_recs;
+inline void launch_rec_begin(const char* name, cudaStream_t stream) {
+  if (g_timing_mode < 2) return;
+  LaunchRec r{name, nullptr, nullptr};
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, stream);
+  g_launch_recs.push_back(r);
+}
+inline void launch_rec_end(cudaStream_t stream) {
+  if (g_timing_mode < 2 || g_launch_recs.empty()) return;
+  cudaEventRecord(g_launch_recs.back().b, stream);
+}
+
+// All kernels are launched with programmatic stream serialization (see pdl_prologue() in
+// nvbx_kernels.cuh); NVBX_PDL=0 falls back to plain stream order.
+bool use_pdl() {
+  static const bool v = [] {
+    const char* e = getenv("NVBX_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 #define LAUNCH(kernel, grid, block, smem, stream, ...)                                              \
   do {                                                                                              \
-    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                     \
+    launch_rec_begin(#kernel, (stream));                                                            \
+    cudaError_t _le = launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), (stream), __VA_ARGS__); \
+    launch_rec_end((stream));                                                                       \
     g_launches.fetch_add(1, std::memory_order_relaxed);                                             \
-    CUDA_TRY(cudaPeekAtLastError());                                                                \
+    if (_le != cudaSuccess)                                                                         \
+      return fail(NVBX_ERR_CUDA, "launch of %s failed: %s (%s:%d)", #kernel, cudaGetErrorString(_le), __FILE__, \
+                  __LINE__);                                                                        \
   } while (0)
 
 template <typename T>
@@ -138,7 +188,7 @@ struct Map {
   CacheEntry scratch_ray, scratch_planes;  // used when the cache is disabled
   DevBuf<unsigned> grid;   // view bitmap; all-zero between frames (k_view_compact_alloc cleans it)
   bool grid_dirty = false;  // a frame failed between marking and compaction
-  DevBuf<int> view_slots, band_slots;
+  DevBuf<int> view_slots, band_slots, newfeat_slots;
   DevBuf<FeatItem> items;
   DevBuf<float> synth;
   int synth_rows = 0, synth_cols = 0;
@@ -180,6 +230,16 @@ constexpr int kFeatureChunkBlocks = 8192;                // band blocks per geom
 
 int persistent_grid(const nvbx_mapper* m, int ctas_per_sm) { return m->sm_count * ctas_per_sm; }
 
+// Test aid (NVBX_POISON_ARENAS=1, set by tests/conftest.py): fresh slabs are filled with garbage so that a
+// missing zero-initialisation of a new block cannot hide behind cudaMalloc handing out zero pages.
+bool poison_arenas() {
+  static const bool v = [] {
+    const char* e = getenv("NVBX_POISON_ARENAS");
+    return e && e[0] == '1';
+  }();
+  return v;
+}
+
 int upload_slab_tables(Map& mp, cudaStream_t stream) {
   if (!mp.tsdf_slabs.empty())
     CUDA_TRY(cudaMemcpyAsync(mp.d_tsdf_table, mp.tsdf_slabs.data(), mp.tsdf_slabs.size() * sizeof(void*),
@@ -218,7 +278,9 @@ int grow_slots(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
   CUDA_TRY(cudaMemsetAsync(mp.dev.blk_layers + old, 0, new_cap - old, stream));
   while ((int)mp.tsdf_slabs.size() < (new_cap >> kTsdfSlabShift)) {
     void* s = nullptr;
-    CUDA_TRY(cudaMalloc(&s, (size_t)(1 << kTsdfSlabShift) * kVoxelsPerBlock * sizeof(float2)));
+    const size_t bytes = (size_t)(1 << kTsdfSlabShift) * kVoxelsPerBlock * sizeof(float2);
+    CUDA_TRY(cudaMalloc(&s, bytes));
+    if (poison_arenas()) CUDA_TRY(cudaMemsetAsync(s, 0x7b, bytes, stream));
     mp.tsdf_slabs.push_back(s);
   }
   if ((rc = upload_slab_tables(mp, stream))) return rc;
@@ -254,6 +316,7 @@ int grow_feats(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
   while ((int)mp.feat_slabs.size() < (new_cap >> kFeatSlabShift)) {
     void* s = nullptr;
     CUDA_TRY(cudaMalloc(&s, slab_bytes));
+    if (poison_arenas()) CUDA_TRY(cudaMemsetAsync(s, 0x7b, slab_bytes, stream));
     mp.feat_slabs.push_back(s);
   }
   if ((rc = upload_slab_tables(mp, stream))) return rc;
@@ -466,6 +529,7 @@ void destroy_map(Map& mp) {
   mp.grid.release();
   mp.view_slots.release();
   mp.band_slots.release();
+  mp.newfeat_slots.release();
   mp.items.release();
   mp.synth.release();
   mp.cnt_v.release();
@@ -496,7 +560,7 @@ Cam make_cam(float fx, float fy, float cx, float cy, int H, int W) {
 }
 
 int timing_begin(nvbx_mapper* m, int which, cudaStream_t stream) {
-  if (!m->timing) return NVBX_OK;
+  if (!m->timing || g_timing_mode >= 2) return NVBX_OK;
   cudaEvent_t a, b;
   CUDA_TRY(cudaEventCreate(&a));
   CUDA_TRY(cudaEventCreate(&b));
@@ -505,15 +569,15 @@ int timing_begin(nvbx_mapper* m, int which, cudaStream_t stream) {
   return NVBX_OK;
 }
 int timing_end(nvbx_mapper* m, int which, cudaStream_t stream) {
-  if (!m->timing) return NVBX_OK;
+  if (!m->timing || g_timing_mode >= 2) return NVBX_OK;
   CUDA_TRY(cudaEventRecord(m->timing_events[which].back().second, stream));
   return NVBX_OK;
 }
 
-int gather_variant() {  // tuning hook: NVBX_GATHER_VARIANT=0..3 (default 1)
+int gather_variant() {  // tuning hook: NVBX_GATHER_VARIANT=0..3 (default 0; see profiles/r01b_gather_variants.md)
   static const int v = [] {
     const char* e = getenv("NVBX_GATHER_VARIANT");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 0;
   }();
   return v;
 }
@@ -522,9 +586,9 @@ template <int CH>
 int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, cudaStream_t stream) {
   int rc;
   if ((rc = timing_begin(m, 0, stream))) return rc;
-  switch (gather_variant()) {
-    case 0:
-      LAUNCH((k_feature_gather<CH, 1, 4>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
+  switch (gather_variant()) {  // <CH, units in flight per warp, resident CTAs per SM>
+    case 1:
+      LAUNCH((k_feature_gather<CH, 2, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
       break;
     case 2:
       LAUNCH((k_feature_gather<CH, 1, 6>), persistent_grid(m, 6), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
@@ -533,7 +597,7 @@ int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, 
       LAUNCH((k_feature_gather<CH, 1, 8>), persistent_grid(m, 8), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
       break;
     default:
-      LAUNCH((k_feature_gather<CH, 2, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
+      LAUNCH((k_feature_gather<CH, 1, 4>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
   }
   return timing_end(m, 0, stream);
 }
@@ -699,16 +763,34 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
     const int n_rows = (int)std::ceil((float)(height + 1) / (float)s);
     const int n_cols = (int)std::ceil((float)(width + 1) / (float)s);
     const int tiles_x = (n_cols + 15) / 16, n_tiles = tiles_x * ((n_rows + 15) / 16);
-    const int rgrid = std::max(1, std::min(n_tiles, persistent_grid(m, 4)));
+    // one tile per CTA while they all fit on the machine at once (8 CTAs of 256 threads per SM): the hardware
+    // scheduler then balances tiles of unequal cost; larger images loop
+    const int rgrid = std::max(1, std::min(n_tiles, persistent_grid(m, 8)));
     mp.grid_dirty = true;
+    RaycastFrame rf;
+    rf.T_L_C = T_L_C;
+    rf.cam = cam;
+    rf.depth = (const float*)depth;
+    rf.rows = height;
+    rf.cols = width;
+    rf.block_size = mp.block_size;
+    rf.max_dist = p.max_integration_distance_m;
+    rf.behind = trunc;
+    rf.sub = s;
+    rf.g = gs.g;
+    for (int i = 0; i < 3; ++i) {  // RayCaster constructor, pixel-independent half (ray_caster_impl.h:26-53)
+      rf.s[i] = (T_L_C.t[i] / mp.block_size) / 1.0f;
+      rf.start[i] = (int)floorf(rf.s[i]);
+      rf.shifted[i] = rf.s[i] - (float)rf.start[i];
+    }
+    rf.lin0 = (int)((unsigned)(rf.start[0] - gs.g.mn.x) + (unsigned)(rf.start[1] - gs.g.mn.y) * (unsigned)gs.g.sx +
+                    (unsigned)(rf.start[2] - gs.g.mn.z) * (unsigned)gs.g.sx * (unsigned)gs.g.sy);
+    rf.tiles_x = tiles_x;
+    rf.n_tiles = n_tiles;
     if (n_words <= (size_t)kRayBitmapWords) {
-      LAUNCH(k_raycast_mark<true>, rgrid, 256, n_words * sizeof(unsigned), stream, T_L_C, cam, (const float*)depth,
-             height, width, mp.block_size, p.max_integration_distance_m, trunc, s, gs.g, mp.grid.p, tiles_x, n_tiles,
-             entry->d_count);
+      LAUNCH(k_raycast_mark<true>, rgrid, 256, n_words * sizeof(unsigned), stream, rf, mp.grid.p, entry->d_count);
     } else {
-      LAUNCH(k_raycast_mark<false>, rgrid, 256, 0, stream, T_L_C, cam, (const float*)depth, height, width,
-             mp.block_size, p.max_integration_distance_m, trunc, s, gs.g, mp.grid.p, tiles_x, n_tiles,
-             entry->d_count);
+      LAUNCH(k_raycast_mark<false>, rgrid, 256, 0, stream, rf, mp.grid.p, entry->d_count);
     }
     const int cgrid = std::max(1, std::min(persistent_grid(m, 4), (int)((n_words + 7) / 8)));  // warp per word
     if (!slots_fit(m, mp, (long long)n)) {
@@ -741,7 +823,7 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
   f.max_weight = p.max_weight;
   f.invalid_decay = p.invalid_depth_decay_factor;
   f.weighting_mode = p.weighting_mode;
-  const int tgrid = std::max(1, std::min(persistent_grid(m, 2), entry->bound));
+  const int tgrid = std::max(1, std::min(persistent_grid(m, 3), entry->bound));  // one block per CTA up to 3 CTAs/SM
   if ((rc = timing_begin(m, 1, stream))) return rc;
   LAUNCH(k_tsdf_update, tgrid, 512, 0, stream, mp.dev, mp.view_slots.p, entry->d_count, f);
   return timing_end(m, 1, stream);
@@ -803,6 +885,7 @@ int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, in
   const long long cand_bound = std::min((long long)entry->bound, std::max(1LL, mp.slot_used_ub));
   if ((rc = ensure_feats(m, mp, cand_bound, stream))) return rc;
   if ((rc = mp.band_slots.ensure((size_t)cand_bound, stream))) return rc;
+  if ((rc = mp.newfeat_slots.ensure((size_t)cand_bound, stream))) return rc;
   const long long chunk_blocks = std::min<long long>(cand_bound, kFeatureChunkBlocks);
   if ((rc = mp.items.ensure((size_t)chunk_blocks * kVoxelsPerBlock, stream))) return rc;
   const int srows = height / sub, scols = width / sub;
@@ -829,7 +912,7 @@ int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, in
     const int n_trace = trace_tiles_x * ((srows + 15) / 16);
     const int n_band = std::max(1, std::min(n_tiles, persistent_grid(m, 4)));
     LAUNCH(k_trace_and_band, n_trace + n_band, 256, 0, stream, mp.dev, tp, mp.synth.p, trace_tiles_x, n_trace, pv,
-           trunc, mp.band_slots.p, tile_cells, n_tiles);
+           trunc, mp.band_slots.p, mp.newfeat_slots.p, tile_cells, n_tiles);
   }
 
   FeatFrame ff;
@@ -861,8 +944,9 @@ int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, in
     const long long end = std::min(cand_bound, begin + chunk_blocks);
     const int last = end >= cand_bound ? 1 : 0;
     if (begin > 0) CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->item_count, 0, sizeof(int), stream));
-    const int ggrid = (int)std::max<long long>(1, std::min<long long>(persistent_grid(m, 2), end - begin));
-    LAUNCH(k_feature_geometry, ggrid, 512, 0, stream, mp.dev, mp.band_slots.p, ff, mp.items.p, (int)begin, (int)end);
+    const int ggrid = persistent_grid(m, 2);  // full grid: new feature blocks are zero-filled by all CTAs
+    LAUNCH(k_feature_geometry, ggrid, 512, 0, stream, mp.dev, mp.band_slots.p, mp.newfeat_slots.p, ff, mp.items.p,
+           (int)begin, (int)end);
     if (m->C % 256 == 0 && m->C / 256 == 3)
       rc = launch_gather<3>(m, mp, ff, last, stream);
     else if (m->C % 256 == 0 && m->C / 256 == 4)
@@ -1175,7 +1259,42 @@ int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream_v) {
 int nvbx_set_kernel_timing(nvbx_mapper* m, int enabled) {
   if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper handle");
   m->timing = enabled != 0;
+  g_timing_mode = enabled;
   return NVBX_OK;
+}
+
+int64_t nvbx_kernel_timing_report(nvbx_mapper* m, char* json, int64_t capacity) {
+  if (!m || !json || capacity <= 2) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad timing report buffer");
+  CUDA_TRY(cudaSetDevice(m->device));
+  std::vector<std::pair<std::string, std::pair<double, long long>>> agg;
+  for (auto& r : g_launch_recs) {
+    float ms = 0.f;
+    if (r.b && cudaEventSynchronize(r.b) == cudaSuccess) cudaEventElapsedTime(&ms, r.a, r.b);
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+    std::string name = r.name;
+    const size_t par = name.find('(');  // "(k_feature_gather<CH, 1, 4>)" -> strip the macro parentheses
+    if (par == 0) name = name.substr(1, name.size() - 2);
+    auto it = std::find_if(agg.begin(), agg.end(), [&](auto& e) { return e.first == name; });
+    if (it == agg.end()) {
+      agg.push_back({name, {ms, 1}});
+    } else {
+      it->second.first += ms;
+      it->second.second += 1;
+    }
+  }
+  g_launch_recs.clear();
+  std::string out = "{";
+  for (size_t i = 0; i < agg.size(); ++i) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s\"%s\": [%.6f, %lld]", i ? ", " : "", agg[i].first.c_str(), agg[i].second.first,
+             agg[i].second.second);
+    out += buf;
+  }
+  out += "}";
+  if ((int64_t)out.size() + 1 > capacity) return fail(NVBX_ERR_INVALID_ARGUMENT, "timing report buffer too small");
+  std::memcpy(json, out.c_str(), out.size() + 1);
+  return (int64_t)out.size();
 }
 int nvbx_get_kernel_timing(nvbx_mapper* m, int which, double* total_ms, int64_t* launches) {
   if (!m || which < 0 || which > 1) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad timing query");

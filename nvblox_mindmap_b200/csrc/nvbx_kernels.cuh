@@ -24,6 +24,17 @@ namespace nvbx {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Programmatic dependent launch (sm_90+): every kernel of the library is launched with the
+// programmatic-stream-serialization attribute and starts with pdl_prologue().  launch_dependents lets the
+// NEXT kernel of the stream be scheduled while this one still runs (its CTAs fill free SM slots and park
+// in griddepcontrol.wait); wait blocks until the PREVIOUS kernel has completed and its writes are
+// visible.  Net effect: the ~2-3 us launch latency of each of the 6 kernels of a frame is hidden behind
+// its predecessor.  Nothing produced by an earlier kernel may be read before pdl_prologue().
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ void count_add(const MapDev& m, int id, unsigned long long v) {
   atomicAdd(&m.ctrl->counters[id], v);
 }
@@ -47,11 +58,11 @@ struct ViewGrid {
 
 constexpr int kRayBitmapWords = 8192;  // 32 KiB of shared memory = 262 144 cells
 
+// Mark linear cell `lin` (already aliased exactly like setIndexUpdated: any int whose unsigned value is
+// below n_cells hits a cell, whatever the per-axis indices were).
 template <bool SMEM>
-__device__ __forceinline__ void mark_cell(unsigned* bm, const ViewGrid& g, int x, int y, int z) {
-  const int lx = x - g.mn.x, ly = y - g.mn.y, lz = z - g.mn.z;
-  const size_t lin = (size_t)(int)(lx + ly * g.sx + lz * g.sx * g.sy);
-  if (lin < (size_t)g.n_cells) {
+__device__ __forceinline__ void mark_lin(unsigned* bm, int n_cells, int lin) {
+  if ((unsigned)lin < (unsigned)n_cells) {
     const unsigned w = (unsigned)lin >> 5, bit = 1u << ((unsigned)lin & 31u);
     if (SMEM) {
       if (!(bm[w] & bit)) atomicOr(&bm[w], bit);
@@ -61,12 +72,29 @@ __device__ __forceinline__ void mark_cell(unsigned* bm, const ViewGrid& g, int x
   }
 }
 
+// Everything about a depth frame's rays that does not depend on the pixel, computed once on the host
+// with the same IEEE operations the per-ray code of the reference performs (RayCaster constructor,
+// ray_caster_impl.h:26-53: start = origin / block_size, floor, shifted start).
+struct RaycastFrame {
+  Pose T_L_C;
+  Cam cam;
+  const float* depth;
+  int rows, cols;
+  float block_size, max_dist, behind;
+  int sub;
+  ViewGrid g;
+  float s[3];        // ray start in block units: (T_L_C.t / block_size) / 1
+  int start[3];      // floor(s)
+  float shifted[3];  // s - start
+  int lin0;          // linear (aliased) grid index of the start block
+  int tiles_x, n_tiles;
+};
+
 template <bool SMEM>
-__global__ void __launch_bounds__(256) k_raycast_mark(Pose T_L_C, Cam cam, const float* __restrict__ depth, int rows,
-                                                      int cols, float block_size, float max_dist, float behind,
-                                                      int sub, ViewGrid g, unsigned* gbits, int tiles_x, int n_tiles,
-                                                      int* entry_count) {
+__global__ void __launch_bounds__(256) k_raycast_mark(RaycastFrame f, unsigned* gbits, int* entry_count) {
+  pdl_prologue();
   extern __shared__ unsigned s_bits[];
+  const ViewGrid& g = f.g;
   const int n_words = (g.n_cells + 31) >> 5;
   unsigned* bm = SMEM ? s_bits : gbits;
   if (SMEM) {
@@ -74,69 +102,57 @@ __global__ void __launch_bounds__(256) k_raycast_mark(Pose T_L_C, Cam cam, const
     __syncthreads();
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *entry_count = 0;  // consumed by k_view_compact_alloc (next launch)
+  const int stride_y = g.sx, stride_z = g.sx * g.sy;
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int ray_col = (tile % tiles_x) * 16 + (threadIdx.x & 15);
-    const int ray_row = (tile / tiles_x) * 16 + (threadIdx.x >> 4);
-    int prow = ray_row * sub, pcol = ray_col * sub;
-    if (prow >= rows + sub - 1 || pcol >= cols + sub - 1) continue;
-    if (prow >= rows) prow = rows - 1;
-    if (pcol >= cols) pcol = cols - 1;
-    float d = __ldg(depth + (size_t)prow * cols + pcol);
+  for (int tile = blockIdx.x; tile < f.n_tiles; tile += gridDim.x) {
+    const int ray_col = (tile % f.tiles_x) * 16 + (threadIdx.x & 15);
+    const int ray_row = (tile / f.tiles_x) * 16 + (threadIdx.x >> 4);
+    int prow = ray_row * f.sub, pcol = ray_col * f.sub;
+    if (prow >= f.rows + f.sub - 1 || pcol >= f.cols + f.sub - 1) continue;
+    if (prow >= f.rows) prow = f.rows - 1;
+    if (pcol >= f.cols) pcol = f.cols - 1;
+    float d = __ldg(f.depth + (size_t)prow * f.cols + pcol);
     if (d <= 0.0f) continue;
-    if (max_dist > 0.0f && d > max_dist) d = max_dist;
-    const V3 ray = ray_from_image_plane(cam, (float)pcol + 0.5f, (float)prow + 0.5f);
-    const float len = d + behind;
+    if (f.max_dist > 0.0f && d > f.max_dist) d = f.max_dist;
+    const V3 ray = ray_from_image_plane(f.cam, (float)pcol + 0.5f, (float)prow + 0.5f);
+    const float len = d + f.behind;
     V3 p_C;
     p_C.x = len * ray.x;
     p_C.y = len * ray.y;
     p_C.z = len * ray.z;
-    const V3 p_L = xform(T_L_C, p_C);
-    const I3 b = block_index_from_position(block_size, p_L);
-    mark_cell<SMEM>(bm, g, b.x, b.y, b.z);
+    const V3 p_L = xform(f.T_L_C, p_C);
+    // ray end in block units; its floor is also the block index of the end point (view_calculator.cu:231-236)
+    const float e[3] = {(p_L.x / f.block_size) / 1.0f, (p_L.y / f.block_size) / 1.0f, (p_L.z / f.block_size) / 1.0f};
+    const int end[3] = {(int)floorf(e[0]), (int)floorf(e[1]), (int)floorf(e[2])};
+    mark_lin<SMEM>(bm, g.n_cells, (end[0] - g.mn.x) + (end[1] - g.mn.y) * stride_y + (end[2] - g.mn.z) * stride_z);
 
-    // RayCaster(origin / bs, p_L / bs), scale 1
-    const float s[3] = {(T_L_C.t[0] / block_size) / 1.0f, (T_L_C.t[1] / block_size) / 1.0f,
-                        (T_L_C.t[2] / block_size) / 1.0f};
-    const float e[3] = {(p_L.x / block_size) / 1.0f, (p_L.y / block_size) / 1.0f, (p_L.z / block_size) / 1.0f};
-    int cur[3], sign[3];
+    // RayCaster(origin / bs, p_L / bs), scale 1 -- the per-pixel half of the constructor
+    int dlin[3];
     float t_next[3], t_step[3];
     int steps = 0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      cur[i] = (int)floorf(s[i]);
-      const int end = (int)floorf(e[i]);
-      steps += abs(end - cur[i]);
-      const float r = e[i] - s[i];
-      sign[i] = (r > 0.0f) ? 1 : ((r < 0.0f) ? -1 : 0);
-      const int corrected = max(sign[i], 0);
-      const float shifted = s[i] - (float)cur[i];
-      const float dist = (float)corrected - shifted;
+      steps += abs(end[i] - f.start[i]);
+      const float r = e[i] - f.s[i];
+      const int sign = (r > 0.0f) ? 1 : ((r < 0.0f) ? -1 : 0);
+      const float dist = (float)max(sign, 0) - f.shifted[i];
       t_next[i] = dist / r;
-      t_step[i] = (float)sign[i] / r;
+      t_step[i] = (float)sign / r;
+      dlin[i] = sign * (i == 0 ? 1 : (i == 1 ? stride_y : stride_z));
     }
+    int lin = f.lin0;
     for (int step = 0; step <= steps; ++step) {
-      mark_cell<SMEM>(bm, g, cur[0], cur[1], cur[2]);
-      int mi = 0;
-      float mv = t_next[0];
-      if (t_next[1] < mv) {
-        mi = 1;
-        mv = t_next[1];
-      }
-      if (t_next[2] < mv) {
-        mi = 2;
-      }
-      // if-chain (not cur[mi]) keeps cur/t_next in registers
-      if (mi == 0) {
-        cur[0] += sign[0];
-        t_next[0] += t_step[0];
-      } else if (mi == 1) {
-        cur[1] += sign[1];
-        t_next[1] += t_step[1];
-      } else {
-        cur[2] += sign[2];
-        t_next[2] += t_step[2];
-      }
+      mark_lin<SMEM>(bm, g.n_cells, lin);
+      // Eigen minCoeff: first minimum wins; NaNs (0/0 on a degenerate axis) never compare smaller
+      const bool y_lt_x = t_next[1] < t_next[0];
+      const float mxy = y_lt_x ? t_next[1] : t_next[0];
+      const bool z_min = t_next[2] < mxy;
+      const bool y_min = y_lt_x && !z_min;
+      const bool x_min = !y_lt_x && !z_min;
+      lin += z_min ? dlin[2] : (y_min ? dlin[1] : dlin[0]);
+      t_next[0] += x_min ? t_step[0] : 0.0f;
+      t_next[1] += y_min ? t_step[1] : 0.0f;
+      t_next[2] += z_min ? t_step[2] : 0.0f;
     }
   }
   if (SMEM) {
@@ -150,6 +166,7 @@ __global__ void __launch_bounds__(256) k_raycast_mark(Pose T_L_C, Cam cam, const
 
 // Number of marked cells (only launched while the block arena is still growing, see ensure_slots()).
 __global__ void __launch_bounds__(256) k_count_marked(const unsigned* __restrict__ gbits, int n_words, int* out) {
+  pdl_prologue();
   int c = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) c += __popc(gbits[i]);
   for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -172,6 +189,7 @@ __device__ __forceinline__ bool ensure_tsdf_layer(const MapDev& m, int slot) {
 // layer_impl.h:130-162 / integrators_common_impl.h:60-121.  One 32-cell word per warp, one cell per lane.
 __global__ void __launch_bounds__(256) k_view_compact_alloc(MapDev m, unsigned* gbits, ViewGrid g, int3* entry_idx,
                                                             int* entry_count, int* view_slots) {
+  pdl_prologue();
   const int n_words = (g.n_cells + 31) >> 5;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int lane = lane_id();
@@ -208,6 +226,7 @@ __global__ void __launch_bounds__(256) k_view_compact_alloc(MapDev m, unsigned* 
 // are (re-)allocated where required (projective_integrator_impl.cuh:288-291).
 __global__ void __launch_bounds__(256) k_view_alloc_from_list(MapDev m, const int3* __restrict__ entry_idx,
                                                               const int* __restrict__ entry_count, int* view_slots) {
+  pdl_prologue();
   const int n = *entry_count;
   unsigned n_new = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -257,8 +276,9 @@ __device__ __forceinline__ bool project_voxel(const Cam& cam, const Pose& T_C_L,
   return true;
 }
 
-__global__ void __launch_bounds__(512, 2) k_tsdf_update(MapDev m, const int* __restrict__ view_slots,
+__global__ void __launch_bounds__(512, 3) k_tsdf_update(MapDev m, const int* __restrict__ view_slots,
                                                         const int* __restrict__ view_count, DepthFrame f) {
+  pdl_prologue();
   const int n = *view_count;
   const int t = threadIdx.x;
   const int vx = t >> 6, vy = (t >> 3) & 7, vz = t & 7;
@@ -334,8 +354,8 @@ struct PlanesView {
 // per thread and compacts the surviving slots into shared memory, phase 2 deals them to the CTA's warps.
 // Small tiles spread the few hundred candidates of a mindmap workspace over many SMs.
 __device__ __forceinline__ void band_select_tile(const MapDev& m, const PlanesView& view, float trunc,
-                                                 int* band_slots, int tile, int tile_cells, int* s_cand,
-                                                 int* s_ncand) {
+                                                 int* band_slots, int* newfeat_slots, int tile, int tile_cells,
+                                                 int* s_cand, int* s_ncand) {
   const ViewGrid& g = view.g;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) *s_ncand = 0;
@@ -390,7 +410,8 @@ __device__ __forceinline__ void band_select_tile(const MapDev& m, const PlanesVi
           m.blk_layers[s] |= kLayerFeatBit;
           atomicAdd(&m.ctrl->n_feat, 1);
           count_add(m, kCntFeatBlocksAllocated, 1);
-          flag = kNewFlag;  // zero-filled by k_feature_geometry
+          newfeat_slots[atomicAdd(&m.ctrl->newfeat_count, 1)] = fs;
+          flag = kNewFlag;  // zero-filled (cooperatively, by all CTAs) in k_feature_geometry
         }
       }
       if (m.blk_feat[s] >= 0) band_slots[atomicAdd(&m.ctrl->band_count, 1)] = s | flag;
@@ -536,7 +557,9 @@ __device__ __forceinline__ void sphere_trace_ray(const MapDev& m, const TracePar
 // band_select_tile.  Both only read the TSDF layer; they overlap instead of queueing.
 __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp, float* __restrict__ image,
                                                         int trace_tiles_x, int n_trace_ctas, PlanesView view,
-                                                        float trunc, int* band_slots, int tile_cells, int n_tiles) {
+                                                        float trunc, int* band_slots, int* newfeat_slots,
+                                                        int tile_cells, int n_tiles) {
+  pdl_prologue();
   __shared__ int s_cand[256];
   __shared__ int s_ncand;
 #ifdef NVBX_PROFILE_COUNTERS
@@ -553,7 +576,7 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
     return;
   }
   for (int tile = (int)blockIdx.x - n_trace_ctas; tile < n_tiles; tile += (int)gridDim.x - n_trace_ctas)
-    band_select_tile(m, view, trunc, band_slots, tile, tile_cells, s_cand, &s_ncand);
+    band_select_tile(m, view, trunc, band_slots, newfeat_slots, tile, tile_cells, s_cand, &s_ncand);
 #ifdef NVBX_PROFILE_COUNTERS
   if (threadIdx.x == 0) atomicMax(&m.ctrl->counters[15], (unsigned long long)(clock64() - t0));
 #endif
@@ -637,9 +660,11 @@ struct __align__(16) FeatItem {
   int row;                // feature voxel row: feature_slot * 512 + voxel
 };
 
-__global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* __restrict__ band_slots, FeatFrame f,
+__global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* __restrict__ band_slots,
+                                                          const int* __restrict__ newfeat_slots, FeatFrame f,
                                                           FeatItem* __restrict__ items, int block_begin,
                                                           int block_end) {
+  pdl_prologue();
   __shared__ int s_warp_base[17];
   __shared__ int s_base;
   const int n = min(m.ctrl->band_count, block_end);
@@ -649,6 +674,20 @@ __global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* _
   const int C = m.C;
   unsigned long long n_updated = 0;
 
+  // Zero-fill the feature blocks allocated by this frame (blox_impl.h:92-97), every CTA taking an equal
+  // slice of each, so that a 794 KB block costs each SM a few KB; the gather kernel runs after us.
+  if (block_begin == 0) {
+    const int n_new = m.ctrl->newfeat_count;
+    const int vec_per_block = (kVoxelsPerBlock * m.row) / 8;
+    const int per_cta = (vec_per_block + gridDim.x - 1) / gridDim.x;
+    const int k0 = blockIdx.x * per_cta, k1 = min(vec_per_block, k0 + per_cta);
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int j = 0; j < n_new; ++j) {
+      uint4* p = reinterpret_cast<uint4*>(feat_block(m, newfeat_slots[j]));
+      for (int k = k0 + t; k < k1; k += 512) p[k] = z;
+    }
+  }
+
   for (int bi = block_begin + blockIdx.x; bi < n; bi += gridDim.x) {
     const int raw = band_slots[bi];
     const bool is_new = (raw & kNewFlag) != 0;
@@ -657,12 +696,6 @@ __global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* _
     const int fs = m.blk_feat[slot];
     __half* blk = feat_block(m, fs);
     if (t == 0) m.blk_dirty[slot] = 1;  // mapper.cpp:462
-    if (is_new) {                       // zero-fill (blox_impl.h:92-97); the gather kernel runs after us
-      uint4* p = reinterpret_cast<uint4*>(blk);
-      const int vec_per_block = (kVoxelsPerBlock * m.row) / 8;
-      const uint4 z = make_uint4(0, 0, 0, 0);
-      for (int k = t; k < vec_per_block; k += 512) p[k] = z;
-    }
 
     bool active = false;
     FeatItem it;
@@ -727,6 +760,7 @@ __global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* _
 template <int CH, int U, int CTAS>  // U: units in flight per warp; CTAS: resident CTAs per SM (register budget)
 __global__ void __launch_bounds__(256, CTAS) k_feature_gather(MapDev m, const FeatItem* __restrict__ items,
                                                               FeatFrame f, int last_chunk) {
+  pdl_prologue();
   const int n_items = m.ctrl->item_count;
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
@@ -782,7 +816,8 @@ __global__ void __launch_bounds__(256, CTAS) k_feature_gather(MapDev m, const Fe
   }
   if (last_chunk && blockIdx.x == 0 && threadIdx.x == 0) {
     m.ctrl->last_band_count = m.ctrl->band_count;
-    m.ctrl->band_count = 0;  // ready for the next frame's k_band_select
+    m.ctrl->band_count = 0;  // ready for the next frame's band_select_tile
+    m.ctrl->newfeat_count = 0;
   }
 }
 
@@ -801,6 +836,7 @@ struct DecayParams {
 };
 
 __global__ void __launch_bounds__(256) k_decay(MapDev m, DecayParams dp) {
+  pdl_prologue();
   const int n = m.ctrl->slot_high;
   const float lo = dp.threshold - 1e-6f;
   const float hi = dp.threshold + 1e-6f;
@@ -849,11 +885,13 @@ __global__ void __launch_bounds__(256) k_decay(MapDev m, DecayParams dp) {
 // Overflow-hash rebuild after releases of hash-resident blocks (three tiny launches, all no-ops unless
 // ctrl->rebuild is set; blocks inside the workspace grid never set it).
 __global__ void __launch_bounds__(256) k_hash_clear(MapDev m, int force) {
+  pdl_prologue();
   if (!force && !m.ctrl->rebuild) return;
   const unsigned n = m.hash_mask + 1;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m.keys[i] = kEmptyKey;
 }
 __global__ void __launch_bounds__(256) k_hash_reinsert(MapDev m, int force) {
+  pdl_prologue();
   if (!force && !m.ctrl->rebuild) return;
   const int n = m.ctrl->slot_high;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
@@ -863,10 +901,12 @@ __global__ void __launch_bounds__(256) k_hash_reinsert(MapDev m, int force) {
     }
   }
 }
-__global__ void k_hash_rebuild_done(MapDev m) { m.ctrl->rebuild = 0; }
+__global__ void k_hash_rebuild_done(MapDev m) {
+  pdl_prologue(); m.ctrl->rebuild = 0; }
 
 // Mapper::clear (py_mapper.cu:286-306): drop every block of every layer.
 __global__ void __launch_bounds__(256) k_clear_all(MapDev m) {
+  pdl_prologue();
   const unsigned n = m.hash_mask + 1;
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m.keys[i] = kEmptyKey;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m.ws_cells; i += gridDim.x * blockDim.x) m.ws_slot[i] = -1;
@@ -874,6 +914,7 @@ __global__ void __launch_bounds__(256) k_clear_all(MapDev m) {
     Ctrl* c = m.ctrl;
     c->n_hash = 0;
     c->band_count = 0;
+    c->newfeat_count = 0;
     c->item_count = 0;
     c->slot_free_top = 0;
     c->slot_high = 0;
@@ -891,6 +932,7 @@ __global__ void __launch_bounds__(256) k_clear_all(MapDev m) {
 // a13. Layer views and point queries.
 // ================================================================================================
 __global__ void __launch_bounds__(256) k_collect_block_indices(MapDev m, uint8_t layer_bit, int3* out, int capacity) {
+  pdl_prologue();
   const int n = m.ctrl->slot_high;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     if (m.blk_layers[s] & layer_bit) {
@@ -902,6 +944,7 @@ __global__ void __launch_bounds__(256) k_collect_block_indices(MapDev m, uint8_t
 
 // single-thread helpers for allocate_block_at_index / get_block_at_index
 __global__ void k_allocate_one(MapDev m, int x, int y, int z, int layer, int* newfeat_slot_out) {
+  pdl_prologue();
   bool is_new;
   const int slot = acquire_slot(m, x, y, z, &is_new);
   *newfeat_slot_out = -1;
@@ -925,6 +968,7 @@ __global__ void k_allocate_one(MapDev m, int x, int y, int z, int layer, int* ne
   }
 }
 __global__ void k_zero_one_feature_block(MapDev m, const int* fslot) {
+  pdl_prologue();
   if (*fslot < 0) return;
   uint4* p = reinterpret_cast<uint4*>(feat_block(m, *fslot));
   const int vec_per_block = (kVoxelsPerBlock * m.row) / 8;
@@ -932,6 +976,7 @@ __global__ void k_zero_one_feature_block(MapDev m, const int* fslot) {
     p[k] = make_uint4(0, 0, 0, 0);
 }
 __global__ void k_find_one(MapDev m, int x, int y, int z, int layer, unsigned long long* ptr_out) {
+  pdl_prologue();
   const int slot = find_slot(m, x, y, z);
   *ptr_out = 0ull;
   if (slot < 0) return;
@@ -945,6 +990,7 @@ __global__ void k_find_one(MapDev m, int x, int y, int z, int layer, unsigned lo
 // queryTSDFKernel (NT/cpp/src/sdf_query.cu:240-270): one thread per query, rows of misses untouched.
 __global__ void __launch_bounds__(128) k_query_tsdf(MapDev m, const float* __restrict__ xyz, long long n,
                                                     float2* __restrict__ out) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   V3 p;
@@ -961,6 +1007,7 @@ __global__ void __launch_bounds__(128) k_query_tsdf(MapDev m, const float* __res
 // (2-byte aligned), so lanes write single halves, coalesced.
 __global__ void __launch_bounds__(128) k_query_features(MapDev m, const float* __restrict__ xyz, long long n,
                                                         __half* __restrict__ out) {
+  pdl_prologue();
   const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= n) return;
   V3 p;

@@ -321,6 +321,7 @@ __device__ void mesh_one_block(const MapDev& m, const MeshParams& mp, MeshSmem& 
 
 // pass 1: per-slot sizes of the NEW mesh
 __global__ void __launch_bounds__(512, 2) k_mesh_count(MapDev m, MeshParams mp, int* cnt_v, int* cnt_t) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MeshSmem& s = *reinterpret_cast<MeshSmem*>(smem_raw);
   const int n = m.ctrl->slot_high;
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(512, 2) k_mesh_count(MapDev m, MeshParams mp, 
 // device-side exclusive scan over the slot table (single CTA; the table is small)
 __global__ void __launch_bounds__(1024) k_mesh_scan(MapDev m, const int* cnt_v, const int* cnt_t, int* off_v,
                                                     int* off_t) {
+  pdl_prologue();
   __shared__ int ws_v[33], ws_t[33];
   __shared__ int carry_v, carry_t;
   const int n = m.ctrl->slot_high;
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(1024) k_mesh_scan(MapDev m, const int* cnt_v, 
 // pass 2: write the new arena; clean blocks are copied from the previous arena
 __global__ void __launch_bounds__(512, 2) k_mesh_emit(MapDev m, MeshParams mp, const int* off_v, const int* off_t,
                                                       MeshArena prev, MeshArena out) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MeshSmem& s = *reinterpret_cast<MeshSmem*>(smem_raw);
   const int n = m.ctrl->slot_high;

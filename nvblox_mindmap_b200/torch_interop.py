@@ -29,5 +29,11 @@ def device_view(ptr, shape, dtype, device_index, strides_elems=None, owner=None)
     return torch.as_tensor(_DeviceBlob(ptr, shape, dtype, strides_elems, owner), device=f'cuda:{device_index}')
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def current_stream_ptr(device_index: int) -> int:
+    """cudaStream_t of torch's current stream on `device_index` (the stream all our kernels ride on)."""
+    if _raw_stream is not None:
+        return int(_raw_stream(device_index))
     return int(torch.cuda.current_stream(device_index).cuda_stream)

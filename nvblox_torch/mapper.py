@@ -32,8 +32,23 @@ class QueryType(Enum):
     COLOR = 'color'
 
 
-def _pose16(t_w_c: torch.Tensor):
-    return (C.c_float * 16)(*t_w_c.reshape(-1).tolist())
+def _pose16(t_w_c: torch.Tensor) -> int:
+    """Address of the 16 row-major floats of a CPU pose tensor (read synchronously by the C ABI)."""
+    if not t_w_c.is_contiguous():
+        t_w_c = t_w_c.contiguous()
+        _pose16.keepalive = t_w_c
+    return t_w_c.data_ptr()
+
+
+_F9 = C.c_float * 9
+
+
+def _fxfycxcy(intrinsics: torch.Tensor):
+    """(fx, fy, cx, cy) of a CPU float32 3x3 tensor without four tensor-indexing round trips."""
+    if not intrinsics.is_contiguous():
+        intrinsics = intrinsics.contiguous()
+    k = _F9.from_address(intrinsics.data_ptr())
+    return k[0], k[4], k[2], k[5]
 
 
 class Mapper:
@@ -113,10 +128,10 @@ class Mapper:
         check_integrator_inputs(depth_frame, t_w_c, intrinsics, 'Depth', 2, torch.float32)
         depth_frame = depth_frame if depth_frame.is_contiguous() else depth_frame.contiguous()
         mask_ptr = self._mask_ptr(mask_frame, depth_frame)
-        k = intrinsics
+        fx, fy, cx, cy = _fxfycxcy(intrinsics)
         _capi.check(self._lib.nvbx_integrate_depth(
             self._handle, mapper_id, depth_frame.data_ptr(), depth_frame.shape[0], depth_frame.shape[1], mask_ptr,
-            _pose16(t_w_c), float(k[0, 0]), float(k[1, 1]), float(k[0, 2]), float(k[1, 2]), self._stream()))
+            _pose16(t_w_c), fx, fy, cx, cy, self._stream()))
 
     def add_color_frame(self,
                         color_frame: torch.Tensor,
@@ -128,10 +143,10 @@ class Mapper:
         assert 0 <= mapper_id < len(self._voxel_sizes)
         check_integrator_inputs(color_frame, t_w_c, intrinsics, 'Color', 3, torch.uint8, 3)
         mask_ptr = self._mask_ptr(mask_frame, color_frame)
-        k = intrinsics
+        fx, fy, cx, cy = _fxfycxcy(intrinsics)
         _capi.check(self._lib.nvbx_integrate_color(
             self._handle, mapper_id, color_frame.data_ptr(), color_frame.shape[0], color_frame.shape[1], mask_ptr,
-            _pose16(t_w_c), float(k[0, 0]), float(k[1, 1]), float(k[0, 2]), float(k[1, 2]), self._stream()))
+            _pose16(t_w_c), fx, fy, cx, cy, self._stream()))
 
     def add_feature_frame(self,
                           feature_frame: torch.Tensor,
@@ -144,22 +159,21 @@ class Mapper:
         check_integrator_inputs(feature_frame, t_w_c, intrinsics, 'Feature', 3, torch.float16, self._feature_channels)
         feature_frame = feature_frame if feature_frame.is_contiguous() else feature_frame.contiguous()
         mask_ptr = self._mask_ptr(mask_frame, feature_frame)
-        k = intrinsics
+        fx, fy, cx, cy = _fxfycxcy(intrinsics)
         _capi.check(self._lib.nvbx_integrate_features(
             self._handle, mapper_id, feature_frame.data_ptr(), feature_frame.shape[0], feature_frame.shape[1],
-            feature_frame.shape[2], mask_ptr, _pose16(t_w_c), float(k[0, 0]), float(k[1, 1]), float(k[0, 2]),
-            float(k[1, 2]), self._stream()))
+            feature_frame.shape[2], mask_ptr, _pose16(t_w_c), fx, fy, cx, cy, self._stream()))
 
     def integrate_frame_from_host(self, depth, features, t_w_c, intrinsics, depth_mask=None, feature_mask=None,
                                   mapper_id: int = 0) -> None:
         """(ours) depth + feature frame from HOST (ideally pinned) tensors; H2D copies ride the stream."""
         assert depth.dtype == torch.float32 and features.dtype == torch.float16 and not depth.is_cuda
-        k = intrinsics
+        fx, fy, cx, cy = _fxfycxcy(intrinsics)
         _capi.check(self._lib.nvbx_integrate_frame_host(
             self._handle, mapper_id, depth.data_ptr(), features.data_ptr(), depth.shape[0], depth.shape[1],
             features.shape[2], None if depth_mask is None else depth_mask.data_ptr(),
-            None if feature_mask is None else feature_mask.data_ptr(), _pose16(t_w_c), float(k[0, 0]), float(k[1, 1]),
-            float(k[0, 2]), float(k[1, 2]), self._stream()))
+            None if feature_mask is None else feature_mask.data_ptr(), _pose16(t_w_c), fx, fy, cx, cy,
+            self._stream()))
 
     # -- map maintenance ------------------------------------------------------------------------------------
     def decay(self, mapper_id: int = -1) -> None:

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# fresh device arenas are filled with garbage in the tests: a block that is not properly initialised must
+# fail parity instead of hiding behind zero pages from cudaMalloc (read once, when libnvbx.so is loaded)
+os.environ.setdefault('NVBX_POISON_ARENAS', '1')
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
