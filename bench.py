@@ -50,55 +50,53 @@ def mapper_params():
 
 
 def poses_and_depths(n):
+    """(K, [(T_W_C, depth)] * n): the 64-pose orbit, repeated when n > 64 (rendered once per pose)."""
     K = S.intrinsics(W, H)
-    out = []
-    for i in range(n):
-        T = S.orbit_pose(i % N_POSES, N_POSES)
-        out.append((T, S.render_depth(K, H, W, T, **S.S_TABLE)))
-    return K, out
+    uniq = []
+    for i in range(min(n, N_POSES)):
+        T = S.orbit_pose(i, N_POSES)
+        uniq.append((T, S.render_depth(K, H, W, T, **S.S_TABLE)))
+    return K, [uniq[i % N_POSES] for i in range(n)]
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region through NVML (every ~2 ms; the
+    nvidia-smi CLI of the profiling recipe needs ~1 s to produce its first line, longer than the region)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+        self.index, self.rows, self.stop_flag, self.max_mhz = index, [], False, None
+        self.armed = threading.Event()
 
     def run(self):
-        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                self.rows.append([x.strip() for x in line.split(',')])
-        except Exception:
-            pass
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            bits = {'hw_slowdown': N.nvmlClocksEventReasonHwSlowdown,
+                    'hw_thermal_slowdown': N.nvmlClocksEventReasonHwThermalSlowdown,
+                    'sw_thermal_slowdown': N.nvmlClocksEventReasonSwThermalSlowdown,
+                    'sw_power_cap': N.nvmlClocksEventReasonSwPowerCap}
+            get_reasons = getattr(N, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                N.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.armed.set()
+            while not self.stop_flag:
+                r = get_reasons(h)
+                self.rows.append((float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)),
+                                  [k for k, b in bits.items() if r & b]))
+                time.sleep(0.002)
+        except Exception as e:      # NVML missing: report no samples rather than fail the bench
+            self.error = repr(e)
+            self.armed.set()
 
     def finish(self):
         self.stop_flag = True
-        if self.proc:
-            try:
-                self.proc.terminate()
-            except Exception:
-                pass
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'),
-                                   r[2:6]):
-                    if v.lower().startswith('active'):
-                        reasons.add(name)
-            except Exception:
-                continue
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        self.join(timeout=2.0)
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({x for r in self.rows for x in r[1]})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.max_mhz,
+                'reasons': reasons, 'samples': len(sm), 'source': 'NVML, 2 ms period, device-timed region only'}
 
 
 def measured_peak_gbs():
@@ -143,7 +141,9 @@ def run_reference(args, rank, world):
     threads = len(os.sched_getaffinity(0))
     O.set_threads(threads)
     _, op = mapper_params()
-    K, frames = poses_and_depths(args.warmup + args.steps)
+    # bounded sample: the CPU path runs at a few frames/s, so at most 64 timed + 4 warm-up frames of the workload
+    n_warm, n_timed = min(args.warmup, 4), min(args.steps, 64)
+    K, frames = poses_and_depths(n_warm + n_timed)
     m = O.OracleMapper(VOXEL, C_FEAT, op)
     feats = [S.feature_frame(H, W, C_FEAT, 1000 + i) for i in range(min(N_FEATURE_BUFFERS, len(frames)))]
     t_timed = 0.0
@@ -151,17 +151,18 @@ def run_reference(args, rank, world):
         t0 = time.perf_counter()
         m.add_depth_frame(depth, T, K)
         m.add_feature_frame(feats[i % len(feats)], T, K)
-        if i >= args.warmup:
+        if i >= n_warm:
             t_timed += time.perf_counter() - t0
-    value = args.steps / t_timed
+    value = n_timed / t_timed
     line = {
         'impl': 'reference', 'metric': 'feature frames integrated/s (C=768, 512^2)', 'value': value,
-        'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1000.0 * t_timed / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': n_timed, 'warmup': n_warm,
+        'requested_steps': args.steps, 'requested_warmup': args.warmup,
+        'ms_per_step': 1000.0 * t_timed / n_timed, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32 geometry + f16 features', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'voxel_size_m': VOXEL, 'workspace': 'cube_stacking box'},
         'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
-                         'sample': f'{args.steps} frames of the workload after {args.warmup} warm-up frames; the '
+                         'sample': f'{n_timed} frames of the workload after {n_warm} warm-up frames (bounded); the '
                                    'reference itself cannot be built offline (Eigen/stdgpu/glog absent), so this is '
                                    'the oracle port of its algorithm with OpenMP over blocks'},
         'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -214,6 +215,8 @@ def run_ours(args, rank, world, local_rank):
     mapper.reset_counters(0)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.armed.wait(5.0)
+    sampler.rows.clear()
     launches0 = int(lib.nvbx_kernel_launch_count())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -278,16 +281,21 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        sample = oracle_sample(2, 1)
-        sample_mt = oracle_sample(2, len(os.sched_getaffinity(0)))
+        n_cores = len(os.sched_getaffinity(0))
+        sample = oracle_sample(4, 1)                    # ~6 s of single-thread CPU work
+        sample_mt = oracle_sample(24, n_cores)          # ~4-20 s with every host thread
         n_upd = counters['feature_voxels_updated'] / args.steps
-        n_cand = counters['feature_candidate_blocks'] / args.steps
-        px_per_voxel = sample['u_px'] / max(1, sample['n_upd'])
-        # B_feat: 2C*U_px + 2(C+1)*N_upd + 2*N_upd + 4096*N_cand + 8*(H/4)(W/4) + N_upd, alpha = 1
-        b_feat = (2 * C_FEAT * px_per_voxel * n_upd + 2 * (C_FEAT + 1) * n_upd + 2 * n_upd + 4096 * n_cand +
-                  8 * (H // 4) * (W // 4) + n_upd)
+        px_per_voxel = sample_mt['u_px'] / max(1, sample_mt['n_upd'])
+        # Algorithmic bytes of the dominant kernel (k_feature_gather) per launch, alpha = 1:
+        # 2C bytes per DISTINCT feature pixel read + 2(C+1) bytes per voxel row written.  N_upd comes from the
+        # device counters of the timed region, distinct pixels per voxel from the oracle sample.
+        b_feat = 2 * C_FEAT * px_per_voxel * n_upd + 2 * (C_FEAT + 1) * n_upd
         kms = kernel_time_ms(args, mapper, depths, poses, feats, K_t)
         achieved = b_feat / (kms * 1e-3) / 1e9 if kms else None
+        traffic, traffic_src = ncu_traffic_bytes()
+        sub = argparse.Namespace(steps=min(args.steps, 128), warmup=args.warmup)
+        per_kernel = per_kernel_us(sub, mapper, depths, poses, feats, K_t)
+        export = export_stage(mapper)
         line = {
             'metric': 'feature frames integrated/s (C=768, 512^2)', 'value': value, 'unit': 'frames/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
@@ -302,16 +310,20 @@ def run_ours(args, rank, world, local_rank):
                     'steps': n_e2e},
             'gpu_launches': launches,
             'clocks': clocks,
-            'roofline': {'bound': 'hbm', 'kernel': 'k_feature_integrate<3>', 'achieved': achieved, 'peak': peak,
-                         'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None, 'traffic': None,
+            'roofline': {'bound': 'hbm', 'kernel': 'k_feature_gather<3,1,4>', 'achieved': achieved, 'peak': peak,
+                         'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None, 'traffic': traffic,
+                         'traffic_source': traffic_src,
                          'peak_source': peak_src, 'kernel_ms': kms, 'algorithmic_bytes_per_launch': b_feat,
                          'n_upd_per_frame': n_upd, 'distinct_pixels_per_voxel': px_per_voxel,
                          'frac_of_nominal_8TBps': (achieved / 8000.0) if achieved else None},
-            'cpu_baseline': {'value': sample['fps'], 'unit': 'frames/s', 'cores': 1, 'kind': 'port',
-                             'sample': 'first 2 frames of the workload through the CPU oracle (1 thread); '
-                                       f"{sample_mt['threads']} threads: {sample_mt['fps']:.3f} frames/s"},
-            'extra': {'feature_call_ms': feat_call_ms, 'counters_per_step': {k: v / args.steps
-                                                                            for k, v in counters.items()}},
+            'cpu_baseline': {'value': sample_mt['fps'], 'unit': 'frames/s', 'cores': n_cores, 'kind': 'port',
+                             'sample': f"first {sample_mt['frames']} frames of the workload through the CPU oracle "
+                                       f"(OpenMP over blocks, {n_cores} threads, {sample_mt['seconds']:.1f} s); "
+                                       f"1 thread, first {sample['frames']} frames: {sample['fps']:.3f} frames/s"},
+            'extra': {'feature_call_ms': feat_call_ms, 'host_enqueue_ms_per_step': 1000.0 * t_host / args.steps,
+                      'per_kernel_us_in_pipeline': per_kernel, 'export_stage': export,
+                      'counters_per_step': {k: v / args.steps for k, v in counters.items()
+                                            if isinstance(v, (int, float))}},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -340,6 +352,43 @@ def kernel_time_ms(args, mapper, depths, poses, feats, K_t):
     return (ms.value / n.value) if n.value else None
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary
+    (profiles/r01b_feature_gather.md: dram__bytes_read.sum + dram__bytes_write.sum, first capture)."""
+    path = os.path.join(ROOT, 'profiles', 'r01b_feature_gather.md')
+    try:
+        rd = wr = None
+        for line in open(path):
+            cells = [c.strip() for c in line.split('|')]
+            if len(cells) > 3 and cells[1] == 'dram__bytes_read.sum' and rd is None:
+                rd = float(cells[2]) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}[cells[3]]
+            if len(cells) > 3 and cells[1] == 'dram__bytes_write.sum' and wr is None:
+                wr = float(cells[2]) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}[cells[3]]
+        if rd is not None and wr is not None:
+            return rd + wr, 'profiles/r01b_feature_gather.md (ncu --set full, one launch of the same workload)'
+    except Exception:
+        pass
+    return None, None
+
+
+def export_stage(mapper, n=8):
+    """Per-step export as mindmap runs it (decay -> update_feature_mesh -> get_feature_mesh), device-timed."""
+    import torch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    nv = 0
+    for a, b in ev:
+        a.record()
+        mapper.decay()
+        mapper.update_feature_mesh(0)
+        mesh = mapper.get_feature_mesh(0)
+        nv = int(mesh.vertices().shape[0])
+        b.record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in ev)
+    return {'ms_median': ms[len(ms) // 2], 'vertices': nv,
+            'note': 'decay marks every block dirty, so each update re-meshes the whole map (SURVEY 3.4)'}
+
+
 def per_kernel_us(args, mapper, depths, poses, feats, K_t):
     """In-pipeline duration of every kernel (event pair around each launch; includes the launch gap)."""
     import ctypes as C
@@ -360,8 +409,8 @@ def per_kernel_us(args, mapper, depths, poses, feats, K_t):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=64)
-    ap.add_argument('--warmup', type=int, default=8)
+    ap.add_argument('--steps', type=int, default=1024)
+    ap.add_argument('--warmup', type=int, default=64)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--quick', action='store_true', help='tuning aid: device-timed pass + kernel timing only')
     args = ap.parse_args()

@@ -123,3 +123,86 @@ def test_unbounded_workspace_and_subsampling():
     assert pair.check_tsdf() > 0
     assert pair.check_features() > 0
     assert pair.check_mesh() > 0
+
+
+def test_full_size_cube_stacking_frames():
+    """BASELINE configs[1] at FULL size (512x512, C=768, 2 cm, mindmap parameters): two frames of the bench
+    workload, every product bit-exact against the oracle (features within 1 ulp: alpha == 1 fast path)."""
+    mp, op = make_params(workspace=S.WS_CUBE_STACKING)
+    pair = Pair(0.02, 768, mp, op)
+    K = S.intrinsics(512, 512)
+    for i in range(2):
+        T = S.orbit_pose(i)
+        depth = S.render_depth(K, 512, 512, T, **S.S_TABLE)
+        pair.depth(depth, T, K)
+        g, c = pair.last_block_list(0)
+        assert np.array_equal(g, c) and len(g) > 300
+        pair.features(S.feature_frame(512, 512, 768, 1000 + i), T, K)
+        g, c = pair.last_block_list(1)
+        assert np.array_equal(g, c) and len(g) > 80
+        gs, cs = pair.synthetic_depth()
+        assert np.array_equal(gs.view(np.uint32), cs.view(np.uint32))
+    assert pair.check_tsdf() > 300
+    assert pair.check_features(max_ulp=1) > 80
+    assert pair.check_mesh() > 1000
+    gc, cc = pair.gpu.counters(0), pair.cpu.counters()
+    assert gc['feature_voxels_updated'] == cc['feature_voxels_updated'] > 30000
+
+
+def test_drill_in_box_two_cameras_1cm():
+    """BASELINE configs[2] scaled to 160x160: head (static -> viewpoint cache hits) + wrist camera, 1 cm voxels,
+    drill-in-box workspace (3 740-cell index grid), decay 0.999, mesh each step."""
+    mp, op = make_params(workspace=S.WS_DRILL_IN_BOX, decay=0.999)
+    pair = Pair(0.01, 64, mp, op)
+    K = S.intrinsics(160, 160)
+    T_head = S.look_at((-0.2, 0.0, 0.6), (0.4, 0.0, 0.05))
+    for i in range(3):
+        if i:
+            pair.decay()
+        for cam, T in (('head', T_head), ('wrist', S.orbit_pose(i, 64, 0.4, 0.45))):
+            depth = S.render_depth(K, 160, 160, T, **S.S_TABLE)
+            pair.depth(depth, T, K)
+            g, c = pair.last_block_list(0)
+            assert np.array_equal(g, c), cam
+            pair.features(S.feature_frame(160, 160, 64, 500 + 2 * i + (cam == 'wrist')), T, K)
+            g, c = pair.last_block_list(1)
+            assert np.array_equal(g, c), cam
+        pair.check_tsdf()
+        pair.check_features(max_ulp=1)
+        assert pair.check_mesh() > 0
+
+
+def test_two_mappers_static_dynamic():
+    """mindmap creates two maps (static / dynamic, nvblox_mapping_helpers.py:72-76): they must not interact."""
+    import torch
+    from nvblox_torch.constants import constants
+    from nvblox_torch.mapper import Mapper
+    from oracle import oracle as O
+    mp, op = make_params(workspace=S.WS_CUBE_STACKING)
+    constants.set_feature_array_num_elements(16)
+    gpu = Mapper(voxel_sizes_m=[0.02, 0.04], mapper_parameters=mp)
+    cpu = [O.OracleMapper(0.02, 16, op), O.OracleMapper(0.04, 16, op)]
+    assert gpu.num_mappers() == 2
+    K = S.intrinsics(96, 96)
+    for i in range(3):
+        T = S.orbit_pose(i)
+        depth = S.render_depth(K, 96, 96, T, **S.S_TABLE)
+        feat = S.feature_frame(96, 96, 16, 700 + i)
+        mid = i % 2
+        gpu.add_depth_frame(torch.from_numpy(depth).cuda(), torch.from_numpy(T), torch.from_numpy(K), None, mid)
+        gpu.add_feature_frame(torch.from_numpy(feat).cuda(), torch.from_numpy(T), torch.from_numpy(K), None, mid)
+        cpu[mid].add_depth_frame(depth, T, K)
+        cpu[mid].add_feature_frame(feat, T, K)
+    gpu.decay()          # mapper_id = -1: all maps
+    for c in cpu:
+        c.decay()
+    from tests.parity_utils import gpu_blocks
+    for mid in range(2):
+        gi, gd = gpu_blocks(gpu.tsdf_layer_view(mid))
+        ci, cd = cpu[mid].all_blocks(0)
+        assert np.array_equal(gi, ci) and len(gi) > 0
+        assert np.array_equal(gd.view(np.uint32), cd.view(np.uint32))
+        gi, gd = gpu_blocks(gpu.feature_layer_view(mid))
+        ci, cd = cpu[mid].all_blocks(1)
+        assert np.array_equal(gi, ci) and len(gi) > 0
+        assert np.array_equal(gd.view(np.uint16)[..., -1], cd.view(np.uint16)[..., -1])
