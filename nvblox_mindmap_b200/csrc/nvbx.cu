@@ -188,6 +188,9 @@ struct Map {
   CacheEntry scratch_ray, scratch_planes;  // used when the cache is disabled
   DevBuf<unsigned> grid;   // view bitmap; all-zero between frames (k_view_compact_alloc cleans it)
   bool grid_dirty = false;  // a frame failed between marking and compaction
+  unsigned* small_grid[2] = {nullptr, nullptr};  // double-buffered bitmap of small views (2 x kFusedBitmapWords)
+  int small_cur = 0;
+  bool small_dirty = false;
   DevBuf<int> view_slots, band_slots, newfeat_slots;
   DevBuf<FeatItem> items;
   DevBuf<float> synth;
@@ -464,6 +467,9 @@ int init_map(nvbx_mapper* m, Map& mp, float voxel_size, cudaStream_t stream) {
   CUDA_TRY(cudaMalloc(&mp.d_tmp_int, sizeof(int)));
   CUDA_TRY(cudaMalloc(&mp.d_tmp_ptr, sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc(&mp.scratch_ray.d_count, sizeof(int)));
+  CUDA_TRY(cudaMalloc(&mp.small_grid[0], 2 * kFusedBitmapWords * sizeof(unsigned)));
+  CUDA_TRY(cudaMemsetAsync(mp.small_grid[0], 0, 2 * kFusedBitmapWords * sizeof(unsigned), stream));
+  mp.small_grid[1] = mp.small_grid[0] + kFusedBitmapWords;
   // level-1 index: direct-mapped grid over the workspace box (same rounding as make_grid)
   if (m->params.workspace_bounds_type == NVBX_WORKSPACE_BOUNDING_BOX) {
     Aabb a;
@@ -526,6 +532,8 @@ void destroy_map(Map& mp) {
   mp.scratch_ray.idx.release();
   mp.scratch_planes.idx.release();
   F(mp.scratch_ray.d_count);
+  F(mp.small_grid[0]);
+  mp.small_grid[1] = nullptr;
   mp.grid.release();
   mp.view_slots.release();
   mp.band_slots.release();
@@ -729,13 +737,13 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
   const Cam cam = make_cam(fx, fy, cx, cy, height, width);
   const float trunc = p.truncation_distance_vox * mp.voxel_size;
 
+  ViewSource vs{};
+  int view_mode;
   CacheEntry* entry = p.cache_last_viewpoint ? mp.raycast_cache.lookup(T_L_C, cam) : nullptr;
   if (entry) {
-    // cache hit: previous block list, blocks (re-)allocated where required
+    // cache hit: previous block list, blocks (re-)allocated where required (inside the TSDF kernel)
     if ((rc = ensure_slots(m, mp, entry->bound, stream))) return rc;
-    if ((rc = mp.view_slots.ensure((size_t)entry->bound, stream))) return rc;
-    LAUNCH(k_view_alloc_from_list, persistent_grid(m, 2), 256, 0, stream, mp.dev, entry->idx.p, entry->d_count,
-           mp.view_slots.p);
+    view_mode = kViewFromEntry;
   } else {
     GridSpec gs;
     if ((rc = make_grid(m, mp, view_aabb(cam, T_L_C, 0.0f, p.max_integration_distance_m), &gs))) return rc;
@@ -751,11 +759,24 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
     const size_t n = (size_t)gs.g.n_cells;
     const size_t n_words = (n + 31) / 32;
     if ((rc = entry->idx.ensure(n, stream))) return rc;
-    const unsigned* old_grid = mp.grid.p;
-    if ((rc = mp.grid.ensure(n_words, stream))) return rc;
-    if (mp.grid.p != old_grid || mp.grid_dirty)  // a fresh (or abandoned) bitmap starts all-zero
-      CUDA_TRY(cudaMemsetAsync(mp.grid.p, 0, mp.grid.cap * sizeof(unsigned), stream));
-    if ((rc = mp.view_slots.ensure(n, stream))) return rc;
+    // Small views (<= 32 768 cells: every mindmap workspace) mark one half of a double-buffered bitmap and the
+    // TSDF kernel compacts it itself; larger views use the growable bitmap + k_view_compact_alloc.
+    const bool fused = n_words <= (size_t)kFusedBitmapWords;
+    unsigned* bits;
+    if (fused) {
+      if (mp.small_dirty) {
+        CUDA_TRY(cudaMemsetAsync(mp.small_grid[0], 0, 2 * kFusedBitmapWords * sizeof(unsigned), stream));
+        mp.small_dirty = false;
+      }
+      bits = mp.small_grid[mp.small_cur];
+    } else {
+      const unsigned* old_grid = mp.grid.p;
+      if ((rc = mp.grid.ensure(n_words, stream))) return rc;
+      if (mp.grid.p != old_grid || mp.grid_dirty)  // a fresh (or abandoned) bitmap starts all-zero
+        CUDA_TRY(cudaMemsetAsync(mp.grid.p, 0, mp.grid.cap * sizeof(unsigned), stream));
+      if ((rc = mp.view_slots.ensure(n, stream))) return rc;
+      bits = mp.grid.p;
+    }
     entry->T = T_L_C;
     entry->cam = cam;
     entry->bound = gs.g.n_cells;
@@ -766,7 +787,7 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
     // one tile per CTA while they all fit on the machine at once (8 CTAs of 256 threads per SM): the hardware
     // scheduler then balances tiles of unequal cost; larger images loop
     const int rgrid = std::max(1, std::min(n_tiles, persistent_grid(m, 8)));
-    mp.grid_dirty = true;
+    (fused ? mp.small_dirty : mp.grid_dirty) = true;
     RaycastFrame rf;
     rf.T_L_C = T_L_C;
     rf.cam = cam;
@@ -788,9 +809,9 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
     rf.tiles_x = tiles_x;
     rf.n_tiles = n_tiles;
     if (n_words <= (size_t)kRayBitmapWords) {
-      LAUNCH(k_raycast_mark<true>, rgrid, 256, n_words * sizeof(unsigned), stream, rf, mp.grid.p, entry->d_count);
+      LAUNCH(k_raycast_mark<true>, rgrid, 256, n_words * sizeof(unsigned), stream, rf, bits, entry->d_count);
     } else {
-      LAUNCH(k_raycast_mark<false>, rgrid, 256, 0, stream, rf, mp.grid.p, entry->d_count);
+      LAUNCH(k_raycast_mark<false>, rgrid, 256, 0, stream, rf, bits, entry->d_count);
     }
     const int cgrid = std::max(1, std::min(persistent_grid(m, 4), (int)((n_words + 7) / 8)));  // warp per word
     if (!slots_fit(m, mp, (long long)n)) {
@@ -798,18 +819,29 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
       // read that one int back.  Only happens while the arena is still growing (or with an unbounded
       // workspace); a bounded workspace reaches its cell count and never synchronises again.
       CUDA_TRY(cudaMemsetAsync(mp.d_tmp_int, 0, sizeof(int), stream));
-      LAUNCH(k_count_marked, cgrid, 256, 0, stream, mp.grid.p, (int)n_words, mp.d_tmp_int);
+      LAUNCH(k_count_marked, cgrid, 256, 0, stream, bits, (int)n_words, mp.d_tmp_int);
       int marked = 0;
       CUDA_TRY(cudaMemcpyAsync(&marked, mp.d_tmp_int, sizeof(int), cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(cudaStreamSynchronize(stream));
       entry->bound = std::max(1, marked);
     }
     if ((rc = ensure_slots(m, mp, (long long)entry->bound, stream))) return rc;
-    LAUNCH(k_view_compact_alloc, cgrid, 256, 0, stream, mp.dev, mp.grid.p, gs.g, entry->idx.p, entry->d_count,
-           mp.view_slots.p);
-    mp.grid_dirty = false;
+    if (fused) {
+      view_mode = kViewFromBitmap;
+      vs.bits = bits;
+      vs.clean_bits = mp.small_grid[mp.small_cur ^ 1];
+      vs.g = gs.g;
+    } else {
+      LAUNCH(k_view_compact_alloc, cgrid, 256, 0, stream, mp.dev, bits, gs.g, entry->idx.p, entry->d_count,
+             mp.view_slots.p);
+      mp.grid_dirty = false;
+      view_mode = kViewFromSlots;
+      vs.view_slots = mp.view_slots.p;
+    }
     if (p.cache_last_viewpoint) mp.raycast_cache.store(entry);
   }
+  vs.entry_idx = entry->idx.p;
+  vs.entry_count = entry->d_count;
   mp.last_depth_entry = entry;
   DepthFrame f;
   f.depth = (const float*)depth;
@@ -825,7 +857,15 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
   f.weighting_mode = p.weighting_mode;
   const int tgrid = std::max(1, std::min(persistent_grid(m, 3), entry->bound));  // one block per CTA up to 3 CTAs/SM
   if ((rc = timing_begin(m, 1, stream))) return rc;
-  LAUNCH(k_tsdf_update, tgrid, 512, 0, stream, mp.dev, mp.view_slots.p, entry->d_count, f);
+  if (view_mode == kViewFromBitmap) {
+    LAUNCH(k_tsdf_update<kViewFromBitmap>, tgrid, 512, 0, stream, mp.dev, vs, f);
+    mp.small_cur ^= 1;  // the other half was cleared by the kernel
+    mp.small_dirty = false;
+  } else if (view_mode == kViewFromEntry) {
+    LAUNCH(k_tsdf_update<kViewFromEntry>, tgrid, 512, 0, stream, mp.dev, vs, f);
+  } else {
+    LAUNCH(k_tsdf_update<kViewFromSlots>, tgrid, 512, 0, stream, mp.dev, vs, f);
+  }
   return timing_end(m, 1, stream);
 }
 

@@ -222,26 +222,6 @@ __global__ void __launch_bounds__(256) k_view_compact_alloc(MapDev m, unsigned* 
   }
 }
 
-// Viewpoint-cache hit: the cached index list is re-used as is (view_calculator.cu:256-265) and blocks
-// are (re-)allocated where required (projective_integrator_impl.cuh:288-291).
-__global__ void __launch_bounds__(256) k_view_alloc_from_list(MapDev m, const int3* __restrict__ entry_idx,
-                                                              const int* __restrict__ entry_count, int* view_slots) {
-  pdl_prologue();
-  const int n = *entry_count;
-  unsigned n_new = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int3 b = entry_idx[i];
-    bool is_new;
-    int slot = acquire_slot(m, b.x, b.y, b.z, &is_new);
-    if (slot >= 0 && ensure_tsdf_layer(m, slot)) {
-      slot |= kNewFlag;
-      ++n_new;
-    }
-    view_slots[i] = slot;
-  }
-  if (n_new) count_add(m, kCntTsdfBlocksAllocated, n_new);
-}
-
 // ================================================================================================
 // a4. TSDF update.  integrateBlocksKernel<TsdfVoxel> (projective_integrator_impl.cuh:58-103) +
 // UpdateTsdfVoxelFunctor (projective_tsdf_integrator.cu:25-99).  One CTA of 512 threads per block,
@@ -276,54 +256,162 @@ __device__ __forceinline__ bool project_voxel(const Cam& cam, const Pose& T_C_L,
   return true;
 }
 
-__global__ void __launch_bounds__(512, 3) k_tsdf_update(MapDev m, const int* __restrict__ view_slots,
-                                                        const int* __restrict__ view_count, DepthFrame f) {
-  pdl_prologue();
-  const int n = *view_count;
-  const int t = threadIdx.x;
+// One voxel of one block (thread t of the CTA); returns 1 if the voxel was fused with a measurement.
+__device__ __forceinline__ unsigned tsdf_update_voxel(const MapDev& m, const DepthFrame& f, int slot, bool is_new,
+                                                      int t) {
   const int vx = t >> 6, vy = (t >> 3) & 7, vz = t & 7;
+  const int3 b = m.blk_index[slot];
+  float2* vox = tsdf_block(m, slot) + t;
+  bool write = is_new;
+  float2 out = make_float2(0.0f, 0.0f);
   unsigned updated = 0;
-  for (int bi = blockIdx.x; bi < n; bi += gridDim.x) {
-    const int raw = view_slots[bi];
-    if (raw < 0) continue;
-    const bool is_new = (raw & kNewFlag) != 0;
-    const int slot = raw & kSlotMask;
-    if (t == 0) m.blk_dirty[slot] = 1;  // blocks_to_update_tracker_.addBlocksToUpdate (mapper.cpp:406)
-    const int3 b = m.blk_index[slot];
-    float2* vox = tsdf_block(m, slot) + t;
-    bool write = is_new;
-    float2 out = make_float2(0.0f, 0.0f);
-    do {
-      float u, v, vd;
-      if (!project_voxel(f.cam, f.T_C_L, m.block_size, f.max_depth, b, vx, vy, vz, &u, &v, &vd)) break;
-      const int ui = (int)floorf(u), vi = (int)floorf(v);
-      if (ui < 0 || vi < 0 || ui >= f.cols || vi >= f.rows) break;
-      const float meas = __ldg(f.depth + (size_t)vi * f.cols + ui);
-      if (isnan(meas)) break;
-      const bool active = (f.mask == nullptr) || __ldg(f.mask + (size_t)vi * f.cols + ui);
-      if (meas <= 0.0f) {
-        if (f.invalid_decay >= 0.0f && !is_new) {
-          out = *vox;
-          out.y *= f.invalid_decay;
-          write = true;
-        }
-        break;
+  do {
+    float u, v, vd;
+    if (!project_voxel(f.cam, f.T_C_L, m.block_size, f.max_depth, b, vx, vy, vz, &u, &v, &vd)) break;
+    const int ui = (int)floorf(u), vi = (int)floorf(v);
+    if (ui < 0 || vi < 0 || ui >= f.cols || vi >= f.rows) break;
+    const float meas = __ldg(f.depth + (size_t)vi * f.cols + ui);
+    if (isnan(meas)) break;
+    const bool active = (f.mask == nullptr) || __ldg(f.mask + (size_t)vi * f.cols + ui);
+    if (meas <= 0.0f) {
+      if (f.invalid_decay >= 0.0f && !is_new) {
+        out = *vox;
+        out.y *= f.invalid_decay;
+        write = true;
       }
-      const float sdf = meas - vd;
-      if (sdf < -f.trunc) break;
-      if (!active && sdf < f.trunc) break;
-      const float2 cur = is_new ? make_float2(0.0f, 0.0f) : *vox;
-      const float w_m = weighting(f.weighting_mode, meas, vd, f.trunc);
-      float fused = (sdf * w_m + cur.x * cur.y) / (w_m + cur.y);
-      if (fused > 0.0f)
-        fused = fminf(f.trunc, fused);
-      else
-        fused = fmaxf(-f.trunc, fused);
-      out = make_float2(fused, fminf(w_m + cur.y, f.max_weight));
-      write = true;
-      ++updated;
-    } while (false);
-    if (write) *vox = out;
+      break;
+    }
+    const float sdf = meas - vd;
+    if (sdf < -f.trunc) break;
+    if (!active && sdf < f.trunc) break;
+    const float2 cur = is_new ? make_float2(0.0f, 0.0f) : *vox;
+    const float w_m = weighting(f.weighting_mode, meas, vd, f.trunc);
+    float fused = (sdf * w_m + cur.x * cur.y) / (w_m + cur.y);
+    if (fused > 0.0f)
+      fused = fminf(f.trunc, fused);
+    else
+      fused = fmaxf(-f.trunc, fused);
+    out = make_float2(fused, fminf(w_m + cur.y, f.max_weight));
+    write = true;
+    updated = 1;
+  } while (false);
+  if (write) *vox = out;
+  return updated;
+}
+
+// Where the list of blocks to update comes from.
+//   kViewFromSlots  : slot list written by k_view_compact_alloc (views whose bitmap exceeds kFusedBitmapWords)
+//   kViewFromBitmap : the marked bitmap itself -- compaction, find-or-allocate and the viewpoint-cache entry
+//                     are folded into this kernel (every CTA ranks the <= 32 768 cells redundantly in shared
+//                     memory and serves ranks blockIdx.x, blockIdx.x + gridDim.x, ...); the OTHER bitmap of
+//                     the double buffer is cleared for the next frame.  One launch less per depth frame.
+//   kViewFromEntry  : viewpoint-cache hit, the cached index list (view_calculator.cu:256-265); blocks are
+//                     (re-)allocated where required (projective_integrator_impl.cuh:288-291)
+enum ViewMode { kViewFromSlots = 0, kViewFromBitmap = 1, kViewFromEntry = 2 };
+constexpr int kFusedBitmapWords = 1024;
+
+struct ViewSource {
+  const int* view_slots;  // kViewFromSlots
+  int* entry_count;       // list length (read in kViewFromSlots / kViewFromEntry, written in kViewFromBitmap)
+  int3* entry_idx;        // cache entry index list (written in kViewFromBitmap, read in kViewFromEntry)
+  const unsigned* bits;   // kViewFromBitmap
+  unsigned* clean_bits;   // kViewFromBitmap: the other half of the double buffer
+  ViewGrid g;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 3) k_tsdf_update(MapDev m, ViewSource src, DepthFrame f) {
+  pdl_prologue();
+  __shared__ int s_off[513];
+  __shared__ int s_warp[17];
+  __shared__ int s_slot;
+  const int t = threadIdx.x;
+  unsigned updated = 0;
+  int n = 0;
+
+  if (MODE == kViewFromSlots) {
+    n = *src.entry_count;
+    for (int bi = blockIdx.x; bi < n; bi += gridDim.x) {
+      const int raw = src.view_slots[bi];
+      if (raw < 0) continue;
+      const int slot = raw & kSlotMask;
+      if (t == 0) m.blk_dirty[slot] = 1;  // blocks_to_update_tracker_.addBlocksToUpdate (mapper.cpp:406)
+      updated += tsdf_update_voxel(m, f, slot, (raw & kNewFlag) != 0, t);
+    }
+  } else {
+    unsigned w0 = 0u, w1 = 0u;
+    if (MODE == kViewFromBitmap) {
+      // rank the marked cells: thread t owns words 2t and 2t + 1
+      const int n_words = (src.g.n_cells + 31) >> 5;
+      if (2 * t < n_words) w0 = src.bits[2 * t];
+      if (2 * t + 1 < n_words) w1 = src.bits[2 * t + 1];
+      for (int w = blockIdx.x * 512 + t; w < kFusedBitmapWords; w += gridDim.x * 512) src.clean_bits[w] = 0u;
+      const int c = __popc(w0) + __popc(w1);
+      int inc = c;
+      const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      if (lane == 31) s_warp[warp + 1] = inc;
+      __syncthreads();
+      if (t == 0) {
+        int acc = 0;
+        s_warp[0] = 0;
+        for (int w = 1; w <= 16; ++w) {
+          acc += s_warp[w];
+          s_warp[w] = acc;
+        }
+      }
+      __syncthreads();
+      s_off[t] = s_warp[warp] + inc - c;
+      if (t == 511) s_off[512] = s_warp[16];
+      __syncthreads();
+      n = s_off[512];
+      if (blockIdx.x == 0 && t == 0) *src.entry_count = n;
+    } else {
+      n = *src.entry_count;
+    }
+    for (int r = blockIdx.x; r < n; r += gridDim.x) {
+      bool owner;
+      int x = 0, y = 0, z = 0;
+      if (MODE == kViewFromBitmap) {
+        owner = (s_off[t] <= r) && (r < s_off[t + 1]);
+        if (owner) {
+          const int k = r - s_off[t], c0 = __popc(w0);
+          const int i = (k < c0) ? (64 * t + (int)__fns(w0, 0, k + 1)) : (64 * t + 32 + (int)__fns(w1, 0, k - c0 + 1));
+          x = i % src.g.sx + src.g.mn.x;
+          y = (i / src.g.sx) % src.g.sy + src.g.mn.y;
+          z = i / (src.g.sx * src.g.sy) + src.g.mn.z;
+          src.entry_idx[r] = make_int3(x, y, z);
+        }
+      } else {
+        owner = (t == 0);
+        if (owner) {
+          const int3 b = src.entry_idx[r];
+          x = b.x;
+          y = b.y;
+          z = b.z;
+        }
+      }
+      if (owner) {
+        bool is_new;
+        int slot = acquire_slot(m, x, y, z, &is_new);
+        if (slot >= 0) {
+          if (ensure_tsdf_layer(m, slot)) {
+            slot |= kNewFlag;
+            count_add(m, kCntTsdfBlocksAllocated, 1);
+          }
+          m.blk_dirty[slot & kSlotMask] = 1;  // blocks_to_update_tracker_.addBlocksToUpdate (mapper.cpp:406)
+        }
+        s_slot = slot;
+      }
+      __syncthreads();
+      const int raw = s_slot;
+      if (raw >= 0) updated += tsdf_update_voxel(m, f, raw & kSlotMask, (raw & kNewFlag) != 0, t);
+      __syncthreads();  // s_slot is rewritten by the next rank
+    }
   }
   // accounting: one atomic per warp
   for (int o = 16; o; o >>= 1) updated += __shfl_xor_sync(0xffffffffu, updated, o);
@@ -451,8 +539,10 @@ __device__ __forceinline__ int floor_div_exact(float p, float bs, float bs_inv) 
   return (int)floorf(p / bs);
 }
 
-__device__ __forceinline__ void sphere_trace_ray(const MapDev& m, const TraceParams& tp, int r, int c,
-                                                 float* __restrict__ image) {
+constexpr int kTraceSmemCells = 4096;  // workspace grids up to this many cells are staged in shared memory
+
+__device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TraceParams& tp, int r, int c,
+                                                float* __restrict__ image, const int* s_ws) {
   const float pu = (float)(c * tp.sub) + 0.5f * (float)tp.sub * 1.0f;
   const float pv = (float)(r * tp.sub) + 0.5f * (float)tp.sub * 1.0f;
   const V3 ray = ray_from_image_plane(tp.cam, pu, pv);
@@ -475,9 +565,6 @@ __device__ __forceinline__ void sphere_trace_ray(const MapDev& m, const TracePar
   int first = 0;
   float t = 0.0f;
   bool ok = false;
-  I3 cached_b;
-  cached_b.x = cached_b.y = cached_b.z = 0x7fffffff;
-  const float2* cached_ptr = nullptr;
   int n_steps = 0;
   for (int i = 0; (i < tp.max_steps) && (t < tp.max_ray_length); ++i) {
     n_steps = i + 1;
@@ -493,22 +580,25 @@ __device__ __forceinline__ void sphere_trace_ray(const MapDev& m, const TracePar
     v.x = min((int)((p.x - bs * (float)b.x) * m.voxel_size_inv), 7);
     v.y = min((int)((p.y - bs * (float)b.y) * m.voxel_size_inv), 7);
     v.z = min((int)((p.z - bs * (float)b.z) * m.voxel_size_inv), 7);
-    if (b.x != cached_b.x || b.y != cached_b.y || b.z != cached_b.z) {
-      cached_b = b;
-      // A slot without a TSDF layer has an all-zero TSDF payload (k_allocate_one), i.e. reads as
-      // unobserved, so the layer bits need not be consulted here.
-      const int slot = find_slot(m, b.x, b.y, b.z);
-      cached_ptr = nullptr;
-      if (slot >= 0)
-        cached_ptr = (slot < (1 << kTsdfSlabShift)) ? slab0 + (size_t)slot * kVoxelsPerBlock : tsdf_block(m, slot);
-      if (closed_world && slot < 0) {
-        // t only grows (steps are >= 0), so each coordinate of p moves monotonically along sign(dl)
-        const bool gone = (b.x > ws_mx.x && dl.x >= 0.0f) || (b.x < m.ws_mn.x && dl.x <= 0.0f) ||
-                          (b.y > ws_mx.y && dl.y >= 0.0f) || (b.y < m.ws_mn.y && dl.y <= 0.0f) ||
-                          (b.z > ws_mx.z && dl.z >= 0.0f) || (b.z < m.ws_mn.z && dl.z <= 0.0f);
-        if (gone) break;  // miss
-      }
+    // Block lookup on every sample (no per-thread block cache: with the table in shared memory the lookup is
+    // cheaper than the divergence a cache introduces).  A slot without a TSDF layer has an all-zero TSDF
+    // payload (k_allocate_one), i.e. reads as unobserved, so the layer bits need not be consulted here.
+    const int cell = ws_cell(m, b.x, b.y, b.z);
+    int slot = -1;
+    if (cell >= 0) {
+      slot = s_ws ? s_ws[cell] : m.ws_slot[cell];
+    } else if (!closed_world) {
+      slot = hash_find(m, b.x, b.y, b.z);
+    } else {
+      // t only grows (steps are >= 0), so each coordinate of p moves monotonically along sign(dl)
+      const bool gone = (b.x > ws_mx.x && dl.x >= 0.0f) || (b.x < m.ws_mn.x && dl.x <= 0.0f) ||
+                        (b.y > ws_mx.y && dl.y >= 0.0f) || (b.y < m.ws_mn.y && dl.y <= 0.0f) ||
+                        (b.z > ws_mx.z && dl.z >= 0.0f) || (b.z < m.ws_mn.z && dl.z <= 0.0f);
+      if (gone) break;  // miss
     }
+    const float2* cached_ptr = nullptr;
+    if (slot >= 0)
+      cached_ptr = (slot < (1 << kTsdfSlabShift)) ? slab0 + (size_t)slot * kVoxelsPerBlock : tsdf_block(m, slot);
     bool valid = false;
     float dist = 0.0f;
     if (cached_ptr) {
@@ -546,10 +636,7 @@ __device__ __forceinline__ void sphere_trace_ray(const MapDev& m, const TracePar
     t += step;
   }
   image[(size_t)r * tp.cols + c] = ok ? t * dc.z : -1.0f;
-#ifdef NVBX_PROFILE_COUNTERS
-  atomicAdd(&m.ctrl->counters[12], (unsigned long long)n_steps);
-  atomicMax(&m.ctrl->counters[13], (unsigned long long)n_steps);
-#endif
+  return n_steps;
 }
 
 // The two independent, latency-bound preparations of a feature frame in ONE launch: CTAs
@@ -562,6 +649,7 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
   pdl_prologue();
   __shared__ int s_cand[256];
   __shared__ int s_ncand;
+  __shared__ int s_ws[kTraceSmemCells];
 #ifdef NVBX_PROFILE_COUNTERS
   const long long t0 = clock64();
 #endif
@@ -569,9 +657,29 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
     if (blockIdx.x == 0 && threadIdx.x == 0) m.ctrl->item_count = 0;  // consumed by k_feature_geometry
     const int c = (blockIdx.x % trace_tiles_x) * 16 + (threadIdx.x & 7) + ((threadIdx.x >> 7) << 3);
     const int r = (blockIdx.x / trace_tiles_x) * 16 + ((threadIdx.x >> 3) & 15);
-    if (r < tp.rows && c < tp.cols) sphere_trace_ray(m, tp, r, c, image);
+    const bool stage_ws = m.ws_cells > 0 && m.ws_cells <= kTraceSmemCells;
+    if (stage_ws) {
+      for (int i = threadIdx.x; i < m.ws_cells; i += 256) s_ws[i] = m.ws_slot[i];
+      __syncthreads();
+    }
+    [[maybe_unused]] int n_steps = 0;
+    if (r < tp.rows && c < tp.cols) n_steps = sphere_trace_ray(m, tp, r, c, image, stage_ws ? s_ws : nullptr);
 #ifdef NVBX_PROFILE_COUNTERS
-    atomicMax(&m.ctrl->counters[14], (unsigned long long)(clock64() - t0));
+    {  // tuning aid: steps (sum / max over rays) and the slowest warp's cycles, one atomic set per warp
+      const long long dt = clock64() - t0;
+      int sum = n_steps, mx = n_steps;
+      for (int o = 16; o; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      }
+      if (lane_id() == 0) {
+        atomicAdd(&m.ctrl->counters[12], (unsigned long long)sum);
+        atomicMax(&m.ctrl->counters[13], (unsigned long long)mx);
+        atomicMax(&m.ctrl->counters[14], (unsigned long long)dt);
+      }
+    }
+#else
+    (void)n_steps;
 #endif
     return;
   }

@@ -206,3 +206,22 @@ def test_two_mappers_static_dynamic():
         ci, cd = cpu[mid].all_blocks(1)
         assert np.array_equal(gi, ci) and len(gi) > 0
         assert np.array_equal(gd.view(np.uint16)[..., -1], cd.view(np.uint16)[..., -1])
+
+
+def test_large_view_global_bitmap_and_hash_index():
+    """1 cm voxels, no workspace box, 4 m range: the view AABB has > 262 144 cells, so rays mark the GLOBAL
+    bitmap (k_raycast_mark<false>), compaction runs as its own kernel (kViewFromSlots), every block lives in the
+    overflow hash and the arenas grow while frames arrive."""
+    mp, op = make_params(workspace=None, max_dist=4.0, raycast_sub=2, alpha=0.8)
+    pair = Pair(0.01, 16, mp, op)
+    for i, T, K, depth, feat in orbit_frames(2, 64, 64, 16, S.S_TABLE, radius=0.8, height=0.7):
+        pair.depth(depth, T, K)
+        g, c = pair.last_block_list(0)
+        assert np.array_equal(g, c) and len(g) > 100
+        pair.features(feat, T, K)
+        g, c = pair.last_block_list(1)
+        assert np.array_equal(g, c)
+    assert pair.check_tsdf() > 100
+    assert pair.check_features() > 0
+    pair.decay()
+    assert pair.check_mesh() > 0
