@@ -36,6 +36,7 @@ extern "C" {
 /* Layer selectors. */
 #define NVBX_LAYER_TSDF 0
 #define NVBX_LAYER_FEATURE 1
+#define NVBX_LAYER_COLOR 2
 
 /* WeightingFunctionType, nvblox/integrators/weighting_function.h:11-18 */
 #define NVBX_WEIGHT_CONSTANT 0
@@ -115,8 +116,12 @@ typedef struct nvbx_counters {
   int64_t feature_blocks_allocated;
   int64_t blocks_deallocated;
   int64_t mesh_blocks_remeshed;
-  int64_t mesh_vertices;            /* N_v of the last update                                  */
-  int64_t reserved[4];
+  int64_t mesh_vertices;            /* N_v of the last feature-mesh update                     */
+  int64_t color_frames;             /* nvbx_integrate_color calls                              */
+  int64_t color_band_blocks;        /* blocks handed to the colour update                      */
+  int64_t color_voxels_updated;
+  int64_t color_blocks_allocated;
+  int64_t reserved[4];              /* NVBX_PROFILE_COUNTERS builds only                       */
 } nvbx_counters;
 
 /* ---- lifecycle ---------------------------------------------------------------------------------- */
@@ -153,8 +158,13 @@ int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, in
                             int channels, const void* mask, const float* T_L_C, float fx, float fy,
                             float cx, float cy, void* stream);
 
-/* Mapper::integrateColor, py_mapper.cu:115-144.  SURVEY 8(f) N1 ("next"): arguments are validated,
- * the planes-viewpoint cache is not touched and no colour layer is kept in this round. */
+/* Mapper::integrateColor, py_mapper.cu:115-144 -> mapper.cpp:436-449 ->
+ * ProjectiveAppearanceIntegrator<ColorLayer>::integrateFrame projective_appearance_integrator.cu:72-169
+ * (SURVEY 8(f) N1).  rgb: device uint8 [H*W*3] (HWC); height/width must be multiples of
+ * sphere_tracing_subsampling.  The colour layer stores the reference's ColorVoxel record (r, g, b, pad,
+ * float weight: 8 bytes, voxels.h:77-83); a colour frame that follows a feature / colour frame with the same
+ * pose, intrinsics and TSDF state re-uses that frame's synthetic depth image instead of sphere tracing again
+ * (the result is identical: the image is a pure function of those three). */
 int nvbx_integrate_color(nvbx_mapper* m, int map_id, const void* rgb, int height, int width,
                          const void* mask, const float* T_L_C, float fx, float fy, float cx, float cy,
                          void* stream);
@@ -187,6 +197,13 @@ int nvbx_update_feature_mesh(nvbx_mapper* m, int map_id, void* stream);
 int nvbx_get_feature_mesh(nvbx_mapper* m, int map_id, const void** vertices, const void** features,
                           const void** triangles, int64_t* n_vertices, int64_t* n_triangles);
 
+/* Mapper::updateColorMesh, py_mapper.cu:186-194 (the colour mesh is its own mesh layer with its own
+ * "to update" set, blocks_to_update_tracker.cpp:32-60) and Mapper::getColorMesh, py_mapper.cu:206-221 +
+ * PyMesh<Color>::vertex_appearances py_mesh.cpp:54-90.  colors: uint8[n_vertices*3]. */
+int nvbx_update_color_mesh(nvbx_mapper* m, int map_id, void* stream);
+int nvbx_get_color_mesh(nvbx_mapper* m, int map_id, const void** vertices, const void** colors,
+                        const void** triangles, int64_t* n_vertices, int64_t* n_triangles);
+
 /* ---- layer views (PyVoxelBlockLayer, py_layer.cpp:24-47,99-198) ---------------------------------- */
 
 int64_t nvbx_num_blocks(nvbx_mapper* m, int map_id, int layer, void* stream);           /* numBlocks            */
@@ -199,7 +216,8 @@ int64_t nvbx_get_block_indices(nvbx_mapper* m, int map_id, int layer, int32_t* o
 /* get_block_at_index: device pointer of the block's voxel array and its voxel stride in ELEMENTS.
  * TSDF: float [8][8][8][2], stride 2.  Feature: fp16 [8][8][8][stride], stride = C + 8 (the first C are
  * the feature, element C is the weight, the rest is padding that keeps rows 16-byte aligned), to be
- * viewed as [8,8,8,C+1].  NVBX_ERR_NOT_FOUND if the block is not allocated. */
+ * viewed as [8,8,8,C+1].  Colour: uint8 [8][8][8][8] = (r, g, b, pad, float weight), stride 8, to be viewed
+ * as the [8,8,8,3] uint8 tensor of py_layer.cpp:49-70.  NVBX_ERR_NOT_FOUND if the block is not allocated. */
 int nvbx_get_block_ptr(nvbx_mapper* m, int map_id, int layer, int x, int y, int z, void** ptr,
                        int64_t* voxel_stride_elems, void* stream);
 /* allocate_block_at_index (zero-initialised). */
@@ -234,6 +252,7 @@ int64_t nvbx_kernel_launch_count(void);
 /* Debug / parity hooks: copy the last frame's intermediate products to HOST memory.
  *   which = 0: block indices handed to the last TSDF update   (int32 triples)
  *   which = 1: block indices handed to the last feature update (int32 triples)
+ *   which = 2: block indices handed to the last colour update  (int32 triples)
  * returns the count (or a negative error). */
 int64_t nvbx_debug_last_block_list(nvbx_mapper* m, int map_id, int which, int32_t* out_xyz, int64_t capacity,
                                    void* stream);

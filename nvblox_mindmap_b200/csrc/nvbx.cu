@@ -179,22 +179,37 @@ struct Map {
   int feat_capacity = 0;
   long long slot_used_ub = 0;  // host upper bounds of live ids (pessimistic between syncs)
   long long feat_used_ub = 0;
-  std::vector<void*> tsdf_slabs, feat_slabs;
+  std::vector<void*> tsdf_slabs, feat_slabs, color_slabs;
   float2** d_tsdf_table = nullptr;
   __half** d_feat_table = nullptr;
+  uint2** d_color_table = nullptr;
+  bool color_enabled = false;  // colour slabs exist (allocated by the first colour frame / colour block request)
   Ctrl* d_ctrl = nullptr;
   Ctrl* h_ctrl = nullptr;  // pinned mirror
-  ViewCache raycast_cache, planes_cache;
+  ViewCache raycast_cache, planes_cache, color_planes_cache;  // one ViewCalculator (and cache) per integrator
   CacheEntry scratch_ray, scratch_planes;  // used when the cache is disabled
   DevBuf<unsigned> grid;   // view bitmap; all-zero between frames (k_view_compact_alloc cleans it)
   bool grid_dirty = false;  // a frame failed between marking and compaction
   unsigned* small_grid[2] = {nullptr, nullptr};  // double-buffered bitmap of small views (2 x kFusedBitmapWords)
   int small_cur = 0;
   bool small_dirty = false;
-  DevBuf<int> view_slots, band_slots, newfeat_slots;
+  DevBuf<int> view_slots, band_slots, newfeat_slots, cband_slots;
+  int color_parity = 0;
+  bool have_cband_list = false;
   DevBuf<FeatItem> items;
   DevBuf<float> synth;
   int synth_rows = 0, synth_cols = 0;
+  // The synthetic depth image is a pure function of (pose, camera, truncation, TSDF contents): the colour and
+  // feature frames of one mindmap step share all four, so the second one skips the sphere tracing.
+  struct SynthKey {
+    Pose T;
+    Cam cam;
+    float trunc = 0;
+    int sub = 0;
+    unsigned long long tsdf_version = 0;
+    bool valid = false;
+  } synth_key;
+  unsigned long long tsdf_version = 1;  // bumped by everything that may change TSDF voxels or the block set
   CacheEntry* last_depth_entry = nullptr;
   bool have_band_list = false;
   // mesh
@@ -204,6 +219,11 @@ struct Map {
   DevBuf<int> arena_t[2];
   int arena_cur = 0;
   long long mesh_nv = 0, mesh_nt = 0;
+  DevBuf<float> carena_v[2];  // colour mesh layer (its own geometry + uint8 rgb per vertex)
+  DevBuf<uint8_t> carena_c[2];
+  DevBuf<int> carena_t[2];
+  int carena_cur = 0;
+  long long cmesh_nv = 0, cmesh_nt = 0;
   // host staging for nvbx_integrate_frame_host
   DevBuf<float> st_depth;
   DevBuf<__half> st_feat;
@@ -250,6 +270,9 @@ int upload_slab_tables(Map& mp, cudaStream_t stream) {
   if (!mp.feat_slabs.empty())
     CUDA_TRY(cudaMemcpyAsync(mp.d_feat_table, mp.feat_slabs.data(), mp.feat_slabs.size() * sizeof(void*),
                              cudaMemcpyHostToDevice, stream));
+  if (!mp.color_slabs.empty())
+    CUDA_TRY(cudaMemcpyAsync(mp.d_color_table, mp.color_slabs.data(), mp.color_slabs.size() * sizeof(void*),
+                             cudaMemcpyHostToDevice, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));  // the host vectors may reallocate later
   return NVBX_OK;
 }
@@ -265,6 +288,18 @@ int regrow(T** p, size_t old_n, size_t new_n, cudaStream_t stream) {
   return NVBX_OK;
 }
 
+// Colour payload slabs mirror the TSDF slabs one to one (payload id == slot id).
+int grow_color_slabs(Map& mp, cudaStream_t stream) {
+  const size_t bytes = (size_t)(1 << kTsdfSlabShift) * kVoxelsPerBlock * sizeof(uint2);
+  while (mp.color_slabs.size() < mp.tsdf_slabs.size()) {
+    void* s = nullptr;
+    CUDA_TRY(cudaMalloc(&s, bytes));
+    if (poison_arenas()) CUDA_TRY(cudaMemsetAsync(s, 0x7b, bytes, stream));
+    mp.color_slabs.push_back(s);
+  }
+  return NVBX_OK;
+}
+
 // Grow the slot table (and TSDF slabs, hash) to hold `new_cap` block indices.
 int grow_slots(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
   CUDA_TRY(cudaStreamSynchronize(stream));
@@ -277,6 +312,7 @@ int grow_slots(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
   if ((rc = regrow(&mp.dev.blk_feat, old, new_cap, stream))) return rc;
   if ((rc = regrow(&mp.dev.blk_dirty, old, new_cap, stream))) return rc;
   if ((rc = regrow(&mp.dev.blk_mesh, old, new_cap, stream))) return rc;
+  if ((rc = regrow(&mp.dev.blk_cmesh, old, new_cap, stream))) return rc;
   if ((rc = regrow(&mp.dev.slot_free, old, new_cap, stream))) return rc;
   CUDA_TRY(cudaMemsetAsync(mp.dev.blk_layers + old, 0, new_cap - old, stream));
   while ((int)mp.tsdf_slabs.size() < (new_cap >> kTsdfSlabShift)) {
@@ -286,6 +322,7 @@ int grow_slots(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
     if (poison_arenas()) CUDA_TRY(cudaMemsetAsync(s, 0x7b, bytes, stream));
     mp.tsdf_slabs.push_back(s);
   }
+  if (mp.color_enabled && (rc = grow_color_slabs(mp, stream))) return rc;
   if ((rc = upload_slab_tables(mp, stream))) return rc;
   mp.slot_capacity = new_cap;
   mp.dev.slot_capacity = new_cap;
@@ -326,6 +363,15 @@ int grow_feats(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
   mp.feat_capacity = new_cap;
   mp.dev.feat_capacity = new_cap;
   return NVBX_OK;
+}
+
+// First use of the colour layer: allocate its slabs next to the TSDF slabs.
+int enable_color(Map& mp, cudaStream_t stream) {
+  if (mp.color_enabled) return NVBX_OK;
+  int rc;
+  if ((rc = grow_color_slabs(mp, stream))) return rc;
+  mp.color_enabled = true;
+  return upload_slab_tables(mp, stream);
 }
 
 int read_ctrl(Map& mp, cudaStream_t stream) {
@@ -462,8 +508,10 @@ int init_map(nvbx_mapper* m, Map& mp, float voxel_size, cudaStream_t stream) {
   mp.dev.ctrl = mp.d_ctrl;
   CUDA_TRY(cudaMalloc(&mp.d_tsdf_table, kMaxSlabs * sizeof(void*)));
   CUDA_TRY(cudaMalloc(&mp.d_feat_table, kMaxSlabs * sizeof(void*)));
+  CUDA_TRY(cudaMalloc(&mp.d_color_table, kMaxSlabs * sizeof(void*)));
   mp.dev.tsdf_slabs = mp.d_tsdf_table;
   mp.dev.feat_slabs = mp.d_feat_table;
+  mp.dev.color_slabs = mp.d_color_table;
   CUDA_TRY(cudaMalloc(&mp.d_tmp_int, sizeof(int)));
   CUDA_TRY(cudaMalloc(&mp.d_tmp_ptr, sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc(&mp.scratch_ray.d_count, sizeof(int)));
@@ -514,14 +562,18 @@ void destroy_map(Map& mp) {
   F(mp.dev.blk_feat);
   F(mp.dev.blk_dirty);
   F(mp.dev.blk_mesh);
+  F(mp.dev.blk_cmesh);
   F(mp.dev.slot_free);
   F(mp.dev.feat_free);
   for (void* s : mp.tsdf_slabs) cudaFree(s);
   for (void* s : mp.feat_slabs) cudaFree(s);
+  for (void* s : mp.color_slabs) cudaFree(s);
   mp.tsdf_slabs.clear();
   mp.feat_slabs.clear();
+  mp.color_slabs.clear();
   F(mp.d_tsdf_table);
   F(mp.d_feat_table);
+  F(mp.d_color_table);
   F(mp.d_ctrl);
   if (mp.h_ctrl) cudaFreeHost(mp.h_ctrl);
   mp.h_ctrl = nullptr;
@@ -529,6 +581,7 @@ void destroy_map(Map& mp) {
   F(mp.d_tmp_ptr);
   mp.raycast_cache.release();
   mp.planes_cache.release();
+  mp.color_planes_cache.release();
   mp.scratch_ray.idx.release();
   mp.scratch_planes.idx.release();
   F(mp.scratch_ray.d_count);
@@ -538,6 +591,7 @@ void destroy_map(Map& mp) {
   mp.view_slots.release();
   mp.band_slots.release();
   mp.newfeat_slots.release();
+  mp.cband_slots.release();
   mp.items.release();
   mp.synth.release();
   mp.cnt_v.release();
@@ -548,6 +602,9 @@ void destroy_map(Map& mp) {
     mp.arena_v[i].release();
     mp.arena_f[i].release();
     mp.arena_t[i].release();
+    mp.carena_v[i].release();
+    mp.carena_c[i].release();
+    mp.carena_t[i].release();
   }
   mp.st_depth.release();
   mp.st_feat.release();
@@ -689,8 +746,14 @@ int nvbx_create(int n_maps, const float* voxel_sizes_m, const nvbx_params* param
   if (p.raycast_subsampling_factor <= 0 || p.sphere_tracing_subsampling <= 0)
     return fail(NVBX_ERR_INVALID_ARGUMENT, "subsampling factors must be positive");
   // the mesh kernels need > 48 KiB of dynamic shared memory
-  CUDA_TRY(cudaFuncSetAttribute(k_mesh_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem)));
-  CUDA_TRY(cudaFuncSetAttribute(k_mesh_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MeshSmem)));
+  CUDA_TRY(cudaFuncSetAttribute(k_mesh_count<kMeshFeature>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(MeshSmem)));
+  CUDA_TRY(cudaFuncSetAttribute(k_mesh_emit<kMeshFeature>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(MeshSmem)));
+  CUDA_TRY(cudaFuncSetAttribute(k_mesh_count<kMeshColor>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(MeshSmem)));
+  CUDA_TRY(cudaFuncSetAttribute(k_mesh_emit<kMeshColor>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(MeshSmem)));
   for (int i = 0; i < n_maps; ++i) {
     if (!(voxel_sizes_m[i] > 0.0f)) return fail(NVBX_ERR_INVALID_ARGUMENT, "voxel size must be positive");
     m->maps.emplace_back(new Map());
@@ -856,6 +919,7 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
   f.invalid_decay = p.invalid_depth_decay_factor;
   f.weighting_mode = p.weighting_mode;
   const int tgrid = std::max(1, std::min(persistent_grid(m, 3), entry->bound));  // one block per CTA up to 3 CTAs/SM
+  ++mp.tsdf_version;
   if ((rc = timing_begin(m, 1, stream))) return rc;
   if (view_mode == kViewFromBitmap) {
     LAUNCH(k_tsdf_update<kViewFromBitmap>, tgrid, 512, 0, stream, mp.dev, vs, f);
@@ -869,37 +933,52 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
   return timing_end(m, 1, stream);
 }
 
-// ---- features ------------------------------------------------------------------------------------
-int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, int height, int width, int channels,
-                            const void* mask, const float* T_L_C_rm, float fx, float fy, float cx, float cy,
-                            void* stream_v) {
-  int rc = check_map(m, map_id);
-  if (rc) return rc;
-  if (!features || !T_L_C_rm || height <= 0 || width <= 0) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad feature frame");
-  if (channels != m->C)
-    return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame has %d channels, the map was created with %d", channels,
-                m->C);
-  if (((uintptr_t)features) & 15) return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame must be 16-byte aligned");
+}  // extern "C"
+
+// ---- appearance frames (features, colour) ----------------------------------------------------------
+namespace {
+
+// What the feature and the colour integrator share (ProjectiveAppearanceIntegrator<LayerType>::integrateFrame,
+// projective_appearance_integrator.cu:72-169): the planes view of the frame (through the integrator's own
+// viewpoint cache), the band-select / sphere-trace launch and the synthetic depth image.
+struct AppearancePrep {
+  bool empty = false;
+  float trunc = 0;
+  Pose T_L_C, T_C_L;
+  Cam cam;
+  int srows = 0, scols = 0, sub = 0;
+  long long cand_bound = 0;
+};
+
+// color_parity < 0: feature frame (band list -> mp.band_slots / ctrl->band_count, feature slots allocated);
+// otherwise colour frame (band list -> mp.cband_slots / ctrl->cband_count[parity]).
+int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, int width, const float* T_L_C_rm,
+                       float fx, float fy, float cx, float cy, int color_parity, cudaStream_t stream,
+                       AppearancePrep* out) {
   const nvbx_params& p = m->params;
+  int rc;
   const int sub = p.sphere_tracing_subsampling;
   if (width % sub || height % sub)
-    return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame %dx%d is not divisible by the sphere-tracing subsampling %d",
-                height, width, sub);
-  cudaStream_t stream = (cudaStream_t)stream_v;
-  Map& mp = *m->maps[map_id];
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "frame %dx%d is not divisible by the sphere-tracing subsampling %d", height,
+                width, sub);
   const Pose T_L_C = pose_from_row_major(T_L_C_rm);
   const Cam cam = make_cam(fx, fy, cx, cy, height, width);
   const float trunc = p.appearance_truncation_distance_vox * mp.voxel_size;
-  const Pose T_C_L = inverse(T_L_C);
-  mp.have_band_list = false;
+  out->T_L_C = T_L_C;
+  out->T_C_L = inverse(T_L_C);
+  out->cam = cam;
+  out->trunc = trunc;
 
-  CacheEntry* entry = p.cache_last_viewpoint ? mp.planes_cache.lookup(T_L_C, cam) : nullptr;
+  CacheEntry* entry = p.cache_last_viewpoint ? cache.lookup(T_L_C, cam) : nullptr;
   if (!entry) {
     GridSpec gs;
     if ((rc = make_grid(m, mp, view_aabb(cam, T_L_C, 1e-6f, p.max_integration_distance_m + trunc), &gs))) return rc;
-    if (gs.empty) return NVBX_OK;
+    if (gs.empty) {
+      out->empty = true;
+      return NVBX_OK;
+    }
     if (p.cache_last_viewpoint) {
-      if ((rc = mp.planes_cache.acquire(&entry, false))) return rc;
+      if ((rc = cache.acquire(&entry, false))) return rc;
     } else {
       entry = &mp.scratch_planes;
     }
@@ -907,7 +986,7 @@ int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, in
     entry->cam = cam;
     entry->grid = gs.g;
     entry->bound = gs.g.n_cells;
-    if (p.cache_last_viewpoint) mp.planes_cache.store(entry);
+    if (p.cache_last_viewpoint) cache.store(entry);
   }
   // The in-view test runs with the pose / camera / AABB of the cache entry: on a hit these are the
   // cached ones, i.e. the block list the reference would have re-used (view_calculator.cu:401-405).
@@ -923,15 +1002,25 @@ int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, in
     pv.vmax_y = vmax.y;
   }
   const long long cand_bound = std::min((long long)entry->bound, std::max(1LL, mp.slot_used_ub));
-  if ((rc = ensure_feats(m, mp, cand_bound, stream))) return rc;
-  if ((rc = mp.band_slots.ensure((size_t)cand_bound, stream))) return rc;
-  if ((rc = mp.newfeat_slots.ensure((size_t)cand_bound, stream))) return rc;
-  const long long chunk_blocks = std::min<long long>(cand_bound, kFeatureChunkBlocks);
-  if ((rc = mp.items.ensure((size_t)chunk_blocks * kVoxelsPerBlock, stream))) return rc;
+  out->cand_bound = cand_bound;
+  int* band_list;
+  if (color_parity < 0) {
+    if ((rc = ensure_feats(m, mp, cand_bound, stream))) return rc;
+    if ((rc = mp.band_slots.ensure((size_t)cand_bound, stream))) return rc;
+    if ((rc = mp.newfeat_slots.ensure((size_t)cand_bound, stream))) return rc;
+    const long long chunk_blocks = std::min<long long>(cand_bound, kFeatureChunkBlocks);
+    if ((rc = mp.items.ensure((size_t)chunk_blocks * kVoxelsPerBlock, stream))) return rc;
+    band_list = mp.band_slots.p;
+  } else {
+    if ((rc = enable_color(mp, stream))) return rc;
+    if ((rc = mp.cband_slots.ensure((size_t)cand_bound, stream))) return rc;
+    band_list = mp.cband_slots.p;
+  }
   const int srows = height / sub, scols = width / sub;
   if ((rc = mp.synth.ensure((size_t)srows * scols, stream))) return rc;
-  mp.synth_rows = srows;
-  mp.synth_cols = scols;
+  out->srows = srows;
+  out->scols = scols;
+  out->sub = height / srows;  // projective_integrator_impl.cuh:424-425
 
   TraceParams tp;
   tp.cam = cam;
@@ -943,17 +1032,63 @@ int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, in
   tp.sub = sub;
   tp.rows = srows;
   tp.cols = scols;
+  // synthetic depth already rendered for exactly this pose / camera / TSDF state (the other appearance frame of
+  // the same step): skip the sphere tracing, keep the band selection
+  Map::SynthKey& key = mp.synth_key;
+  const bool reuse = key.valid && key.tsdf_version == mp.tsdf_version && key.trunc == trunc && key.sub == sub &&
+                     mp.synth_rows == srows && mp.synth_cols == scols &&
+                     std::memcmp(&key.T, &T_L_C, sizeof(Pose)) == 0 && std::memcmp(&key.cam, &cam, sizeof(Cam)) == 0;
+  mp.synth_rows = srows;
+  mp.synth_cols = scols;
   {
     // band-select tiles: small enough that a mindmap-sized AABB (a few hundred cells) spreads over many SMs
     int tile_cells = 32;
     while (tile_cells < 256 && (entry->bound + tile_cells - 1) / tile_cells > 2 * m->sm_count) tile_cells <<= 1;
     const int n_tiles = (entry->bound + tile_cells - 1) / tile_cells;
     const int trace_tiles_x = (scols + 15) / 16;
-    const int n_trace = trace_tiles_x * ((srows + 15) / 16);
+    const int n_trace = reuse ? 0 : trace_tiles_x * ((srows + 15) / 16);
     const int n_band = std::max(1, std::min(n_tiles, persistent_grid(m, 4)));
+    key.valid = false;  // a failed launch leaves no valid image behind
     LAUNCH(k_trace_and_band, n_trace + n_band, 256, 0, stream, mp.dev, tp, mp.synth.p, trace_tiles_x, n_trace, pv,
-           trunc, mp.band_slots.p, mp.newfeat_slots.p, tile_cells, n_tiles);
+           trunc, band_list, mp.newfeat_slots.p, tile_cells, n_tiles, color_parity);
+    key.T = T_L_C;
+    key.cam = cam;
+    key.trunc = trunc;
+    key.sub = sub;
+    key.tsdf_version = mp.tsdf_version;
+    key.valid = true;
   }
+  return NVBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, int height, int width, int channels,
+                            const void* mask, const float* T_L_C_rm, float fx, float fy, float cx, float cy,
+                            void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (!features || !T_L_C_rm || height <= 0 || width <= 0) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad feature frame");
+  if (channels != m->C)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame has %d channels, the map was created with %d", channels,
+                m->C);
+  if (((uintptr_t)features) & 15) return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame must be 16-byte aligned");
+  const nvbx_params& p = m->params;
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  Map& mp = *m->maps[map_id];
+  mp.have_band_list = false;
+  AppearancePrep prep;
+  if ((rc = appearance_prepare(m, mp, mp.planes_cache, height, width, T_L_C_rm, fx, fy, cx, cy, -1, stream, &prep)))
+    return rc;
+  if (prep.empty) return NVBX_OK;
+  const float trunc = prep.trunc;
+  const Cam cam = prep.cam;
+  const Pose T_C_L = prep.T_C_L;
+  const int srows = prep.srows, scols = prep.scols;
+  const long long cand_bound = prep.cand_bound;
+  const long long chunk_blocks = std::min<long long>(cand_bound, kFeatureChunkBlocks);
 
   FeatFrame ff;
   ff.img = (const __half*)features;
@@ -1004,17 +1139,48 @@ int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, in
 }
 
 int nvbx_integrate_color(nvbx_mapper* m, int map_id, const void* rgb, int height, int width, const void* mask,
-                         const float* T_L_C, float fx, float fy, float cx, float cy, void* stream) {
+                         const float* T_L_C_rm, float fx, float fy, float cx, float cy, void* stream_v) {
   int rc = check_map(m, map_id);
   if (rc) return rc;
-  if (!rgb || !T_L_C || height <= 0 || width <= 0) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad colour frame");
-  (void)mask;
-  (void)fx;
-  (void)fy;
-  (void)cx;
-  (void)cy;
-  (void)stream;
-  return NVBX_OK;  // no colour layer in this round (output-neutral for the feature cloud)
+  if (!rgb || !T_L_C_rm || height <= 0 || width <= 0) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad colour frame");
+  const nvbx_params& p = m->params;
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  Map& mp = *m->maps[map_id];
+  mp.have_cband_list = false;
+  const int parity = mp.color_parity;
+  AppearancePrep prep;
+  if ((rc = appearance_prepare(m, mp, mp.color_planes_cache, height, width, T_L_C_rm, fx, fy, cx, cy, parity, stream,
+                               &prep)))
+    return rc;
+  if (prep.empty) return NVBX_OK;
+  ColorFrame cf;
+  cf.img = (const uint8_t*)rgb;
+  cf.mask = (const uint8_t*)mask;
+  cf.synth = mp.synth.p;
+  cf.rows = height;
+  cf.cols = width;
+  cf.srows = prep.srows;
+  cf.scols = prep.scols;
+  cf.sub = prep.sub;
+  cf.cam = prep.cam;
+  cf.T_C_L = prep.T_C_L;
+  cf.max_depth = p.max_integration_distance_m;
+  cf.trunc = prep.trunc;
+  cf.alpha = p.appearance_measurement_weight;
+  cf.max_weight = p.max_weight;
+  {
+    float w1 = 1.0f - cf.alpha, w2 = cf.alpha;  // blendTwoArrays, projective_appearance_integrator.cu:286-305
+    const float tot = w1 + w2;
+    w1 /= tot;
+    w2 /= tot;
+    cf.w1 = __half2float(__float2half_rn(w1));  // weightedSum(uint8_t, ...) receives __float2half(weight)
+    cf.w2 = __half2float(__float2half_rn(w2));
+  }
+  const int grid = (int)std::max(1LL, std::min<long long>(persistent_grid(m, 2), prep.cand_bound));
+  LAUNCH(k_color_update, grid, 512, 0, stream, mp.dev, mp.cband_slots.p, cf, parity);
+  mp.color_parity ^= 1;
+  mp.have_cband_list = true;
+  return NVBX_OK;
 }
 
 int nvbx_integrate_frame_host(nvbx_mapper* m, int map_id, const float* depth_host, const void* features_host,
@@ -1058,6 +1224,7 @@ static int decay_one(nvbx_mapper* m, Map& mp, cudaStream_t stream) {
   dp.free_distance = m->params.tsdf_decayed_free_distance_vox * mp.voxel_size;
   dp.deallocate = m->params.deallocate_decayed_blocks;
   const int grid = std::max(1, (int)std::min<long long>(persistent_grid(m, 8), std::max(1LL, (long long)mp.slot_capacity)));
+  ++mp.tsdf_version;
   LAUNCH(k_decay, grid, 256, 0, stream, mp.dev, dp);
   if (dp.deallocate) {
     LAUNCH(k_hash_clear, persistent_grid(m, 4), 256, 0, stream, mp.dev, 0);
@@ -1094,60 +1261,89 @@ int nvbx_clear(nvbx_mapper* m, int map_id, void* stream_v) {
   if (rc) return rc;
   Map& mp = *m->maps[map_id];
   cudaStream_t stream = (cudaStream_t)stream_v;
+  ++mp.tsdf_version;
   LAUNCH(k_clear_all, persistent_grid(m, 4), 256, 0, stream, mp.dev);
   mp.slot_used_ub = 0;
   mp.feat_used_ub = 0;
   mp.mesh_nv = 0;
   mp.mesh_nt = 0;
+  mp.cmesh_nv = 0;
+  mp.cmesh_nt = 0;
   // NOTE: the viewpoint caches and the to-update tracker survive, as in the reference
   // (py_mapper.cu:286-306 clears the layers only).
   return NVBX_OK;
 }
 
 // ---- mesh ----------------------------------------------------------------------------------------
-static int update_mesh_one(nvbx_mapper* m, Map& mp, cudaStream_t stream) {
+static int update_mesh_one(nvbx_mapper* m, Map& mp, int kind, cudaStream_t stream) {
   int rc;
   const size_t cap = (size_t)mp.slot_capacity;
   if ((rc = mp.cnt_v.ensure(cap, stream))) return rc;
   if ((rc = mp.cnt_t.ensure(cap, stream))) return rc;
   if ((rc = mp.off_v.ensure(cap, stream))) return rc;
   if ((rc = mp.off_t.ensure(cap, stream))) return rc;
+  if (kind == kMeshColor && (rc = enable_color(mp, stream))) return rc;
   MeshParams mpar;
   mpar.min_weight = m->params.mesh_min_weight;
   mpar.cutoff = m->params.mesh_cutoff_distance_vox * mp.voxel_size;
   mpar.weld = m->params.mesh_weld_vertices;
   const int grid = persistent_grid(m, 2);
-  LAUNCH(k_mesh_count, grid, 512, sizeof(MeshSmem), stream, mp.dev, mpar, mp.cnt_v.p, mp.cnt_t.p);
-  LAUNCH(k_mesh_scan, 1, 1024, 0, stream, mp.dev, mp.cnt_v.p, mp.cnt_t.p, mp.off_v.p, mp.off_t.p);
+  if (kind == kMeshFeature)
+    LAUNCH(k_mesh_count<kMeshFeature>, grid, 512, sizeof(MeshSmem), stream, mp.dev, mpar, mp.cnt_v.p, mp.cnt_t.p);
+  else
+    LAUNCH(k_mesh_count<kMeshColor>, grid, 512, sizeof(MeshSmem), stream, mp.dev, mpar, mp.cnt_v.p, mp.cnt_t.p);
+  LAUNCH(k_mesh_scan, 1, 1024, 0, stream, mp.dev, mp.cnt_v.p, mp.cnt_t.p, mp.off_v.p, mp.off_t.p, kind);
   if ((rc = read_ctrl(mp, stream))) return rc;  // the one synchronisation of the export path
   const long long nv = mp.h_ctrl->mesh_total_v, nt = mp.h_ctrl->mesh_total_t;
   mp.slot_used_ub = (long long)mp.h_ctrl->slot_high - mp.h_ctrl->slot_free_top;  // free refresh of the bounds
   mp.feat_used_ub = (long long)mp.h_ctrl->feat_high - mp.h_ctrl->feat_free_top;
-  const int nxt = mp.arena_cur ^ 1;
-  if ((rc = mp.arena_v[nxt].ensure((size_t)std::max(1LL, nv) * 3, stream))) return rc;
-  if ((rc = mp.arena_f[nxt].ensure((size_t)std::max(1LL, nv) * m->C, stream))) return rc;
-  if ((rc = mp.arena_t[nxt].ensure((size_t)std::max(1LL, nt), stream))) return rc;
-  MeshArena prev{mp.arena_v[mp.arena_cur].p, mp.arena_f[mp.arena_cur].p, mp.arena_t[mp.arena_cur].p};
-  MeshArena out{mp.arena_v[nxt].p, mp.arena_f[nxt].p, mp.arena_t[nxt].p};
-  LAUNCH(k_mesh_emit, grid, 512, sizeof(MeshSmem), stream, mp.dev, mpar, mp.off_v.p, mp.off_t.p, prev, out);
-  mp.arena_cur = nxt;
-  mp.mesh_nv = nv;
-  mp.mesh_nt = nt;
+  if (kind == kMeshFeature) {
+    const int nxt = mp.arena_cur ^ 1;
+    if ((rc = mp.arena_v[nxt].ensure((size_t)std::max(1LL, nv) * 3, stream))) return rc;
+    if ((rc = mp.arena_f[nxt].ensure((size_t)std::max(1LL, nv) * m->C, stream))) return rc;
+    if ((rc = mp.arena_t[nxt].ensure((size_t)std::max(1LL, nt), stream))) return rc;
+    MeshArena prev{mp.arena_v[mp.arena_cur].p, mp.arena_f[mp.arena_cur].p, mp.arena_t[mp.arena_cur].p, nullptr};
+    MeshArena out{mp.arena_v[nxt].p, mp.arena_f[nxt].p, mp.arena_t[nxt].p, nullptr};
+    LAUNCH(k_mesh_emit<kMeshFeature>, grid, 512, sizeof(MeshSmem), stream, mp.dev, mpar, mp.off_v.p, mp.off_t.p, prev,
+           out);
+    mp.arena_cur = nxt;
+    mp.mesh_nv = nv;
+    mp.mesh_nt = nt;
+  } else {
+    const int nxt = mp.carena_cur ^ 1;
+    if ((rc = mp.carena_v[nxt].ensure((size_t)std::max(1LL, nv) * 3, stream))) return rc;
+    if ((rc = mp.carena_c[nxt].ensure((size_t)std::max(1LL, nv) * 3, stream))) return rc;
+    if ((rc = mp.carena_t[nxt].ensure((size_t)std::max(1LL, nt), stream))) return rc;
+    MeshArena prev{mp.carena_v[mp.carena_cur].p, nullptr, mp.carena_t[mp.carena_cur].p, mp.carena_c[mp.carena_cur].p};
+    MeshArena out{mp.carena_v[nxt].p, nullptr, mp.carena_t[nxt].p, mp.carena_c[nxt].p};
+    LAUNCH(k_mesh_emit<kMeshColor>, grid, 512, sizeof(MeshSmem), stream, mp.dev, mpar, mp.off_v.p, mp.off_t.p, prev,
+           out);
+    mp.carena_cur = nxt;
+    mp.cmesh_nv = nv;
+    mp.cmesh_nt = nt;
+  }
   return NVBX_OK;
 }
 
-int nvbx_update_feature_mesh(nvbx_mapper* m, int map_id, void* stream_v) {
+static int update_mesh(nvbx_mapper* m, int map_id, int kind, void* stream_v) {
   if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper handle");
   if (map_id < 0) {
     for (int i = 0; i < (int)m->maps.size(); ++i) {
-      int rc = nvbx_update_feature_mesh(m, i, stream_v);
+      int rc = update_mesh(m, i, kind, stream_v);
       if (rc) return rc;
     }
     return NVBX_OK;
   }
   int rc = check_map(m, map_id);
   if (rc) return rc;
-  return update_mesh_one(m, *m->maps[map_id], (cudaStream_t)stream_v);
+  return update_mesh_one(m, *m->maps[map_id], kind, (cudaStream_t)stream_v);
+}
+
+int nvbx_update_feature_mesh(nvbx_mapper* m, int map_id, void* stream_v) {
+  return update_mesh(m, map_id, kMeshFeature, stream_v);
+}
+int nvbx_update_color_mesh(nvbx_mapper* m, int map_id, void* stream_v) {
+  return update_mesh(m, map_id, kMeshColor, stream_v);
 }
 
 int nvbx_get_feature_mesh(nvbx_mapper* m, int map_id, const void** vertices, const void** features,
@@ -1163,12 +1359,26 @@ int nvbx_get_feature_mesh(nvbx_mapper* m, int map_id, const void** vertices, con
   return NVBX_OK;
 }
 
+int nvbx_get_color_mesh(nvbx_mapper* m, int map_id, const void** vertices, const void** colors,
+                        const void** triangles, int64_t* n_vertices, int64_t* n_triangles) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  Map& mp = *m->maps[map_id];
+  if (vertices) *vertices = mp.carena_v[mp.carena_cur].p;
+  if (colors) *colors = mp.carena_c[mp.carena_cur].p;
+  if (triangles) *triangles = mp.carena_t[mp.carena_cur].p;
+  if (n_vertices) *n_vertices = mp.cmesh_nv;
+  if (n_triangles) *n_triangles = mp.cmesh_nt / 3;
+  return NVBX_OK;
+}
+
 // ---- layer views ---------------------------------------------------------------------------------
 int64_t nvbx_num_blocks(nvbx_mapper* m, int map_id, int layer, void* stream_v) {
   int rc = check_map(m, map_id);
   if (rc) return rc;
   Map& mp = *m->maps[map_id];
   if ((rc = read_ctrl(mp, (cudaStream_t)stream_v))) return rc;
+  if (layer == NVBX_LAYER_COLOR) return mp.h_ctrl->n_color;
   return layer == NVBX_LAYER_TSDF ? mp.h_ctrl->n_tsdf : mp.h_ctrl->n_feat;
 }
 int64_t nvbx_num_allocated_blocks(nvbx_mapper* m, int map_id, int layer, void* stream_v) {
@@ -1176,6 +1386,7 @@ int64_t nvbx_num_allocated_blocks(nvbx_mapper* m, int map_id, int layer, void* s
   if (rc) return rc;
   (void)stream_v;
   Map& mp = *m->maps[map_id];
+  if (layer == NVBX_LAYER_COLOR) return mp.color_enabled ? mp.slot_capacity : 0;
   return layer == NVBX_LAYER_TSDF ? mp.slot_capacity : mp.feat_capacity;
 }
 int64_t nvbx_num_allocated_bytes(nvbx_mapper* m, int map_id, int layer, void* stream_v) {
@@ -1184,6 +1395,8 @@ int64_t nvbx_num_allocated_bytes(nvbx_mapper* m, int map_id, int layer, void* st
   (void)stream_v;
   Map& mp = *m->maps[map_id];
   if (layer == NVBX_LAYER_TSDF) return (int64_t)mp.slot_capacity * kVoxelsPerBlock * (int64_t)sizeof(float2);
+  if (layer == NVBX_LAYER_COLOR)
+    return mp.color_enabled ? (int64_t)mp.slot_capacity * kVoxelsPerBlock * (int64_t)sizeof(uint2) : 0;
   return (int64_t)mp.feat_capacity * kVoxelsPerBlock * (int64_t)mp.dev.row * (int64_t)sizeof(__half);
 }
 
@@ -1196,7 +1409,8 @@ int64_t nvbx_get_block_indices(nvbx_mapper* m, int map_id, int layer, int32_t* o
   if ((rc = mp.idx_out.ensure((size_t)mp.slot_capacity, stream))) return rc;
   CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->list_count, 0, sizeof(int), stream));
   LAUNCH(k_collect_block_indices, persistent_grid(m, 4), 256, 0, stream, mp.dev,
-         (uint8_t)(layer == NVBX_LAYER_TSDF ? kLayerTsdfBit : kLayerFeatBit), mp.idx_out.p, mp.slot_capacity);
+         (uint8_t)(layer == NVBX_LAYER_TSDF ? kLayerTsdfBit : (layer == NVBX_LAYER_COLOR ? kLayerColorBit : kLayerFeatBit)),
+         mp.idx_out.p, mp.slot_capacity);
   if ((rc = read_ctrl(mp, stream))) return rc;
   const int64_t n = mp.h_ctrl->list_count;
   if (out_xyz && capacity > 0) {
@@ -1214,12 +1428,15 @@ int nvbx_get_block_ptr(nvbx_mapper* m, int map_id, int layer, int x, int y, int 
   if (!ptr) return fail(NVBX_ERR_INVALID_ARGUMENT, "ptr is null");
   Map& mp = *m->maps[map_id];
   cudaStream_t stream = (cudaStream_t)stream_v;
+  if (layer == NVBX_LAYER_COLOR && !mp.color_enabled) return fail(NVBX_ERR_NOT_FOUND, "block (%d, %d, %d) is not allocated", x, y, z);
+  if (layer == NVBX_LAYER_TSDF) ++mp.tsdf_version;  // the caller may write through the returned view
   LAUNCH(k_find_one, 1, 1, 0, stream, mp.dev, x, y, z, layer, mp.d_tmp_ptr);
   unsigned long long h = 0;
   CUDA_TRY(cudaMemcpyAsync(&h, mp.d_tmp_ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
   *ptr = (void*)h;
-  if (voxel_stride_elems) *voxel_stride_elems = layer == NVBX_LAYER_TSDF ? 2 : mp.dev.row;
+  if (voxel_stride_elems)
+    *voxel_stride_elems = layer == NVBX_LAYER_TSDF ? 2 : (layer == NVBX_LAYER_COLOR ? 8 : mp.dev.row);
   if (!h) return fail(NVBX_ERR_NOT_FOUND, "block (%d, %d, %d) is not allocated", x, y, z);
   return NVBX_OK;
 }
@@ -1231,14 +1448,17 @@ int nvbx_allocate_block(nvbx_mapper* m, int map_id, int layer, int x, int y, int
   Map& mp = *m->maps[map_id];
   cudaStream_t stream = (cudaStream_t)stream_v;
   if ((rc = ensure_slots(m, mp, 1, stream))) return rc;
-  if (layer != NVBX_LAYER_TSDF) {
+  ++mp.tsdf_version;
+  if (layer == NVBX_LAYER_COLOR) {
+    if ((rc = enable_color(mp, stream))) return rc;
+  } else if (layer != NVBX_LAYER_TSDF) {
     // a stand-alone feature block: capacity is bounded by slots, so size it directly
     if (mp.feat_used_ub + 1 > mp.feat_capacity)
       if ((rc = grow_feats(m, mp, mp.feat_capacity + (1 << kFeatSlabShift), stream))) return rc;
     mp.feat_used_ub += 1;
   }
   LAUNCH(k_allocate_one, 1, 1, 0, stream, mp.dev, x, y, z, layer, mp.d_tmp_int);
-  if (layer != NVBX_LAYER_TSDF) LAUNCH(k_zero_one_feature_block, 64, 256, 0, stream, mp.dev, mp.d_tmp_int);
+  if (layer == NVBX_LAYER_FEATURE) LAUNCH(k_zero_one_feature_block, 64, 256, 0, stream, mp.dev, mp.d_tmp_int);
   return NVBX_OK;
 }
 
@@ -1285,7 +1505,11 @@ int nvbx_get_counters(nvbx_mapper* m, int map_id, nvbx_counters* out, void* stre
   out->blocks_deallocated = (int64_t)c[kCntBlocksDeallocated];
   out->mesh_blocks_remeshed = (int64_t)c[kCntMeshBlocksRemeshed];
   out->mesh_vertices = (int64_t)c[kCntMeshVertices];
-  for (int i = 0; i < 4; ++i) out->reserved[i] = (int64_t)c[12 + i];  // NVBX_PROFILE_COUNTERS builds only
+  out->color_frames = (int64_t)c[kCntColorFrames];
+  out->color_band_blocks = (int64_t)c[kCntColorBandBlocks];
+  out->color_voxels_updated = (int64_t)c[kCntColorVoxelsUpdated];
+  out->color_blocks_allocated = (int64_t)c[kCntColorBlocksAllocated];
+  for (int i = 0; i < 4; ++i) out->reserved[i] = (int64_t)c[kCntProfile0 + i];  // NVBX_PROFILE_COUNTERS builds only
   return NVBX_OK;
 }
 int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream_v) {
@@ -1374,12 +1598,13 @@ int64_t nvbx_debug_last_block_list(nvbx_mapper* m, int map_id, int which, int32_
     }
     return n;
   }
-  if (!mp.have_band_list) return 0;
+  if (which == 2 ? !mp.have_cband_list : !mp.have_band_list) return 0;
   if ((rc = read_ctrl(mp, stream))) return rc;
-  const int n = mp.h_ctrl->last_band_count;
+  const int n = which == 2 ? mp.h_ctrl->last_cband_count : mp.h_ctrl->last_band_count;
   if (out_xyz && capacity > 0 && n > 0) {
     std::vector<int> slots((size_t)n);
-    CUDA_TRY(cudaMemcpyAsync(slots.data(), mp.band_slots.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(slots.data(), which == 2 ? mp.cband_slots.p : mp.band_slots.p, (size_t)n * sizeof(int),
+                             cudaMemcpyDeviceToHost, stream));
     std::vector<int3> all((size_t)mp.slot_capacity);
     CUDA_TRY(cudaMemcpyAsync(all.data(), mp.dev.blk_index, all.size() * sizeof(int3), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));

@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(512, 3) k_tsdf_update(MapDev m, ViewSource src
       const int raw = src.view_slots[bi];
       if (raw < 0) continue;
       const int slot = raw & kSlotMask;
-      if (t == 0) m.blk_dirty[slot] = 1;  // blocks_to_update_tracker_.addBlocksToUpdate (mapper.cpp:406)
+      if (t == 0) m.blk_dirty[slot] = kDirtyAll;  // blocks_to_update_tracker_.addBlocksToUpdate (mapper.cpp:406)
       updated += tsdf_update_voxel(m, f, slot, (raw & kNewFlag) != 0, t);
     }
   } else {
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(512, 3) k_tsdf_update(MapDev m, ViewSource src
             slot |= kNewFlag;
             count_add(m, kCntTsdfBlocksAllocated, 1);
           }
-          m.blk_dirty[slot & kSlotMask] = 1;  // blocks_to_update_tracker_.addBlocksToUpdate (mapper.cpp:406)
+          m.blk_dirty[slot & kSlotMask] = kDirtyAll;  // blocks_to_update_tracker_.addBlocksToUpdate (mapper.cpp:406)
         }
         s_slot = slot;
       }
@@ -441,9 +441,12 @@ struct PlanesView {
 // One tile = `tile_cells` consecutive cells of the AABB (a multiple of 32, <= 256): phase 1 tests one cell
 // per thread and compacts the surviving slots into shared memory, phase 2 deals them to the CTA's warps.
 // Small tiles spread the few hundred candidates of a mindmap workspace over many SMs.
+// color_parity < 0: feature frame (band blocks get a feature slot).  color_parity = 0 / 1: colour frame -- band
+// blocks get the colour layer bit (their ColorVoxel payload lives at the slot id, like the TSDF payload) and are
+// appended to the colour band list counted by ctrl->cband_count[color_parity].
 __device__ __forceinline__ void band_select_tile(const MapDev& m, const PlanesView& view, float trunc,
                                                  int* band_slots, int* newfeat_slots, int tile, int tile_cells,
-                                                 int* s_cand, int* s_ncand) {
+                                                 int* s_cand, int* s_ncand, int color_parity) {
   const ViewGrid& g = view.g;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) *s_ncand = 0;
@@ -488,7 +491,17 @@ __device__ __forceinline__ void band_select_tile(const MapDev& m, const PlanesVi
     for (int j = 0; j < 8; ++j)
       hit |= (q[j].y > 0.0f && fabsf(q[j].x) < trunc) || (q[j].w > 0.0f && fabsf(q[j].z) < trunc);
     if (!__any_sync(0xffffffffu, hit)) continue;
-    if (lane == 0) {
+    if (lane == 0 && color_parity >= 0) {
+      int flag = 0;
+      const uint8_t layers = m.blk_layers[s];
+      if (!(layers & kLayerColorBit)) {
+        m.blk_layers[s] = layers | kLayerColorBit;
+        atomicAdd(&m.ctrl->n_color, 1);
+        count_add(m, kCntColorBlocksAllocated, 1);
+        flag = kNewFlag;  // k_color_update writes all 512 voxels of such a block (gray, weight 0 where not fused)
+      }
+      band_slots[atomicAdd(&m.ctrl->cband_count[color_parity], 1)] = s | flag;
+    } else if (lane == 0) {
       int flag = 0;
       if (m.blk_feat[s] < 0) {
         const int fs =
@@ -505,7 +518,7 @@ __device__ __forceinline__ void band_select_tile(const MapDev& m, const PlanesVi
       if (m.blk_feat[s] >= 0) band_slots[atomicAdd(&m.ctrl->band_count, 1)] = s | flag;
     }
   }
-  if (threadIdx.x == 0 && n_cand) count_add(m, kCntFeatCandidateBlocks, (unsigned)n_cand);
+  if (threadIdx.x == 0 && n_cand && color_parity < 0) count_add(m, kCntFeatCandidateBlocks, (unsigned)n_cand);
   __syncthreads();  // s_cand / s_ncand are reused by the CTA's next tile
 }
 
@@ -645,7 +658,7 @@ __device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TracePara
 __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp, float* __restrict__ image,
                                                         int trace_tiles_x, int n_trace_ctas, PlanesView view,
                                                         float trunc, int* band_slots, int* newfeat_slots,
-                                                        int tile_cells, int n_tiles) {
+                                                        int tile_cells, int n_tiles, int color_parity) {
   pdl_prologue();
   __shared__ int s_cand[256];
   __shared__ int s_ncand;
@@ -653,8 +666,9 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
 #ifdef NVBX_PROFILE_COUNTERS
   const long long t0 = clock64();
 #endif
+  if (blockIdx.x == 0 && threadIdx.x == 0) m.ctrl->item_count = 0;  // consumed by k_feature_geometry
+  // n_trace_ctas == 0: the synthetic depth image of this pose / camera / TSDF state is already in `image`
   if ((int)blockIdx.x < n_trace_ctas) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) m.ctrl->item_count = 0;  // consumed by k_feature_geometry
     const int c = (blockIdx.x % trace_tiles_x) * 16 + (threadIdx.x & 7) + ((threadIdx.x >> 7) << 3);
     const int r = (blockIdx.x / trace_tiles_x) * 16 + ((threadIdx.x >> 3) & 15);
     const bool stage_ws = m.ws_cells > 0 && m.ws_cells <= kTraceSmemCells;
@@ -673,9 +687,9 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       }
       if (lane_id() == 0) {
-        atomicAdd(&m.ctrl->counters[12], (unsigned long long)sum);
-        atomicMax(&m.ctrl->counters[13], (unsigned long long)mx);
-        atomicMax(&m.ctrl->counters[14], (unsigned long long)dt);
+        atomicAdd(&m.ctrl->counters[kCntProfile0], (unsigned long long)sum);
+        atomicMax(&m.ctrl->counters[kCntProfile0 + 1], (unsigned long long)mx);
+        atomicMax(&m.ctrl->counters[kCntProfile0 + 2], (unsigned long long)dt);
       }
     }
 #else
@@ -684,9 +698,9 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
     return;
   }
   for (int tile = (int)blockIdx.x - n_trace_ctas; tile < n_tiles; tile += (int)gridDim.x - n_trace_ctas)
-    band_select_tile(m, view, trunc, band_slots, newfeat_slots, tile, tile_cells, s_cand, &s_ncand);
+    band_select_tile(m, view, trunc, band_slots, newfeat_slots, tile, tile_cells, s_cand, &s_ncand, color_parity);
 #ifdef NVBX_PROFILE_COUNTERS
-  if (threadIdx.x == 0) atomicMax(&m.ctrl->counters[15], (unsigned long long)(clock64() - t0));
+  if (threadIdx.x == 0) atomicMax(&m.ctrl->counters[kCntProfile0 + 3], (unsigned long long)(clock64() - t0));
 #endif
 }
 
@@ -803,7 +817,7 @@ __global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* _
     const int3 b = m.blk_index[slot];
     const int fs = m.blk_feat[slot];
     __half* blk = feat_block(m, fs);
-    if (t == 0) m.blk_dirty[slot] = 1;  // mapper.cpp:462
+    if (t == 0) m.blk_dirty[slot] = kDirtyAll;  // mapper.cpp:462
 
     bool active = false;
     FeatItem it;
@@ -930,6 +944,99 @@ __global__ void __launch_bounds__(256, CTAS) k_feature_gather(MapDev m, const Fe
 }
 
 // ================================================================================================
+// N1. Colour integration: integrateBlocksKernel<UpdateAppearanceVoxelFunctor<ColorVoxel>>
+// (projective_integrator_impl.cuh:156-214, projective_appearance_integrator.cu:277-353).  Same geometry
+// as the feature path (projection, bilinear synthetic depth, band test, image bounds, mask); the payload
+// is the reference's 8-byte ColorVoxel (r, g, b, pad | float weight), moved as one uint2 per voxel.
+// interpolatePixels(Color) (interpolation_2d_impl.h:50-60) is the fp32 bilinear formula per channel followed
+// by std::round; the blend weights arrive already rounded through binary16 (`__float2half(weight)` at
+// :301-302); the first-observation test looks at the weight rounded to binary16 (:328).
+// One CTA of 512 threads per band block, thread = voxel; 12 bytes of image per updated voxel -- negligible
+// next to the feature gather, so no work-item indirection.
+// ================================================================================================
+struct ColorFrame {
+  const uint8_t* img;
+  const uint8_t* mask;  // may be null
+  const float* synth;
+  int rows, cols;
+  int srows, scols;
+  int sub;
+  Cam cam;
+  Pose T_C_L;
+  float max_depth;
+  float trunc;
+  float alpha;
+  float max_weight;
+  float w1, w2;  // float(half((1-alpha)/total)), float(half(alpha/total))
+};
+
+constexpr unsigned kGrayVoxel = 0x007f7f7fu;  // Color::Gray() + zeroed padding byte (blox.cu:32-54)
+
+__global__ void __launch_bounds__(512) k_color_update(MapDev m, const int* __restrict__ band_slots, ColorFrame f,
+                                                      int parity) {
+  pdl_prologue();
+  const int n = m.ctrl->cband_count[parity];
+  const int t = threadIdx.x;
+  const int vx = t >> 6, vy = (t >> 3) & 7, vz = t & 7;
+  unsigned updated = 0;
+  for (int bi = blockIdx.x; bi < n; bi += gridDim.x) {
+    const int raw = band_slots[bi];
+    const bool is_new = (raw & kNewFlag) != 0;
+    const int slot = raw & kSlotMask;
+    const int3 b = m.blk_index[slot];
+    uint2* vox = color_block(m, slot) + t;
+    if (t == 0) m.blk_dirty[slot] = kDirtyAll;  // mapper.cpp:448
+    bool write = is_new;
+    uint2 out = make_uint2(kGrayVoxel, 0u);
+    do {
+      float u, v, vd;
+      if (!project_voxel(f.cam, f.T_C_L, m.block_size, f.max_depth, b, vx, vy, vz, &u, &v, &vd)) break;
+      const float ud = u / (float)f.sub, vdp = v / (float)f.sub;
+      const float uc = ud - 0.5f, vc = vdp - 0.5f;
+      const int lx = (int)floorf(uc), ly = (int)floorf(vc);
+      if (lx < 0 || ly < 0 || (lx + 1) > (f.scols - 1) || (ly + 1) > (f.srows - 1)) break;
+      const float* sp = f.synth + (size_t)ly * f.scols + lx;
+      const float surface = interp_float(uc - (float)lx, vc - (float)ly, sp[0], sp[f.scols], sp[1], sp[f.scols + 1]);
+      if (fabsf(surface - vd) > f.trunc) break;
+      const float fu = u - 0.5f, fv = v - 0.5f;
+      const int px = (int)floorf(fu), py = (int)floorf(fv);
+      if (px < 0 || py < 0 || (px + 1) > (f.cols - 1) || (py + 1) > (f.rows - 1)) break;
+      if (f.mask != nullptr && !__ldg(f.mask + (size_t)((int)v) * f.cols + (int)u)) break;
+      const uint2 cur = is_new ? make_uint2(kGrayVoxel, 0u) : *vox;
+      const float w_cur = __uint_as_float(cur.y);
+      const bool first = __half2float(__float2half_rn(w_cur)) == 0.0f;
+      const float ox = fu - (float)px, oy = fv - (float)py;
+      const uint8_t* p00 = f.img + ((size_t)py * f.cols + px) * 3;
+      const uint8_t* p01 = p00 + (size_t)f.cols * 3;
+      unsigned rgb = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float m00 = (float)__ldg(p00 + c), m10 = (float)__ldg(p00 + 3 + c);
+        const float m01 = (float)__ldg(p01 + c), m11 = (float)__ldg(p01 + 3 + c);
+        unsigned ch = (unsigned)(uint8_t)roundf(interp_float(ox, oy, m00, m01, m10, m11));
+        if (!first) {
+          const float old = (float)((cur.x >> (8 * c)) & 0xffu);
+          ch = (unsigned)(uint8_t)roundf(old * f.w1 + (float)ch * f.w2);
+        }
+        rgb |= ch << (8 * c);
+      }
+      out = make_uint2(rgb, __float_as_uint(fminf(f.alpha + w_cur, f.max_weight)));
+      write = true;
+      updated = 1;
+    } while (false);
+    if (write) *vox = out;
+  }
+  for (int o = 16; o; o >>= 1) updated += __shfl_xor_sync(0xffffffffu, updated, o);
+  if (lane_id() == 0 && updated) count_add(m, kCntColorVoxelsUpdated, updated);
+  if (blockIdx.x == 0 && t == 0) {
+    count_add(m, kCntColorBandBlocks, (unsigned long long)n);
+    count_add(m, kCntColorFrames, 1);
+    m.ctrl->last_cband_count = n;
+    m.ctrl->cband_count[parity ^ 1] = 0;  // ready for the next colour frame's band_select_tile
+  }
+}
+
+// ================================================================================================
 // a9. Decay.  decayKernel + TsdfDecayFunctor (decayer_impl.cuh:83-125, tsdf_decay_integrator.cu:58-112)
 // fused with deallocateFullyDecayedBlocks (:259-274) and Mapper::clearBlocksInLayers
 // (mapper.cpp:761-849): a fully decayed block releases its TSDF slot, feature slot and mesh extent on
@@ -978,13 +1085,15 @@ __global__ void __launch_bounds__(256) k_decay(MapDev m, DecayParams dp) {
           atomicAdd(&m.ctrl->n_feat, -1);
           m.blk_feat[slot] = -1;
         }
+        if (layers & kLayerColorBit) atomicAdd(&m.ctrl->n_color, -1);
         m.blk_mesh[slot] = make_int4(0, 0, 0, 0);
+        m.blk_cmesh[slot] = make_int4(0, 0, 0, 0);
         m.blk_dirty[slot] = 0;
         unindex_slot(m, slot);
         push_id(&m.ctrl->slot_free_top, m.slot_free, slot);
         count_add(m, kCntBlocksDeallocated, 1);
       } else {
-        m.blk_dirty[slot] = 1;  // decayTsdf marks every TSDF block "to update" (mapper.cpp:469-471)
+        m.blk_dirty[slot] = kDirtyAll;  // decayTsdf marks every TSDF block "to update" (mapper.cpp:469-471)
       }
     }
   }
@@ -1030,6 +1139,9 @@ __global__ void __launch_bounds__(256) k_clear_all(MapDev m) {
     c->feat_high = 0;
     c->n_tsdf = 0;
     c->n_feat = 0;
+    c->n_color = 0;
+    c->cband_count[0] = 0;
+    c->cband_count[1] = 0;
     c->rebuild = 0;
     c->mesh_total_v = 0;
     c->mesh_total_t = 0;
@@ -1064,6 +1176,13 @@ __global__ void k_allocate_one(MapDev m, int x, int y, int z, int layer, int* ne
   }
   if (layer == 0) {
     ensure_tsdf_layer(m, slot);
+  } else if (layer == 2) {
+    if (!(m.blk_layers[slot] & kLayerColorBit)) {
+      m.blk_layers[slot] |= kLayerColorBit;
+      atomicAdd(&m.ctrl->n_color, 1);
+      uint2* c = color_block(m, slot);
+      for (int i = 0; i < kVoxelsPerBlock; ++i) c[i] = make_uint2(kGrayVoxel, 0u);
+    }
   } else if (m.blk_feat[slot] < 0) {
     const int fs =
         pop_id(&m.ctrl->feat_free_top, &m.ctrl->feat_high, m.feat_free, m.feat_capacity, &m.ctrl->overflow);
@@ -1090,6 +1209,8 @@ __global__ void k_find_one(MapDev m, int x, int y, int z, int layer, unsigned lo
   if (slot < 0) return;
   if (layer == 0) {
     if (m.blk_layers[slot] & kLayerTsdfBit) *ptr_out = (unsigned long long)tsdf_block(m, slot);
+  } else if (layer == 2) {
+    if (m.blk_layers[slot] & kLayerColorBit) *ptr_out = (unsigned long long)color_block(m, slot);
   } else {
     if (m.blk_feat[slot] >= 0) *ptr_out = (unsigned long long)feat_block(m, m.blk_feat[slot]);
   }

@@ -33,6 +33,12 @@ constexpr unsigned long long kEmptyKey = ~0ull;
 
 constexpr uint8_t kLayerTsdfBit = 1;
 constexpr uint8_t kLayerFeatBit = 2;
+constexpr uint8_t kLayerColorBit = 4;
+// blk_dirty bits: one "to update" set per mesh layer (BlocksToUpdateTracker, blocks_to_update_tracker.cpp:32-60:
+// every addBlocksToUpdate feeds all consumer sets, every consumer clears only its own)
+constexpr uint8_t kDirtyFeatMesh = 1;
+constexpr uint8_t kDirtyColorMesh = 2;
+constexpr uint8_t kDirtyAll = 3;
 // slot lists carry "freshly allocated, payload not initialised yet" in bit 30 (slot ids are < 2^30)
 constexpr int kNewFlag = 0x40000000;
 constexpr int kSlotMask = 0x3fffffff;
@@ -51,7 +57,12 @@ enum CounterId {
   kCntBlocksDeallocated,
   kCntMeshBlocksRemeshed,
   kCntMeshVertices,
-  kCntNum = 16
+  kCntColorFrames,
+  kCntColorBandBlocks,
+  kCntColorVoxelsUpdated,
+  kCntColorBlocksAllocated,
+  kCntProfile0 = 16,  // NVBX_PROFILE_COUNTERS builds: 16..19
+  kCntNum = 24
 };
 
 // Device-side control block (one per map).
@@ -74,6 +85,10 @@ struct Ctrl {
   int item_count;      // length of the feature work-item list of the current chunk
   int last_band_count; // band_count of the last completed feature frame (debug / parity hook)
   int n_hash;          // blocks resident in the overflow hash (0: every block is in the workspace grid)
+  int n_color;         // live colour blocks
+  int cband_count[2];  // colour band list length, double-buffered by frame parity (the consumer of one frame
+                       // clears the other half, so no kernel both reads and resets the same counter)
+  int last_cband_count;
   int pad[2];
   unsigned long long counters[kCntNum];
 };
@@ -94,11 +109,14 @@ struct MapDev {
   int* blk_feat;
   uint8_t* blk_dirty;
   int4* blk_mesh;  // (vertex offset, vertex count, triangle-index offset, triangle-index count)
+  int4* blk_cmesh; // the same for the colour mesh layer
   int slot_capacity;
   int feat_capacity;
   // payload arenas
   float2* const* tsdf_slabs;
   __half* const* feat_slabs;
+  uint2* const* color_slabs;  // ColorVoxel records (r, g, b, pad | float weight), slot-indexed like the TSDF slabs;
+                              // allocated on the first colour frame
   // free lists
   int* slot_free;
   int* feat_free;
@@ -113,6 +131,9 @@ struct MapDev {
 
 __device__ __forceinline__ float2* tsdf_block(const MapDev& m, int slot) {
   return m.tsdf_slabs[slot >> kTsdfSlabShift] + (size_t)(slot & ((1 << kTsdfSlabShift) - 1)) * kVoxelsPerBlock;
+}
+__device__ __forceinline__ uint2* color_block(const MapDev& m, int slot) {
+  return m.color_slabs[slot >> kTsdfSlabShift] + (size_t)(slot & ((1 << kTsdfSlabShift) - 1)) * kVoxelsPerBlock;
 }
 __device__ __forceinline__ __half* feat_block(const MapDev& m, int fslot) {
   return m.feat_slabs[fslot >> kFeatSlabShift] +
@@ -218,6 +239,7 @@ __device__ __forceinline__ int acquire_slot(const MapDev& m, int x, int y, int z
   m.blk_feat[slot] = -1;
   m.blk_dirty[slot] = 0;
   m.blk_mesh[slot] = make_int4(0, 0, 0, 0);
+  m.blk_cmesh[slot] = make_int4(0, 0, 0, 0);
   if (cell >= 0) {
     m.ws_slot[cell] = slot;
   } else {

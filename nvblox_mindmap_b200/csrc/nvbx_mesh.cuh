@@ -32,10 +32,23 @@ struct MeshParams {
 };
 
 struct MeshArena {
-  float* verts;    // [cap_v * 3]
-  __half* feats;   // [cap_v * C]
-  int* tris;       // [cap_t]
+  float* verts;     // [cap_v * 3]
+  __half* feats;    // [cap_v * C]   (feature mesh)
+  int* tris;        // [cap_t]
+  uint8_t* colors;  // [cap_v * 3]   (colour mesh)
 };
+
+// The reference keeps one mesh layer per appearance type (MeshBlockLayer<FeatureArray>, MeshBlockLayer<Color>),
+// each with its own "to update" set; KIND selects which one a launch works on.
+enum MeshKind { kMeshFeature = 0, kMeshColor = 1 };
+template <int KIND>
+__device__ __forceinline__ int4* mesh_extents(const MapDev& m) {
+  return KIND == kMeshFeature ? m.blk_mesh : m.blk_cmesh;
+}
+template <int KIND>
+__device__ __forceinline__ uint8_t mesh_dirty_bit() {
+  return KIND == kMeshFeature ? kDirtyFeatMesh : kDirtyColorMesh;
+}
 
 // shared-memory carve-up of the mesh CTA
 struct MeshSmem {
@@ -118,7 +131,7 @@ __device__ __forceinline__ void warp_paint_vertex(const MapDev& m, const __half*
 
 // One CTA (512 threads) meshes one block.  EMIT=false: only sizes.  EMIT=true: writes the block's
 // vertices / triangles / features at (voff, toff) of `out`.
-template <bool EMIT>
+template <bool EMIT, int KIND>
 __device__ void mesh_one_block(const MapDev& m, const MeshParams& mp, MeshSmem& s, int slot, int voff, int toff,
                                const MeshArena& out, int* n_verts_out, int* n_tris_out) {
   const int t = threadIdx.x;
@@ -292,7 +305,42 @@ __device__ void mesh_one_block(const MapDev& m, const MeshParams& mp, MeshSmem& 
     }
   }
 
-  if (EMIT) {
+  if (EMIT && KIND == kMeshColor) {
+    // ---- vertex colours: closest voxel's colour, Gray without a colour block (AppearanceGetter<ColorVoxel>,
+    // mesh_integrator_appearance.cu:43-54), one thread per vertex
+    const bool has_color = (m.blk_layers[slot] & kLayerColorBit) != 0;
+    const uint2* cblk = has_color ? color_block(m, slot) : nullptr;
+    const float vs_paint = m.block_size / 8;
+    if (!weld) __syncthreads();
+    for (int i = t; i < n_unique; i += 512) {
+      float x, y, z;
+      if (weld) {
+        const int src = s.head[i];
+        x = s.vx[src];
+        y = s.vy[src];
+        z = s.vz[src];
+      } else {
+        const float* o = out.verts + (size_t)(voff + i) * 3;
+        x = o[0];
+        y = o[1];
+        z = o[2];
+      }
+      unsigned rgb = kGrayVoxel;
+      if (cblk) {
+        int ix = (int)((x - origin[0]) / vs_paint), iy = (int)((y - origin[1]) / vs_paint),
+            iz = (int)((z - origin[2]) / vs_paint);
+        ix = max(min(ix, 7), 0);
+        iy = max(min(iy, 7), 0);
+        iz = max(min(iz, 7), 0);
+        rgb = cblk[(ix * 8 + iy) * 8 + iz].x;
+      }
+      uint8_t* d = out.colors + (size_t)(voff + i) * 3;
+      d[0] = (uint8_t)(rgb & 0xffu);
+      d[1] = (uint8_t)((rgb >> 8) & 0xffu);
+      d[2] = (uint8_t)((rgb >> 16) & 0xffu);
+    }
+  }
+  if (EMIT && KIND == kMeshFeature) {
     // ---- vertex features: one warp per vertex ---------------------------------------------------------
     const int fs = m.blk_feat[slot];
     const __half* fblk = fs >= 0 ? feat_block(m, fs) : nullptr;
@@ -320,6 +368,7 @@ __device__ void mesh_one_block(const MapDev& m, const MeshParams& mp, MeshSmem& 
 }
 
 // pass 1: per-slot sizes of the NEW mesh
+template <int KIND>
 __global__ void __launch_bounds__(512, 2) k_mesh_count(MapDev m, MeshParams mp, int* cnt_v, int* cnt_t) {
   pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -330,12 +379,12 @@ __global__ void __launch_bounds__(512, 2) k_mesh_count(MapDev m, MeshParams mp, 
     int nv = 0, nt = 0;
     const bool has_tsdf = (m.blk_layers[slot] & kLayerTsdfBit) != 0;
     if (has_tsdf) {
-      if (m.blk_dirty[slot]) {
-        MeshArena none = {nullptr, nullptr, nullptr};
-        mesh_one_block<false>(m, mp, s, slot, 0, 0, none, &nv, &nt);
+      if (m.blk_dirty[slot] & mesh_dirty_bit<KIND>()) {
+        MeshArena none = {nullptr, nullptr, nullptr, nullptr};
+        mesh_one_block<false, KIND>(m, mp, s, slot, 0, 0, none, &nv, &nt);
         ++remeshed;
       } else {
-        const int4 old = m.blk_mesh[slot];
+        const int4 old = mesh_extents<KIND>(m)[slot];
         nv = old.y;
         nt = old.w;
       }
@@ -346,12 +395,12 @@ __global__ void __launch_bounds__(512, 2) k_mesh_count(MapDev m, MeshParams mp, 
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0 && remeshed) count_add(m, kCntMeshBlocksRemeshed, remeshed);
+  if (KIND == kMeshFeature && threadIdx.x == 0 && remeshed) count_add(m, kCntMeshBlocksRemeshed, remeshed);
 }
 
 // device-side exclusive scan over the slot table (single CTA; the table is small)
 __global__ void __launch_bounds__(1024) k_mesh_scan(MapDev m, const int* cnt_v, const int* cnt_t, int* off_v,
-                                                    int* off_t) {
+                                                    int* off_t, int kind) {
   pdl_prologue();
   __shared__ int ws_v[33], ws_t[33];
   __shared__ int carry_v, carry_t;
@@ -402,11 +451,12 @@ __global__ void __launch_bounds__(1024) k_mesh_scan(MapDev m, const int* cnt_v, 
   if (threadIdx.x == 0) {
     m.ctrl->mesh_total_v = carry_v;
     m.ctrl->mesh_total_t = carry_t;
-    m.ctrl->counters[kCntMeshVertices] = (unsigned long long)carry_v;
+    if (kind == kMeshFeature) m.ctrl->counters[kCntMeshVertices] = (unsigned long long)carry_v;
   }
 }
 
 // pass 2: write the new arena; clean blocks are copied from the previous arena
+template <int KIND>
 __global__ void __launch_bounds__(512, 2) k_mesh_emit(MapDev m, MeshParams mp, const int* off_v, const int* off_t,
                                                       MeshArena prev, MeshArena out) {
   pdl_prologue();
@@ -418,24 +468,28 @@ __global__ void __launch_bounds__(512, 2) k_mesh_emit(MapDev m, MeshParams mp, c
     if (!(m.blk_layers[slot] & kLayerTsdfBit)) continue;
     const int voff = off_v[slot], toff = off_t[slot];
     int nv = 0, nt = 0;
-    if (m.blk_dirty[slot]) {
-      mesh_one_block<true>(m, mp, s, slot, voff, toff, out, &nv, &nt);
+    if (m.blk_dirty[slot] & mesh_dirty_bit<KIND>()) {
+      mesh_one_block<true, KIND>(m, mp, s, slot, voff, toff, out, &nv, &nt);
     } else {
-      const int4 old = m.blk_mesh[slot];
+      const int4 old = mesh_extents<KIND>(m)[slot];
       nv = old.y;
       nt = old.w;
       for (int i = t; i < nv * 3; i += 512) out.verts[(size_t)voff * 3 + i] = prev.verts[(size_t)old.x * 3 + i];
       const int shift = voff - old.x;
       for (int i = t; i < nt; i += 512) out.tris[toff + i] = prev.tris[old.z + i] + shift;
-      const size_t nvecs = (size_t)nv * (size_t)(m.C >> 3);
-      const uint4* src = reinterpret_cast<const uint4*>(prev.feats + (size_t)old.x * m.C);
-      uint4* dst = reinterpret_cast<uint4*>(out.feats + (size_t)voff * m.C);
-      for (size_t i = t; i < nvecs; i += 512) dst[i] = src[i];
+      if (KIND == kMeshFeature) {
+        const size_t nvecs = (size_t)nv * (size_t)(m.C >> 3);
+        const uint4* src = reinterpret_cast<const uint4*>(prev.feats + (size_t)old.x * m.C);
+        uint4* dst = reinterpret_cast<uint4*>(out.feats + (size_t)voff * m.C);
+        for (size_t i = t; i < nvecs; i += 512) dst[i] = src[i];
+      } else {
+        for (int i = t; i < nv * 3; i += 512) out.colors[(size_t)voff * 3 + i] = prev.colors[(size_t)old.x * 3 + i];
+      }
     }
     __syncthreads();
     if (t == 0) {
-      m.blk_mesh[slot] = make_int4(voff, nv, toff, nt);
-      m.blk_dirty[slot] = 0;  // markBlocksAsUpdated (mapper.cpp:611)
+      mesh_extents<KIND>(m)[slot] = make_int4(voff, nv, toff, nt);
+      m.blk_dirty[slot] &= (uint8_t)~mesh_dirty_bit<KIND>();  // markBlocksAsUpdated (mapper.cpp:611)
     }
     __syncthreads();
   }

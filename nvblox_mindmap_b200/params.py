@@ -55,6 +55,10 @@ class NvbxCounters(C.Structure):
         ('blocks_deallocated', C.c_int64),
         ('mesh_blocks_remeshed', C.c_int64),
         ('mesh_vertices', C.c_int64),
+        ('color_frames', C.c_int64),
+        ('color_band_blocks', C.c_int64),
+        ('color_voxels_updated', C.c_int64),
+        ('color_blocks_allocated', C.c_int64),
         ('reserved', C.c_int64 * 4),
     ]
 

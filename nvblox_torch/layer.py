@@ -1,7 +1,7 @@
 """Layer views (reference: nvblox_torch/layer.py, cpp/src/py_layer.cpp:24-198).
 
 A layer view shares the mapper's device-resident map.  Block tensors are zero-copy views:
-TSDF [8,8,8,2] float32 (distance, weight), feature [8,8,8,C+1] float16 (C features, weight) -- the
+TSDF [8,8,8,2] float32 (distance, weight), colour [8,8,8,3] uint8, feature [8,8,8,C+1] float16 (C features, weight) -- the
 feature view is STRIDED (voxel rows are padded to C+8 halves so they stay 16-byte aligned); call
 .contiguous() if a dense copy is needed.  Views are invalidated by any call that mutates the map.
 """
@@ -17,7 +17,7 @@ from nvblox_mindmap_b200.torch_interop import current_stream_ptr, device_view
 from nvblox_torch import indexing
 from nvblox_torch.constants import constants
 
-_TSDF, _FEATURE = 0, 1
+_TSDF, _FEATURE, _COLOR = 0, 1, 2
 
 
 class Layer(abc.ABC):
@@ -82,7 +82,7 @@ class Layer(abc.ABC):
             return None
         _capi.check(rc)
         n, s = self.num_elements_per_voxel(), int(stride.value)
-        dtype = torch.float32 if self._layer_id == _TSDF else torch.float16
+        dtype = {_TSDF: torch.float32, _FEATURE: torch.float16, _COLOR: torch.uint8}[self._layer_id]
         return device_view(ptr.value, (8, 8, 8, n), dtype, self._mapper._device,
                            strides_elems=(64 * s, 8 * s, s, 1), owner=self._mapper)
 
@@ -162,7 +162,12 @@ class FeatureLayer(Layer):
 
 
 class ColorLayer(Layer):
-    """Not on this path."""
+    """Colour layer view: [8,8,8,3] uint8 RGB, striding over the per-voxel weight exactly like the reference's
+    tensorFromBlock(ColorBlock*) (py_layer.cpp:49-70: 8-byte ColorVoxel = r, g, b, pad, float weight)."""
+    _layer_id = _COLOR
+
+    def __init__(self, voxel_size_m: float, c_layer=None):
+        super().__init__(voxel_size_m, 'ColorLayer', c_layer)
 
     @staticmethod
     def num_elements_per_voxel() -> int:

@@ -139,9 +139,10 @@ class Mapper:
                         intrinsics: torch.Tensor,
                         mask_frame: Optional[torch.Tensor] = None,
                         mapper_id: int = 0) -> None:
-        """(H, W, 3) uint8 colour frame.  Validated and ignored in this round."""
+        """Integrate a (H, W, 3) uint8 CUDA colour frame into the colour layer (reference mapper.py:112-129)."""
         assert 0 <= mapper_id < len(self._voxel_sizes)
         check_integrator_inputs(color_frame, t_w_c, intrinsics, 'Color', 3, torch.uint8, 3)
+        color_frame = color_frame if color_frame.is_contiguous() else color_frame.contiguous()
         mask_ptr = self._mask_ptr(mask_frame, color_frame)
         fx, fy, cx, cy = _fxfycxcy(intrinsics)
         _capi.check(self._lib.nvbx_integrate_color(
@@ -189,7 +190,9 @@ class Mapper:
         raise NotImplementedError('ESDF is not on the accelerated path (SURVEY.md 2.3)')
 
     def update_color_mesh(self, mapper_id: int = -1) -> None:
-        assert -1 <= mapper_id < len(self._voxel_sizes)    # no colour layer yet
+        """Re-mesh the blocks touched since the last colour-mesh update and refresh their vertex colours."""
+        assert -1 <= mapper_id < len(self._voxel_sizes)
+        _capi.check(self._lib.nvbx_update_color_mesh(self._handle, mapper_id, self._stream()))
 
     def update_feature_mesh(self, mapper_id: int = -1) -> None:
         """Re-mesh the blocks touched since the last update and refresh their vertex features."""
@@ -197,8 +200,18 @@ class Mapper:
         _capi.check(self._lib.nvbx_update_feature_mesh(self._handle, mapper_id, self._stream()))
 
     def get_color_mesh(self, mapper_id: int = 0) -> ColorMesh:
+        """Serialised colour mesh as zero-copy device views: vertices [N,3] f32, colours [N,3] u8, triangles."""
         assert 0 <= mapper_id < len(self._voxel_sizes)
-        return ColorMesh()
+        v, c, t = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nv, nt = C.c_int64(), C.c_int64()
+        _capi.check(self._lib.nvbx_get_color_mesh(self._handle, mapper_id, C.byref(v), C.byref(c), C.byref(t),
+                                                  C.byref(nv), C.byref(nt)))
+        d = self._device
+        return ColorMesh(c_mesh={
+            'vertices': device_view(v.value, (nv.value, 3), torch.float32, d, owner=self),
+            'appearances': device_view(c.value, (nv.value, 3), torch.uint8, d, owner=self),
+            'triangles': device_view(t.value, (nt.value, 3), torch.int32, d, owner=self),
+        })
 
     def get_feature_mesh(self, mapper_id: int = 0) -> FeatureMesh:
         """Serialised feature mesh as zero-copy device views (no kernel, no copy)."""
@@ -224,7 +237,8 @@ class Mapper:
         return FeatureLayer(voxel_size_m=self._voxel_sizes[mapper_id], c_layer=(self, mapper_id))
 
     def color_layer_view(self, mapper_id: int = 0) -> ColorLayer:
-        raise NotImplementedError('colour layer: SURVEY.md 8(f) N1 (next)')
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        return ColorLayer(voxel_size_m=self._voxel_sizes[mapper_id], c_layer=(self, mapper_id))
 
     def save_map(self, map_fname: str, mapper_id: int) -> None:
         raise NotImplementedError('.nvblx serialisation: SURVEY.md 8(f) N3 (next)')

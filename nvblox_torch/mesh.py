@@ -64,7 +64,8 @@ class FeatureMesh(Mesh):
 
 
 class ColorMesh(Mesh):
-    """Colour mesh -- SURVEY 8(f) N1 ("next"): always empty in this round."""
+    """Mesh whose vertices carry the uint8 RGB of the closest colour voxel (Gray where no colour block exists)."""
 
     def vertex_colors(self) -> torch.Tensor:
+        """Vertex colours (N, 3) uint8."""
         return self.vertex_appearances()

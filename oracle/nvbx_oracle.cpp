@@ -437,10 +437,22 @@ struct TsdfBlock {
 };
 inline int vlin(int x, int y, int z) { return (x * 8 + y) * 8 + z; }  // voxels[x][y][z], blox.h:28-67
 
+// ColorVoxel {Color color = Gray (127,127,127); float weight = 0}, NB/include/nvblox/map/voxels.h:77-83,
+// gray initialisation NB/src/map/blox.cu:32-54
+struct ColorBlock {
+  uint8_t c[512][3];
+  float w[512];
+  ColorBlock() {
+    std::memset(c, 127, sizeof(c));
+    std::memset(w, 0, sizeof(w));
+  }
+};
+
 struct MeshBlock {
   std::vector<V3> verts;
   std::vector<int> tris;             // block-local vertex ids, size = unwelded vertex count
-  std::vector<uint16_t> feats;       // verts.size() * C
+  std::vector<uint16_t> feats;       // verts.size() * C     (feature mesh layer)
+  std::vector<uint8_t> colors;       // verts.size() * 3     (colour mesh layer)
 };
 
 struct Counters {
@@ -454,10 +466,14 @@ struct Oracle {
   nvbx_params p;
   std::map<I3, TsdfBlock> tsdf;
   std::map<I3, std::vector<uint16_t>> feat;  // 512 * (C+1): [voxel][0..C) feature, [C] weight
-  std::map<I3, MeshBlock> mesh;
-  std::set<I3> mesh_dirty;  // BlocksToUpdateTracker::feature_mesh_blocks_to_update_
-  ViewCache raycast_cache, planes_cache;
-  std::vector<I3> last_tsdf_list, last_feat_list;
+  std::map<I3, ColorBlock> color;
+  std::map<I3, MeshBlock> mesh;    // MeshBlockLayer<FeatureArray>
+  std::map<I3, MeshBlock> cmesh;   // MeshBlockLayer<Color> -- a separate layer with its own geometry
+  std::set<I3> mesh_dirty;   // BlocksToUpdateTracker::feature_mesh_blocks_to_update_
+  std::set<I3> cmesh_dirty;  // BlocksToUpdateTracker::color_mesh_blocks_to_update_
+  // every integrator owns a ViewCalculator and with it a viewpoint cache (projective_integrator.h)
+  ViewCache raycast_cache, planes_cache, color_planes_cache;
+  std::vector<I3> last_tsdf_list, last_feat_list, last_color_list;
   std::vector<float> synth;
   int synth_rows = 0, synth_cols = 0;
   nvbx_counters cnt;
@@ -645,16 +661,20 @@ void integrate_depth(Oracle& o, const float* depth, int rows, int cols, const ui
   }
   o.cnt.tsdf_voxels_updated += n_updated;
   o.cnt.tsdf_blocks_in_view += (int64_t)blocks.size();
-  for (const I3& b : blocks) o.mesh_dirty.insert(b);  // mapper.cpp:406
+  for (const I3& b : blocks) {  // mapper.cpp:406 -> blocks_to_update_tracker.cpp:32-60 (every consumer set)
+    o.mesh_dirty.insert(b);
+    o.cmesh_dirty.insert(b);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // a6: planes view + band filter.  view_calculator.cu:392-470, bounding_boxes_impl.h:28-52,
 // projective_appearance_integrator.cu:374-477
 // ------------------------------------------------------------------------------------------------
-std::vector<I3> blocks_in_view_planes(Oracle& o, const Pose& T_L_C, const Cam& cam, float max_distance) {
+std::vector<I3> blocks_in_view_planes(Oracle& o, ViewCache& cache, const Pose& T_L_C, const Cam& cam,
+                                      float max_distance) {
   if (o.p.cache_last_viewpoint) {
-    if (const std::vector<I3>* hit = o.planes_cache.get(T_L_C, cam)) return *hit;
+    if (const std::vector<I3>* hit = cache.get(T_L_C, cam)) return *hit;
   }
   Aabb aabb = view_aabb(cam, T_L_C, 1e-6f, max_distance);
   if (!apply_workspace_bounds(o.p, &aabb)) return {};
@@ -678,7 +698,7 @@ std::vector<I3> blocks_in_view_planes(Oracle& o, const Pose& T_L_C, const Cam& c
           if (vmin.x <= un && vmin.y <= vn && un <= vmax.x && vn <= vmax.y) out.push_back(I3{x, y, z});
         }
       }
-  if (o.p.cache_last_viewpoint) o.planes_cache.store(T_L_C, cam, out);
+  if (o.p.cache_last_viewpoint) cache.store(T_L_C, cam, out);
   return out;
 }
 
@@ -783,7 +803,8 @@ void integrate_features(Oracle& o, const uint16_t* img, int rows, int cols, cons
   o.last_n_upd = 0;
   const int C = o.C;
   const float trunc = o.p.appearance_truncation_distance_vox * o.voxel_size;
-  std::vector<I3> cand = blocks_in_view_planes(o, T_L_C, cam, o.p.max_integration_distance_m + trunc);
+  std::vector<I3> cand =
+      blocks_in_view_planes(o, o.planes_cache, T_L_C, cam, o.p.max_integration_distance_m + trunc);
   // reduceBlocksToThoseInTruncationBand
   std::vector<I3> band;
   for (const I3& b : cand) {
@@ -883,7 +904,113 @@ void integrate_features(Oracle& o, const uint16_t* img, int rows, int cols, cons
   o.last_n_upd += n_upd;
   o.cnt.feature_band_blocks += (int64_t)band.size();
   o.last_distinct_pixels = (int64_t)o.pixel_seen.size();
-  for (const I3& b : band) o.mesh_dirty.insert(b);  // mapper.cpp:462
+  for (const I3& b : band) {  // mapper.cpp:462
+    o.mesh_dirty.insert(b);
+    o.cmesh_dirty.insert(b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// N1: colour integration.  The same ProjectiveAppearanceIntegrator template instantiated for ColorLayer
+// (projective_appearance_integrator.cu:72-169; kernel projective_integrator_impl.cuh:156-214), with
+//   * interpolatePixels(Color) interpolation_2d_impl.h:50-60: per channel the fp32 bilinear formula on the
+//     uint8 values, then static_cast<uint8_t>(std::round(.));
+//   * weightedSum(uint8_t, float, uint8_t, float) projective_appearance_integrator.cu:277-284, called with
+//     __float2half(weight) (:301-302), i.e. both blend weights rounded to binary16 and widened back;
+//   * ColorVoxel::weight is a float, but the first-observation test is `__half2float(voxel_ptr->weight) == 0`
+//     (:328), i.e. the float weight rounded to binary16.
+// ------------------------------------------------------------------------------------------------
+inline uint8_t interp_color_channel(float x, float y, uint8_t c00, uint8_t c01, uint8_t c10, uint8_t c11) {
+  const float v = interp_float(x, y, (float)c00, (float)c01, (float)c10, (float)c11);
+  return (uint8_t)std::round(v);
+}
+inline uint8_t blend_color_channel(uint8_t a, float wa, uint8_t b, float wb) {
+  return (uint8_t)std::round((float)a * wa + (float)b * wb);
+}
+
+void integrate_color(Oracle& o, const uint8_t* img, int rows, int cols, const uint8_t* mask, const Pose& T_L_C,
+                     const Cam& cam) {
+  o.cnt.color_frames++;
+  o.last_color_list.clear();
+  const float trunc = o.p.appearance_truncation_distance_vox * o.voxel_size;
+  std::vector<I3> cand =
+      blocks_in_view_planes(o, o.color_planes_cache, T_L_C, cam, o.p.max_integration_distance_m + trunc);
+  std::vector<I3> band;
+  for (const I3& b : cand) {
+    auto it = o.tsdf.find(b);
+    if (it == o.tsdf.end()) continue;
+    bool in_band = false;
+    for (int l = 0; l < 512 && !in_band; ++l)
+      if (it->second.w[l] > 0.0f && std::fabs(it->second.d[l]) < trunc) in_band = true;
+    if (in_band) band.push_back(b);
+  }
+  o.last_color_list = band;
+  if (band.empty()) return;
+  for (const I3& b : band) {
+    if (!o.color.count(b)) {
+      o.color[b];
+      o.cnt.color_blocks_allocated++;
+    }
+  }
+  render_synthetic_depth(o, cam, T_L_C, trunc);
+  const int sub = rows / o.synth_rows;
+  const Pose T_C_L = inverse(T_L_C);
+  const float alpha = o.p.appearance_measurement_weight;
+  int64_t n_upd = 0;
+  for (const I3& b : band) {
+    ColorBlock& blk = o.color[b];
+    for (int x = 0; x < 8; ++x)
+      for (int y = 0; y < 8; ++y)
+        for (int z = 0; z < 8; ++z) {
+          float u, v, vd;
+          if (!project_voxel(o, b, I3{x, y, z}, cam, T_C_L, &u, &v, &vd)) continue;
+          const float ud = u / (float)sub, vdp = v / (float)sub;
+          float surface;
+          {
+            const float uc = ud - 0.5f, vc = vdp - 0.5f;
+            const int lx = (int)std::floor(uc), ly = (int)std::floor(vc);
+            if (lx < 0 || ly < 0 || (lx + 1) > (o.synth_cols - 1) || (ly + 1) > (o.synth_rows - 1)) continue;
+            const float f00 = o.synth[(size_t)ly * o.synth_cols + lx];
+            const float f01 = o.synth[(size_t)(ly + 1) * o.synth_cols + lx];
+            const float f10 = o.synth[(size_t)ly * o.synth_cols + lx + 1];
+            const float f11 = o.synth[(size_t)(ly + 1) * o.synth_cols + lx + 1];
+            surface = interp_float(uc - (float)lx, vc - (float)ly, f00, f01, f10, f11);
+          }
+          if (std::fabs(surface - vd) > trunc) continue;
+          const float uc = u - 0.5f, vc = v - 0.5f;
+          const int lx = (int)std::floor(uc), ly = (int)std::floor(vc);
+          if (lx < 0 || ly < 0 || (lx + 1) > (cols - 1) || (ly + 1) > (rows - 1)) continue;
+          const bool active = (mask == nullptr) || mask[(size_t)((int)v) * cols + (int)u];
+          if (!active) continue;
+          const float ox = uc - (float)lx, oy = vc - (float)ly;
+          const uint8_t* p00 = img + ((size_t)ly * cols + lx) * 3;
+          const uint8_t* p01 = img + ((size_t)(ly + 1) * cols + lx) * 3;
+          const uint8_t* p10 = img + ((size_t)ly * cols + lx + 1) * 3;
+          const uint8_t* p11 = img + ((size_t)(ly + 1) * cols + lx + 1) * 3;
+          uint8_t meas[3];
+          for (int c = 0; c < 3; ++c) meas[c] = interp_color_channel(ox, oy, p00[c], p01[c], p10[c], p11[c]);
+          const int l = vlin(x, y, z);
+          const float w_cur = blk.w[l];
+          if (h2f(f2h(w_cur)) == 0.0f) {
+            for (int c = 0; c < 3; ++c) blk.c[l][c] = meas[c];
+          } else {
+            float w1 = 1.0f - alpha, w2 = alpha;
+            const float tot = w1 + w2;
+            w1 /= tot;
+            w2 /= tot;
+            const float h1 = h2f(f2h(w1)), h2 = h2f(f2h(w2));
+            for (int c = 0; c < 3; ++c) blk.c[l][c] = blend_color_channel(blk.c[l][c], h1, meas[c], h2);
+          }
+          blk.w[l] = std::fmin(alpha + w_cur, o.p.max_weight);
+          n_upd++;
+        }
+  }
+  o.cnt.color_voxels_updated += n_upd;
+  o.cnt.color_band_blocks += (int64_t)band.size();
+  for (const I3& b : band) {  // mapper.cpp:448
+    o.mesh_dirty.insert(b);
+    o.cmesh_dirty.insert(b);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -891,7 +1018,10 @@ void integrate_features(Oracle& o, const uint16_t* img, int rows, int cols, cons
 // mapper.cpp:466-495,761-849
 // ------------------------------------------------------------------------------------------------
 void decay(Oracle& o) {
-  for (auto& kv : o.tsdf) o.mesh_dirty.insert(kv.first);
+  for (auto& kv : o.tsdf) {
+    o.mesh_dirty.insert(kv.first);
+    o.cmesh_dirty.insert(kv.first);
+  }
   const float thr = o.p.tsdf_decayed_weight_threshold;
   const float free_d = o.p.tsdf_decayed_free_distance_vox * o.voxel_size;
   std::vector<I3> removed;
@@ -913,8 +1043,11 @@ void decay(Oracle& o) {
   for (const I3& b : removed) {
     o.tsdf.erase(b);
     o.feat.erase(b);
+    o.color.erase(b);
     o.mesh.erase(b);
+    o.cmesh.erase(b);
     o.mesh_dirty.erase(b);
+    o.cmesh_dirty.erase(b);
     o.cnt.blocks_deallocated++;
   }
 }
@@ -1044,6 +1177,56 @@ void paint_block(Oracle& o, const I3& bi, MeshBlock* mb) {
   }
 }
 
+// AppearanceGetter<ColorVoxel> (mesh_integrator_appearance.cu:43-54): closest voxel's colour, Gray without a
+// colour block
+void paint_block_color(Oracle& o, const I3& bi, MeshBlock* mb) {
+  mb->colors.assign(mb->verts.size() * 3, 127);
+  auto it = o.color.find(bi);
+  if (it == o.color.end()) return;
+  const V3 origin{o.block_size * (float)bi.x, o.block_size * (float)bi.y, o.block_size * (float)bi.z};
+  const float vs = o.block_size / 8;
+  for (size_t i = 0; i < mb->verts.size(); ++i) {
+    const V3& v = mb->verts[i];
+    int ix = (int)((v.x - origin.x) / vs), iy = (int)((v.y - origin.y) / vs), iz = (int)((v.z - origin.z) / vs);
+    ix = std::max(std::min(ix, 7), 0);
+    iy = std::max(std::min(iy, 7), 0);
+    iz = std::max(std::min(iz, 7), 0);
+    std::memcpy(mb->colors.data() + i * 3, it->second.c[vlin(ix, iy, iz)], 3);
+  }
+}
+
+// Mapper::updateColorMesh (mapper.cpp:616-619): the same updateMeshTemplate over the colour mesh layer and
+// the colour "to update" set.
+void update_color_mesh(Oracle& o) {
+  std::vector<I3> blocks;
+  for (const I3& b : o.cmesh_dirty)
+    if (o.tsdf.count(b)) blocks.push_back(b);
+  const float cutoff = o.p.mesh_cutoff_distance_vox * o.voxel_size;
+  for (const I3& b : blocks) {
+    auto mit = o.cmesh.find(b);
+    if (mit != o.cmesh.end()) {
+      mit->second.verts.clear();
+      mit->second.tris.clear();
+      mit->second.colors.clear();
+    }
+    const TsdfBlock& tb = o.tsdf[b];
+    bool meshable = false;
+    for (int l = 0; l < 512 && !meshable; ++l)
+      if (std::fabs(tb.d[l]) <= cutoff && tb.w[l] >= o.p.mesh_min_weight) meshable = true;
+    if (!meshable) continue;
+    MeshBlock mb;
+    mesh_block(o, b, &mb);
+    if (mb.tris.empty()) continue;
+    o.cmesh[b] = mb;
+  }
+  for (const I3& b : blocks) {
+    auto mit = o.cmesh.find(b);
+    if (mit == o.cmesh.end()) continue;
+    paint_block_color(o, b, &mit->second);
+  }
+  o.cmesh_dirty.clear();
+}
+
 void update_feature_mesh(Oracle& o) {
   // getIndicesInLayer: only blocks still allocated in the TSDF layer
   std::vector<I3> blocks;
@@ -1158,14 +1341,57 @@ void orc_integrate_features(void* h, const uint16_t* feat, int H, int W, const u
                             float fx, float fy, float cx, float cy) {
   integrate_features(*(Oracle*)h, feat, H, W, mask, pose_from_row_major(T), make_cam(fx, fy, cx, cy, H, W));
 }
+void orc_integrate_color(void* h, const uint8_t* rgb, int H, int W, const uint8_t* mask, const float* T, float fx,
+                         float fy, float cx, float cy) {
+  integrate_color(*(Oracle*)h, rgb, H, W, mask, pose_from_row_major(T), make_cam(fx, fy, cx, cy, H, W));
+}
 void orc_decay(void* h) { decay(*(Oracle*)h); }
 void orc_clear(void* h) {  // py_mapper.cu:286-306 -- layers only; caches and tracker survive
   Oracle& o = *(Oracle*)h;
   o.tsdf.clear();
   o.feat.clear();
+  o.color.clear();
   o.mesh.clear();
+  o.cmesh.clear();
 }
 void orc_update_feature_mesh(void* h) { update_feature_mesh(*(Oracle*)h); }
+void orc_update_color_mesh(void* h) { update_color_mesh(*(Oracle*)h); }
+void orc_color_mesh_sizes(void* h, int64_t* n_verts, int64_t* n_tri_idx) {
+  Oracle& o = *(Oracle*)h;
+  int64_t nv = 0, nt = 0;
+  for (auto& kv : o.cmesh) {
+    nv += (int64_t)kv.second.verts.size();
+    nt += (int64_t)kv.second.tris.size();
+  }
+  *n_verts = nv;
+  *n_tri_idx = nt;
+}
+void orc_color_mesh_copy(void* h, float* verts, uint8_t* colors, int32_t* tris) {
+  Oracle& o = *(Oracle*)h;
+  int64_t vo = 0, to = 0;
+  for (auto& kv : o.cmesh) {
+    const MeshBlock& mb = kv.second;
+    for (size_t i = 0; i < mb.verts.size(); ++i) {
+      verts[(vo + (int64_t)i) * 3 + 0] = mb.verts[i].x;
+      verts[(vo + (int64_t)i) * 3 + 1] = mb.verts[i].y;
+      verts[(vo + (int64_t)i) * 3 + 2] = mb.verts[i].z;
+    }
+    if (colors && !mb.colors.empty()) std::memcpy(colors + vo * 3, mb.colors.data(), mb.colors.size());
+    for (size_t i = 0; i < mb.tris.size(); ++i) tris[to + (int64_t)i] = mb.tris[i] + (int32_t)vo;
+    vo += (int64_t)mb.verts.size();
+    to += (int64_t)mb.tris.size();
+  }
+}
+// colour blocks in block-index order: out_rgb uint8[n*512*3], out_w float[n*512]
+void orc_get_all_color_blocks(void* h, uint8_t* out_rgb, float* out_w) {
+  Oracle& o = *(Oracle*)h;
+  for (auto& kv : o.color) {
+    std::memcpy(out_rgb, kv.second.c, 512 * 3);
+    std::memcpy(out_w, kv.second.w, 512 * 4);
+    out_rgb += 512 * 3;
+    out_w += 512;
+  }
+}
 
 void orc_mesh_sizes(void* h, int64_t* n_verts, int64_t* n_tri_idx) {
   Oracle& o = *(Oracle*)h;
@@ -1202,6 +1428,7 @@ void orc_mesh_copy(void* h, float* verts, uint16_t* feats, int32_t* tris, int32_
 
 int64_t orc_num_blocks(void* h, int layer) {
   Oracle& o = *(Oracle*)h;
+  if (layer == NVBX_LAYER_COLOR) return (int64_t)o.color.size();
   return layer == NVBX_LAYER_TSDF ? (int64_t)o.tsdf.size() : (int64_t)o.feat.size();
 }
 void orc_block_indices(void* h, int layer, int32_t* out) {
@@ -1209,6 +1436,13 @@ void orc_block_indices(void* h, int layer, int32_t* out) {
   int64_t i = 0;
   if (layer == NVBX_LAYER_TSDF) {
     for (auto& kv : o.tsdf) {
+      out[i * 3] = kv.first.x;
+      out[i * 3 + 1] = kv.first.y;
+      out[i * 3 + 2] = kv.first.z;
+      ++i;
+    }
+  } else if (layer == NVBX_LAYER_COLOR) {
+    for (auto& kv : o.color) {
       out[i * 3] = kv.first.x;
       out[i * 3 + 1] = kv.first.y;
       out[i * 3 + 2] = kv.first.z;
@@ -1270,7 +1504,10 @@ void orc_set_tsdf_block(void* h, int x, int y, int z, const float* in) {
 }
 void orc_mark_all_dirty(void* h) {
   Oracle& o = *(Oracle*)h;
-  for (auto& kv : o.tsdf) o.mesh_dirty.insert(kv.first);
+  for (auto& kv : o.tsdf) {
+    o.mesh_dirty.insert(kv.first);
+    o.cmesh_dirty.insert(kv.first);
+  }
 }
 // queryTSDFKernel / queryFeatureKernel, NT/cpp/src/sdf_query.cu:206-270
 void orc_query_tsdf(void* h, const float* xyz, int64_t n, float* out) {
@@ -1305,7 +1542,7 @@ int64_t orc_last_trace_steps(void* h) { return ((Oracle*)h)->last_trace_steps; }
 int64_t orc_last_trace_max_steps(void* h) { return ((Oracle*)h)->last_trace_max_steps; }
 int64_t orc_last_block_list(void* h, int which, int32_t* out, int64_t cap) {
   Oracle& o = *(Oracle*)h;
-  const std::vector<I3>& l = which == 0 ? o.last_tsdf_list : o.last_feat_list;
+  const std::vector<I3>& l = which == 0 ? o.last_tsdf_list : (which == 1 ? o.last_feat_list : o.last_color_list);
   if (out)
     for (int64_t i = 0; i < (int64_t)l.size() && i < cap; ++i) {
       out[3 * i] = l[i].x;

@@ -41,8 +41,13 @@ def lib() -> C.CDLL:
                  C.c_float]
         L.orc_integrate_depth.argtypes = frame
         L.orc_integrate_features.argtypes = frame
-        for n in ('orc_decay', 'orc_clear', 'orc_update_feature_mesh', 'orc_mark_all_dirty', 'orc_reset_counters'):
+        L.orc_integrate_color.argtypes = frame
+        for n in ('orc_decay', 'orc_clear', 'orc_update_feature_mesh', 'orc_update_color_mesh', 'orc_mark_all_dirty',
+                  'orc_reset_counters'):
             getattr(L, n).argtypes = [C.c_void_p]
+        L.orc_color_mesh_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.orc_color_mesh_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_get_all_color_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_mesh_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.orc_mesh_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_num_blocks.restype = C.c_int64
@@ -146,6 +151,15 @@ class OracleMapper:
         self.L.orc_integrate_features(self.h, _ptr(feat), feat.shape[0], feat.shape[1], _ptr(m),
                                       T.ctypes.data_as(C.POINTER(C.c_float)), K[0, 0], K[1, 1], K[0, 2], K[1, 2])
 
+    def add_color_frame(self, rgb, t_w_c, intrinsics, mask=None):
+        rgb = np.ascontiguousarray(rgb)
+        assert rgb.dtype == np.uint8 and rgb.shape[2] == 3
+        T = _f32(t_w_c).reshape(16)
+        K = _f32(intrinsics)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self.L.orc_integrate_color(self.h, _ptr(rgb), rgb.shape[0], rgb.shape[1], _ptr(m),
+                                   T.ctypes.data_as(C.POINTER(C.c_float)), K[0, 0], K[1, 1], K[0, 2], K[1, 2])
+
     def decay(self):
         self.L.orc_decay(self.h)
 
@@ -165,6 +179,26 @@ class OracleMapper:
         vb = np.zeros((nv.value, 3), np.int32) if with_block_index else None
         self.L.orc_mesh_copy(self.h, _ptr(verts), _ptr(feats), _ptr(tris), _ptr(vb))
         return (verts, feats, tris, vb) if with_block_index else (verts, feats, tris)
+
+    def update_color_mesh(self):
+        self.L.orc_update_color_mesh(self.h)
+
+    def get_color_mesh(self):
+        nv, nt = C.c_int64(), C.c_int64()
+        self.L.orc_color_mesh_sizes(self.h, C.byref(nv), C.byref(nt))
+        verts = np.zeros((nv.value, 3), np.float32)
+        cols = np.zeros((nv.value, 3), np.uint8)
+        tris = np.zeros((nt.value // 3, 3), np.int32)
+        self.L.orc_color_mesh_copy(self.h, _ptr(verts), _ptr(cols), _ptr(tris))
+        return verts, cols, tris
+
+    def all_color_blocks(self):
+        """(indices [N,3] sorted, rgb [N,8,8,8,3] u8, weight [N,8,8,8] f32)."""
+        idx = self.block_indices(2)
+        rgb = np.zeros((len(idx), 8, 8, 8, 3), np.uint8)
+        w = np.zeros((len(idx), 8, 8, 8), np.float32)
+        self.L.orc_get_all_color_blocks(self.h, _ptr(rgb), _ptr(w))
+        return idx, rgb, w
 
     # -- layers ---------------------------------------------------------------------------------
     def num_blocks(self, layer: int) -> int:

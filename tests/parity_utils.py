@@ -128,6 +128,12 @@ class Pair:
                                    None if mask is None else t.from_numpy(mask).to(self.dev))
         self.cpu.add_feature_frame(feat, T, K, mask)
 
+    def color(self, rgb, T, K, mask=None):
+        t = self.torch
+        self.gpu.add_color_frame(t.from_numpy(rgb).to(self.dev), t.from_numpy(T), t.from_numpy(K),
+                                 None if mask is None else t.from_numpy(mask).to(self.dev))
+        self.cpu.add_color_frame(rgb, T, K, mask)
+
     def decay(self):
         self.gpu.decay()
         self.cpu.decay()
@@ -184,6 +190,41 @@ class Pair:
             ulp = np.abs(ordered_half(g16).astype(np.int32) - ordered_half(c16).astype(np.int32))
             assert ulp.max() <= max_ulp, f'max fp16 ulp distance {ulp.max()} > {max_ulp}'
         return len(gi)
+
+    def check_color(self):
+        """Colour layer: block set, RGB bytes and float weights bit-exact."""
+        import torch
+        from nvblox_mindmap_b200.torch_interop import device_view
+        layer = self.gpu.color_layer_view(0)
+        gi, gd = gpu_blocks(layer)
+        ci, crgb, cw = self.cpu.all_color_blocks()
+        assert np.array_equal(gi, ci), f'colour block sets differ: gpu {len(gi)} vs oracle {len(ci)}'
+        if len(gi) == 0:
+            return 0
+        assert np.array_equal(gd, crgb), f'{int((gd != crgb).any(-1).sum())} colour voxels differ'
+        # the weights sit behind the RGB bytes of each 8-byte ColorVoxel: read them through the raw block view
+        for k, row in enumerate(gi):
+            blk = layer.get_block_at_index(torch.from_numpy(row))
+            raw = device_view(blk.data_ptr(), (8, 8, 8, 8), torch.uint8, self.gpu._device, owner=self.gpu).cpu().numpy()
+            w = raw[..., 4:8].copy().view(np.float32)[..., 0]
+            assert np.array_equal(w.view(np.uint32), cw[k].view(np.uint32)), f'colour weights differ in block {row}'
+            assert not raw[..., 3].any(), 'padding byte of a ColorVoxel is not zero'
+        return len(gi)
+
+    def check_color_mesh(self):
+        self.gpu.update_color_mesh(0)
+        self.cpu.update_color_mesh()
+        m = self.gpu.get_color_mesh(0)
+        gv, gc, gt = (m.vertices().cpu().numpy(), m.vertex_colors().cpu().numpy(), m.triangles().cpu().numpy())
+        cv, cc, ct = self.cpu.get_color_mesh()
+        assert gv.shape == cv.shape, f'vertex count: gpu {gv.shape} vs oracle {cv.shape}'
+        assert gt.shape == ct.shape, f'triangle count: gpu {gt.shape} vs oracle {ct.shape}'
+        # colours ride through canonical_mesh's 16-bit appearance slot
+        gr, gx = canonical_mesh(gv, gc.astype(np.uint16).view(np.float16), gt)
+        cr, cx = canonical_mesh(cv, cc.astype(np.uint16).view(np.float16), ct)
+        assert np.array_equal(gr, cr), 'colour mesh vertices / vertex colours differ'
+        assert np.array_equal(gx, cx), 'colour mesh triangles differ'
+        return len(gv)
 
     def check_mesh(self):
         self.gpu.update_feature_mesh(0)

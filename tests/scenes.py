@@ -104,6 +104,13 @@ def feature_frame(H: int, W: int, C: int, seed: int) -> np.ndarray:
     return rng.standard_normal((H, W, C), dtype=np.float32).astype(np.float16)
 
 
+def color_frame(H: int, W: int, seed: int) -> np.ndarray:
+    """Uniform random uint8 RGB image (every pixel differs from its neighbours, so the bilinear rounding and the
+    blend rounding of the colour path are exercised on every voxel)."""
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+
+
 def border_lower_half_mask(H: int, W: int, border_percent: int = 5) -> np.ndarray:
     """Mask variant of SURVEY 8(d): 5 % border and the lower half zero."""
     m = np.ones((H, W), np.uint8)

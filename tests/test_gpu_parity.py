@@ -225,3 +225,76 @@ def test_large_view_global_bitmap_and_hash_index():
     assert pair.check_features() > 0
     pair.decay()
     assert pair.check_mesh() > 0
+
+
+# ---- colour layer + colour mesh ------------------------------------------------------
+@pytest.mark.parametrize('alpha', [1.0, 0.3])
+def test_color_layer_and_mesh(alpha):
+    """mindmap's integrate_frame order (depth -> colour -> features, nvblox_mapping_helpers.py:207-261) on an
+    orbit with decay: colour blocks / bytes / weights, colour mesh and feature mesh all bit-exact; the feature
+    frame re-uses the colour frame's synthetic depth (same pose, same TSDF state)."""
+    mp, op = make_params(workspace=S.WS_CUBE_STACKING, alpha=alpha)
+    pair = Pair(0.02, 32, mp, op)
+    for i, T, K, depth, feat in orbit_frames(6, 96, 96, 32, S.S_TABLE):
+        if i:
+            pair.decay()
+        pair.depth(depth, T, K)
+        mask = S.border_lower_half_mask(96, 96) if i % 3 == 2 else None
+        pair.color(S.color_frame(96, 96, 2000 + i), T, K, mask=mask)
+        g, c = pair.last_block_list(2)
+        assert np.array_equal(g, c) and len(g) > 0
+        pair.features(feat, T, K, mask=mask)
+        gs, cs = pair.synthetic_depth()
+        assert np.array_equal(gs.view(np.uint32), cs.view(np.uint32))
+        assert pair.check_color() > 0
+        pair.check_features(max_ulp=0 if alpha != 1.0 else 1)
+        if i % 2:
+            assert pair.check_color_mesh() > 0
+            pair.check_mesh()
+    gc, cc = pair.gpu.counters(0), pair.cpu.counters()
+    for k in ('color_frames', 'color_band_blocks', 'color_voxels_updated', 'color_blocks_allocated',
+              'feature_voxels_updated'):
+        assert gc[k] == cc[k] and gc[k] > 0, (k, gc[k], cc[k])
+
+
+def test_color_static_camera_and_features_first():
+    """Static camera (every viewpoint cache hits), features BEFORE colour (the colour frame re-uses the synthetic
+    depth), a second colour frame after a TSDF change (must re-trace), decay until the colour blocks are freed."""
+    mp, op = make_params(workspace=S.WS_CUBE_STACKING, alpha=0.5, decay=0.5)
+    pair = Pair(0.02, 16, mp, op)
+    K = S.intrinsics(64, 64)
+    T = S.orbit_pose(3)
+    depth = S.render_depth(K, 64, 64, T, **S.S_TABLE)
+    for i in range(3):
+        pair.depth(depth, T, K)
+        pair.features(S.feature_frame(64, 64, 16, 50 + i), T, K)
+        pair.color(S.color_frame(64, 64, 60 + i), T, K)
+        assert pair.check_color() > 0
+        pair.check_features()
+        pair.check_color_mesh()
+    for _ in range(16):
+        pair.decay()
+    assert pair.check_tsdf() == 0
+    assert pair.check_color() == 0
+    assert pair.check_color_mesh() == 0
+    assert pair.gpu.color_layer_view(0).num_blocks() == 0
+
+
+def test_color_mesh_without_color_frames():
+    """A colour mesh of a map that never saw a colour frame is Gray (AppearanceGetter<ColorVoxel>::
+    getDefaultAppearance, mesh_integrator_appearance.cu:50-53); the two mesh layers update independently."""
+    mp, op = make_params(workspace=S.WS_CUBE_STACKING)
+    pair = Pair(0.02, 16, mp, op)
+    for i, T, K, depth, feat in orbit_frames(2, 64, 64, 16, S.S_SPHERE_SMALL):
+        pair.depth(depth, T, K)
+        pair.features(feat, T, K)
+    n = pair.check_color_mesh()
+    assert n > 0
+    cols = pair.gpu.get_color_mesh(0).vertex_colors()
+    assert bool((cols == 127).all())
+    assert pair.check_mesh() == n
+    # colour frame afterwards: only the colour mesh's dirty set makes the colour mesh pick the colours up
+    T, K = S.orbit_pose(1), S.intrinsics(64, 64)
+    pair.color(S.color_frame(64, 64, 5), T, K)
+    assert pair.check_color_mesh() == n
+    assert not bool((pair.gpu.get_color_mesh(0).vertex_colors() == 127).all())

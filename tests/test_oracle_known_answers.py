@@ -362,3 +362,112 @@ def test_fused_half_variant_spread_is_bounded():
     d = np.abs(ordered_half(res[0].view(np.uint16)).astype(np.int64) -
                ordered_half(res[1].view(np.uint16)).astype(np.int64))
     assert (d <= 1).mean() > 0.6
+
+
+# ---- colour path: test_color_integrator.cpp, test_mapper_masking.py:100-160 --------------------
+def _color_blocks(m):
+    _, rgb, w = m.all_color_blocks()
+    return rgb.reshape(-1, 3), w.reshape(-1)
+
+
+def test_color_solid_image_is_copied_exactly():    # IntegrateColorToGroundTruthDistanceField :225-296 (one view)
+    m, K, T = _sphere_fixture(8, alpha=0.8)
+    red = np.zeros((48, 64, 3), np.uint8)
+    red[..., 0] = 255
+    m.add_color_frame(red, T, K)
+    rgb, w = _color_blocks(m)
+    assert (w > 0).sum() > 0
+    assert np.all(rgb[w > 0] == [255, 0, 0])               # every observed voxel has exactly the image colour
+    assert np.all(rgb[w == 0] == 127)                      # untouched voxels stay Gray (blox.cu:32-54)
+    assert np.all(w[w > 0] == np.float32(0.8))             # WeightingFunction :510-580: weight == measurement weight
+    # every colour block has a TSDF block (:298-301)
+    tsdf_idx = {tuple(r) for r in m.block_indices(0)}
+    assert all(tuple(r) in tsdf_idx for r in m.block_indices(2))
+
+
+def test_color_exponential_filter_rounding():
+    """weightedSum(uint8_t ...) projective_appearance_integrator.cu:277-284 with binary16 blend weights (:301-302):
+    value_2 = round(200 * half(0.7) + 100 * half(0.3)), value_3 likewise from value_2."""
+    m, K, T = _sphere_fixture(8, alpha=0.3)
+    h1 = float(np.float32(np.float16(np.float32(0.7) / (np.float32(0.7) + np.float32(0.3)))))
+    h2 = float(np.float32(np.float16(np.float32(0.3) / (np.float32(0.7) + np.float32(0.3)))))
+    expect = None
+    for v in (200, 100, 31):
+        m.add_color_frame(np.full((48, 64, 3), v, np.uint8), T, K)
+        expect = v if expect is None else int(np.floor(np.float32(np.float32(expect) * np.float32(h1) +
+                                                                  np.float32(v) * np.float32(h2)) + 0.5))
+    rgb, w = _color_blocks(m)
+    assert (w > 0).sum() > 0
+    assert np.all(rgb[w > 0] == expect)
+    assert np.all(w[w > 0] == np.float32(np.float32(np.float32(0.3) + np.float32(0.3)) + np.float32(0.3)))
+
+
+def test_color_occlusion():    # OcclusionTesting :442-508: the sphere behind the first one is never painted
+    vs = np.float32(0.1)
+    bs = float(vs * 8)
+    trunc = float(np.float32(4) * vs)
+    p = O.default_params()
+    m = O.OracleMapper(float(vs), 8, p)
+    g = (np.arange(8, dtype=np.float32) + 0.5) * vs
+    c1, c2 = np.array([5.0, 0, 0]), np.array([10.0, 0, 0])
+    for bx in range(2, 16):
+        for by in range(-4, 4):
+            for bz in range(-4, 4):
+                o = np.array([bx, by, bz], np.float32) * np.float32(bs)
+                X, Y, Z = np.meshgrid(o[0] + g, o[1] + g, o[2] + g, indexing='ij')
+                d1 = np.sqrt((X - c1[0]) ** 2 + Y ** 2 + Z ** 2) - 2.0
+                d2 = np.sqrt((X - c2[0]) ** 2 + Y ** 2 + Z ** 2) - 2.0
+                d = np.clip(np.minimum(d1, d2), -trunc, trunc)
+                blk = np.zeros((8, 8, 8, 2), np.float32)
+                blk[..., 0], blk[..., 1] = d, 1.0
+                m.set_tsdf_block((bx, by, bz), blk)
+    T = np.eye(4, dtype=np.float32)       # camera z -> world +x (rotation by +90 deg about y)
+    T[:3, :3] = np.array([[0, 0, 1], [0, 1, 0], [-1, 0, 0]], np.float32)
+    K = np.array([[300, 0, 320], [0, 300, 240], [0, 0, 1]], np.float32)
+    red = np.zeros((480, 640, 3), np.uint8)
+    red[..., 0] = 255
+    m.add_color_frame(red, T, K)
+    idx, rgb, w = m.all_color_blocks()
+    centers = (idx[:, None, None, None, :].astype(np.float32) * 8 +
+               np.stack(np.meshgrid(np.arange(8), np.arange(8), np.arange(8), indexing='ij'), -1) + 0.5) * vs
+    r1 = np.linalg.norm(centers - c1, axis=-1)
+    r2 = np.linalg.norm(centers - c2, axis=-1)
+    front = (np.abs(r1 - 2.0) < 0.1) & (centers[..., 0] < 4.0)
+    assert (w[front] > 0).mean() > 0.2 and np.all(rgb[front & (w > 0)] == [255, 0, 0])
+    back = np.abs(r2 - 2.0) < 0.3
+    assert back.sum() > 0 and np.all(w[back] == 0.0)
+
+
+def test_color_masking_proportions():    # test_mapper_color_masking :132-160
+    ones = np.ones((480, 640), np.uint8)
+    half = ones.copy()
+    half[240:] = 0
+    red = np.zeros((480, 640, 3), np.uint8)
+    red[..., 0] = 255
+    props = {}
+    for name, mask in (('all', ones), ('none', np.zeros_like(ones)), ('half', half)):
+        m, K, T = _plane_mapper(None)
+        m.update_color_mesh()                               # map_plane_with_mask ends with update_color_mesh
+        m.add_color_frame(red, T, K, mask)
+        m.update_color_mesh()
+        v, c, t = m.get_color_mesh()
+        assert len(v) > 0 and len(t) > 0
+        props[name] = (c[:, 0] == 255).sum() / len(v)
+        if name == 'none':
+            assert np.all(c == 127)                         # Gray where nothing was painted
+    assert props['all'] > 0.85
+    assert props['none'] == 0.0
+    assert abs(props['half'] - 0.5) < 0.05
+
+
+def test_color_mesh_is_a_separate_layer():
+    """blocks_to_update_tracker.cpp:32-60: both mesh layers have their own dirty set; updating one leaves the other
+    stale, and both meshes share the geometry once both are updated."""
+    m, K, T = _plane_mapper(None)
+    m.update_feature_mesh()
+    v_f, _, _ = m.get_feature_mesh()
+    v_c, _, _ = m.get_color_mesh()
+    assert len(v_f) > 0 and len(v_c) == 0
+    m.update_color_mesh()
+    v_c, c, _ = m.get_color_mesh()
+    assert np.array_equal(v_c, v_f) and np.all(c == 127)
