@@ -204,6 +204,30 @@ int nvbx_update_color_mesh(nvbx_mapper* m, int map_id, void* stream);
 int nvbx_get_color_mesh(nvbx_mapper* m, int map_id, const void** vertices, const void** colors,
                         const void** triangles, int64_t* n_vertices, int64_t* n_triangles);
 
+/* ---- fused export post-processing -------------------------------------------------- */
+
+/* mindmap's get_vertices_and_features, mapping/helpers/nvblox_output_helpers.py:57-74, in one flag pass + one
+ * scatter pass on the device: keep the vertices strictly inside (aabb_min, aabb_max), drop the trailing
+ * `num_excess_features` channels, and (remove_zero_features != 0) drop the rows whose remaining channels are all
+ * == 0.  Order is preserved (boolean-mask indexing).  vertices (float[n*3]) / features (fp16[n*channels]) are
+ * device pointers; vertices == NULL selects the current feature mesh of `map_id` (n and channels are then
+ * ignored).  The result lives in a handle-owned arena (valid until the next nvbx_export_points on this map):
+ * out_vertices float[count*3], out_features fp16[count*(channels - num_excess_features)].  Returns the count
+ * (one stream synchronisation) or a negative error. */
+int64_t nvbx_export_points(nvbx_mapper* m, int map_id, const void* vertices, const void* features, int64_t n,
+                           int channels, const float* aabb_min, const float* aabb_max, int num_excess_features,
+                           int remove_zero_features, const void** out_vertices, const void** out_features,
+                           void* stream);
+
+/* mindmap's sample_to_n_vertices, data_loading/vertex_sampling.py:29-108, applied to the last
+ * nvbx_export_points result of `map_id` in one pass: output row i = exported row indices[i] for i < n_indices
+ * (indices: HOST int64, e.g. torch.randperm(count)[:n] drawn by the caller exactly as the reference draws it;
+ * NULL = identity), zero rows for n_indices <= i < n_out (pad_with_zeros :84-108).  out_vertices: device
+ * float[n_out*3]; out_features: device fp16 or (features_f32 != 0) float32 [n_out*C_keep] -- the float32 cast of
+ * isaaclab_nvblox_mapper.py:243-246 rides the same pass. */
+int nvbx_gather_points(nvbx_mapper* m, int map_id, const int64_t* indices, int64_t n_indices, int64_t n_out,
+                       void* out_vertices, void* out_features, int features_f32, void* stream);
+
 /* ---- layer views (PyVoxelBlockLayer, py_layer.cpp:24-47,99-198) ---------------------------------- */
 
 int64_t nvbx_num_blocks(nvbx_mapper* m, int map_id, int layer, void* stream);           /* numBlocks            */

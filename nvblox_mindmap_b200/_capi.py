@@ -18,7 +18,8 @@ API_SYMBOLS = [
     'nvbx_default_params', 'nvbx_create', 'nvbx_destroy', 'nvbx_num_maps', 'nvbx_feature_channels',
     'nvbx_get_params', 'nvbx_last_error', 'nvbx_integrate_depth', 'nvbx_integrate_features',
     'nvbx_integrate_color', 'nvbx_integrate_frame_host', 'nvbx_decay', 'nvbx_clear',
-    'nvbx_update_feature_mesh', 'nvbx_get_feature_mesh', 'nvbx_update_color_mesh', 'nvbx_get_color_mesh', 'nvbx_num_blocks', 'nvbx_num_allocated_blocks',
+    'nvbx_update_feature_mesh', 'nvbx_get_feature_mesh', 'nvbx_update_color_mesh', 'nvbx_get_color_mesh',
+    'nvbx_export_points', 'nvbx_gather_points', 'nvbx_num_blocks', 'nvbx_num_allocated_blocks',
     'nvbx_num_allocated_bytes', 'nvbx_voxel_size', 'nvbx_get_block_indices', 'nvbx_get_block_ptr',
     'nvbx_allocate_block', 'nvbx_query_tsdf', 'nvbx_query_features', 'nvbx_get_counters',
     'nvbx_reset_counters', 'nvbx_set_kernel_timing', 'nvbx_get_kernel_timing', 'nvbx_kernel_timing_report', 'nvbx_kernel_launch_count', 'nvbx_debug_last_block_list',
@@ -70,6 +71,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
             getattr(L, n).argtypes = [vp, C.c_int, vp]
         L.nvbx_get_feature_mesh.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i64p, i64p]
         L.nvbx_get_color_mesh.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), i64p, i64p]
+        L.nvbx_export_points.argtypes = [vp, C.c_int, vp, vp, C.c_int64, C.c_int, fp, fp, C.c_int, C.c_int,
+                                         C.POINTER(vp), C.POINTER(vp), vp]
+        L.nvbx_export_points.restype = C.c_int64
+        L.nvbx_gather_points.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int64, vp, vp, C.c_int, vp]
         for n in ('nvbx_num_blocks', 'nvbx_num_allocated_blocks', 'nvbx_num_allocated_bytes'):
             getattr(L, n).argtypes = [vp, C.c_int, C.c_int, vp]
             getattr(L, n).restype = C.c_int64

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "../../include/nvbx_c_api.h"
+#include "nvbx_export.cuh"
 #include "nvbx_mesh.cuh"
 
 using namespace nvbx;
@@ -224,6 +225,15 @@ struct Map {
   DevBuf<int> carena_t[2];
   int carena_cur = 0;
   long long cmesh_nv = 0, cmesh_nt = 0;
+  // fused export post-processing (N2)
+  DevBuf<uint8_t> exp_keep;
+  DevBuf<int> exp_tile_cnt;
+  DevBuf<long long> exp_tile_off, exp_idx;
+  DevBuf<float> exp_v;
+  DevBuf<__half> exp_f;
+  long long* d_exp_total = nullptr;
+  long long exp_count = 0;
+  int exp_C_keep = 0;
   // host staging for nvbx_integrate_frame_host
   DevBuf<float> st_depth;
   DevBuf<__half> st_feat;
@@ -514,6 +524,7 @@ int init_map(nvbx_mapper* m, Map& mp, float voxel_size, cudaStream_t stream) {
   mp.dev.color_slabs = mp.d_color_table;
   CUDA_TRY(cudaMalloc(&mp.d_tmp_int, sizeof(int)));
   CUDA_TRY(cudaMalloc(&mp.d_tmp_ptr, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&mp.d_exp_total, sizeof(long long)));
   CUDA_TRY(cudaMalloc(&mp.scratch_ray.d_count, sizeof(int)));
   CUDA_TRY(cudaMalloc(&mp.small_grid[0], 2 * kFusedBitmapWords * sizeof(unsigned)));
   CUDA_TRY(cudaMemsetAsync(mp.small_grid[0], 0, 2 * kFusedBitmapWords * sizeof(unsigned), stream));
@@ -579,6 +590,13 @@ void destroy_map(Map& mp) {
   mp.h_ctrl = nullptr;
   F(mp.d_tmp_int);
   F(mp.d_tmp_ptr);
+  F(mp.d_exp_total);
+  mp.exp_keep.release();
+  mp.exp_tile_cnt.release();
+  mp.exp_tile_off.release();
+  mp.exp_idx.release();
+  mp.exp_v.release();
+  mp.exp_f.release();
   mp.raycast_cache.release();
   mp.planes_cache.release();
   mp.color_planes_cache.release();
@@ -1369,6 +1387,100 @@ int nvbx_get_color_mesh(nvbx_mapper* m, int map_id, const void** vertices, const
   if (triangles) *triangles = mp.carena_t[mp.carena_cur].p;
   if (n_vertices) *n_vertices = mp.cmesh_nv;
   if (n_triangles) *n_triangles = mp.cmesh_nt / 3;
+  return NVBX_OK;
+}
+
+// ---- fused export post-processing (N2) -----------------------------------------------------------------
+int64_t nvbx_export_points(nvbx_mapper* m, int map_id, const void* vertices, const void* features, int64_t n,
+                           int channels, const float* aabb_min, const float* aabb_max, int num_excess_features,
+                           int remove_zero_features, const void** out_vertices, const void** out_features,
+                           void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (!aabb_min || !aabb_max) return fail(NVBX_ERR_INVALID_ARGUMENT, "null AABB");
+  Map& mp = *m->maps[map_id];
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (!vertices) {  // the map's current feature mesh
+    vertices = mp.arena_v[mp.arena_cur].p;
+    features = mp.arena_f[mp.arena_cur].p;
+    n = mp.mesh_nv;
+    channels = m->C;
+  }
+  if (n < 0 || channels <= 0 || num_excess_features < 0 || num_excess_features > channels || (n > 0 && !features))
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "bad point cloud (n %lld, channels %d, excess %d)", (long long)n, channels,
+                num_excess_features);
+  ExportParams p;
+  p.verts = (const float*)vertices;
+  p.feats = (const __half*)features;
+  p.n = n;
+  p.C = channels;
+  // features[..., :-num_excess] with num_excess == 0 keeps everything (nvblox_output_helpers.py:66-67)
+  p.C_keep = channels - num_excess_features;
+  for (int i = 0; i < 3; ++i) {
+    p.mn[i] = aabb_min[i];
+    p.mx[i] = aabb_max[i];
+  }
+  p.remove_zero = remove_zero_features ? 1 : 0;
+  p.vec_in = (channels % 8 == 0) && (((uintptr_t)features & 15) == 0);
+  p.vec_out = (p.C_keep % 8 == 0);
+  mp.exp_count = 0;
+  mp.exp_C_keep = p.C_keep;
+  if (out_vertices) *out_vertices = nullptr;
+  if (out_features) *out_features = nullptr;
+  if (n == 0) return 0;
+  const long long n_tiles = (n + kExportTile - 1) / kExportTile;
+  if ((rc = mp.exp_keep.ensure((size_t)n, stream))) return rc;
+  if ((rc = mp.exp_tile_cnt.ensure((size_t)n_tiles, stream))) return rc;
+  if ((rc = mp.exp_tile_off.ensure((size_t)n_tiles, stream))) return rc;
+  if ((rc = mp.exp_v.ensure((size_t)n * 3, stream))) return rc;
+  if ((rc = mp.exp_f.ensure((size_t)n * (size_t)std::max(1, p.C_keep), stream))) return rc;
+  const int grid = (int)std::min<long long>(n_tiles, persistent_grid(m, 8));
+  LAUNCH(k_export_flag, grid, 256, 0, stream, p, mp.exp_keep.p, mp.exp_tile_cnt.p, n_tiles);
+  LAUNCH(k_export_scan, 1, 1024, 0, stream, mp.exp_tile_cnt.p, mp.exp_tile_off.p, n_tiles, mp.d_exp_total);
+  LAUNCH(k_export_scatter, grid, 256, 0, stream, p, mp.exp_keep.p, mp.exp_tile_off.p, n_tiles, mp.exp_v.p,
+         mp.exp_f.p);
+  long long total = 0;
+  CUDA_TRY(cudaMemcpyAsync(&total, mp.d_exp_total, sizeof(total), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  mp.exp_count = total;
+  if (out_vertices) *out_vertices = mp.exp_v.p;
+  if (out_features) *out_features = mp.exp_f.p;
+  return total;
+}
+
+int nvbx_gather_points(nvbx_mapper* m, int map_id, const int64_t* indices, int64_t n_indices, int64_t n_out,
+                       void* out_vertices, void* out_features, int features_f32, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  Map& mp = *m->maps[map_id];
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (n_indices < 0 || n_out < n_indices || (n_out > 0 && (!out_vertices || !out_features)))
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "bad gather request (n_indices %lld, n_out %lld)", (long long)n_indices,
+                (long long)n_out);
+  if (!indices && n_indices > mp.exp_count)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "identity gather of %lld rows from %lld exported points",
+                (long long)n_indices, mp.exp_count);
+  if (n_out == 0) return NVBX_OK;
+  const long long* d_idx = nullptr;
+  if (indices && n_indices > 0) {
+    for (int64_t i = 0; i < n_indices; ++i)
+      if (indices[i] < 0 || indices[i] >= mp.exp_count)
+        return fail(NVBX_ERR_INVALID_ARGUMENT, "index %lld out of range [0, %lld)", (long long)indices[i], mp.exp_count);
+    if ((rc = mp.exp_idx.ensure((size_t)n_indices, stream))) return rc;
+    // pageable source: the copy is staged by the runtime before the call returns
+    CUDA_TRY(cudaMemcpyAsync(mp.exp_idx.p, indices, (size_t)n_indices * sizeof(long long), cudaMemcpyHostToDevice,
+                             stream));
+    d_idx = mp.exp_idx.p;
+  }
+  const int C_keep = mp.exp_C_keep;
+  const int vec = (C_keep % 8 == 0) && (((uintptr_t)out_features & 15) == 0) ? 1 : 0;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((n_out + 7) / 8, persistent_grid(m, 8)));
+  if (features_f32)
+    LAUNCH(k_export_gather<true>, grid, 256, 0, stream, mp.exp_v.p, mp.exp_f.p, C_keep, d_idx, (long long)n_indices,
+           (long long)n_out, (float*)out_vertices, out_features, vec);
+  else
+    LAUNCH(k_export_gather<false>, grid, 256, 0, stream, mp.exp_v.p, mp.exp_f.p, C_keep, d_idx, (long long)n_indices,
+           (long long)n_out, (float*)out_vertices, out_features, vec);
   return NVBX_OK;
 }
 

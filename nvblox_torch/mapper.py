@@ -227,6 +227,52 @@ class Mapper:
             'triangles': device_view(t.value, (nt.value, 3), torch.int32, d, owner=self),
         })
 
+    # -- fused export post-processing (ours) -------------------------------------------------
+    def export_points(self, mapper_id: int, aabb_min_m, aabb_max_m, num_excess_features: int = 0,
+                      remove_zero_features: bool = True, vertices: Optional[torch.Tensor] = None,
+                      features: Optional[torch.Tensor] = None):
+        """AABB filter + excess-channel strip + zero-row drop of the feature point cloud in one device pass
+        (mindmap/mapping/helpers/nvblox_output_helpers.py:57-74).  Works on the current feature mesh of
+        `mapper_id`, or on explicit (vertices [N,3] f32, features [N,C] f16) CUDA tensors.  Returns zero-copy views
+        (vertices [M,3] f32, features [M,C-excess] f16) valid until the next export on this mapper_id."""
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        lo = (C.c_float * 3)(*[float(v) for v in aabb_min_m])
+        hi = (C.c_float * 3)(*[float(v) for v in aabb_max_m])
+        ov, of = C.c_void_p(), C.c_void_p()
+        if vertices is None:
+            vp, fp_, n, ch = None, None, 0, self._feature_channels
+        else:
+            assert vertices.is_cuda and features.is_cuda and vertices.dtype == torch.float32 and \
+                features.dtype == torch.float16 and vertices.shape[0] == features.shape[0]
+            vertices, features = vertices.contiguous(), features.contiguous()
+            vp, fp_, n, ch = vertices.data_ptr(), features.data_ptr(), vertices.shape[0], features.shape[1]
+        count = _capi.check(self._lib.nvbx_export_points(
+            self._handle, mapper_id, vp, fp_, n, ch, lo, hi, int(num_excess_features), int(bool(remove_zero_features)),
+            C.byref(ov), C.byref(of), self._stream()))
+        keep = ch - int(num_excess_features)
+        d = self._device
+        return (device_view(ov.value, (count, 3), torch.float32, d, owner=self),
+                device_view(of.value, (count, keep), torch.float16, d, owner=self))
+
+    def gather_points(self, mapper_id: int, indices: Optional[torch.Tensor], n_out: int, channels: int,
+                      features_dtype: torch.dtype = torch.float16, n_rows: Optional[int] = None):
+        """Rows `indices` (CPU int64 tensor; None = the first n_rows rows) of the last export, zero-padded to n_out
+        rows, features optionally widened to float32 in the same pass (vertex_sampling.py:29-108)."""
+        assert features_dtype in (torch.float16, torch.float32)
+        dev = f'cuda:{self._device}'
+        out_v = torch.empty((n_out, 3), dtype=torch.float32, device=dev)
+        out_f = torch.empty((n_out, channels), dtype=features_dtype, device=dev)
+        if indices is not None:
+            indices = indices.to(torch.int64).contiguous()
+            assert indices.is_cpu
+            ip, n_idx = indices.data_ptr(), indices.shape[0]
+        else:
+            ip, n_idx = None, int(n_rows)
+        _capi.check(self._lib.nvbx_gather_points(self._handle, mapper_id, ip, n_idx, n_out, out_v.data_ptr(),
+                                                 out_f.data_ptr(), int(features_dtype == torch.float32),
+                                                 self._stream()))
+        return out_v, out_f
+
     # -- layer views ------------------------------------------------------------------------------------------
     def tsdf_layer_view(self, mapper_id: int = 0) -> TsdfLayer:
         assert 0 <= mapper_id < len(self._voxel_sizes)
