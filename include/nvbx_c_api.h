@@ -182,6 +182,11 @@ int nvbx_decay(nvbx_mapper* m, int map_id, void* stream);
 /* Mapper::clear, py_mapper.cu:286-306. */
 int nvbx_clear(nvbx_mapper* m, int map_id, void* stream);
 
+/* Mark every TSDF block "to update" for both mesh layers (update*Mesh(UpdateFullLayer::kYes), what
+ * Mapper::loadMap does after swapping in a loaded layer cake, mapper.cpp:884-900).  Used by load_from_file after
+ * the block payloads were written through the layer views. */
+int nvbx_mark_all_dirty(nvbx_mapper* m, int map_id, void* stream);
+
 /* ---- surface extraction ------------------------------------------------------------------------- */
 
 /* Mapper::updateFeatureMesh, py_mapper.cu:196-204 -> Mapper::updateMeshTemplate mapper.cpp:580-614

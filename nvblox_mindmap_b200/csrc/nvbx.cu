@@ -187,7 +187,9 @@ struct Map {
   bool color_enabled = false;  // colour slabs exist (allocated by the first colour frame / colour block request)
   Ctrl* d_ctrl = nullptr;
   Ctrl* h_ctrl = nullptr;  // pinned mirror
-  ViewCache raycast_cache, planes_cache, color_planes_cache;  // one ViewCalculator (and cache) per integrator
+  // the TSDF, colour and feature integrators of one Mapper share one raycasting and one planes viewpoint cache
+  // (shareViewpointCaches, mapper.cpp:56-58)
+  ViewCache raycast_cache, planes_cache;
   CacheEntry scratch_ray, scratch_planes;  // used when the cache is disabled
   DevBuf<unsigned> grid;   // view bitmap; all-zero between frames (k_view_compact_alloc cleans it)
   bool grid_dirty = false;  // a frame failed between marking and compaction
@@ -599,7 +601,6 @@ void destroy_map(Map& mp) {
   mp.exp_f.release();
   mp.raycast_cache.release();
   mp.planes_cache.release();
-  mp.color_planes_cache.release();
   mp.scratch_ray.idx.release();
   mp.scratch_planes.idx.release();
   F(mp.scratch_ray.d_count);
@@ -1167,7 +1168,7 @@ int nvbx_integrate_color(nvbx_mapper* m, int map_id, const void* rgb, int height
   mp.have_cband_list = false;
   const int parity = mp.color_parity;
   AppearancePrep prep;
-  if ((rc = appearance_prepare(m, mp, mp.color_planes_cache, height, width, T_L_C_rm, fx, fy, cx, cy, parity, stream,
+  if ((rc = appearance_prepare(m, mp, mp.planes_cache, height, width, T_L_C_rm, fx, fy, cx, cy, parity, stream,
                                &prep)))
     return rc;
   if (prep.empty) return NVBX_OK;
@@ -1289,6 +1290,15 @@ int nvbx_clear(nvbx_mapper* m, int map_id, void* stream_v) {
   mp.cmesh_nt = 0;
   // NOTE: the viewpoint caches and the to-update tracker survive, as in the reference
   // (py_mapper.cu:286-306 clears the layers only).
+  return NVBX_OK;
+}
+
+int nvbx_mark_all_dirty(nvbx_mapper* m, int map_id, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  Map& mp = *m->maps[map_id];
+  ++mp.tsdf_version;  // called after block payloads were written through layer views (load_from_file)
+  LAUNCH(k_mark_all_dirty, persistent_grid(m, 4), 256, 0, (cudaStream_t)stream_v, mp.dev);
   return NVBX_OK;
 }
 

@@ -1121,6 +1121,15 @@ __global__ void __launch_bounds__(256) k_hash_reinsert(MapDev m, int force) {
 __global__ void k_hash_rebuild_done(MapDev m) {
   pdl_prologue(); m.ctrl->rebuild = 0; }
 
+// Every TSDF block "to update" for every mesh layer: update*Mesh(UpdateFullLayer::kYes), as Mapper::loadMap does
+// after swapping the layer cake (mapper.cpp:884-900).
+__global__ void __launch_bounds__(256) k_mark_all_dirty(MapDev m) {
+  pdl_prologue();
+  const int n = m.ctrl->slot_high;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
+    if (m.blk_layers[s] & kLayerTsdfBit) m.blk_dirty[s] = kDirtyAll;
+}
+
 // Mapper::clear (py_mapper.cu:286-306): drop every block of every layer.
 __global__ void __launch_bounds__(256) k_clear_all(MapDev m) {
   pdl_prologue();

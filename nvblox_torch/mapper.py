@@ -287,10 +287,16 @@ class Mapper:
         return ColorLayer(voxel_size_m=self._voxel_sizes[mapper_id], c_layer=(self, mapper_id))
 
     def save_map(self, map_fname: str, mapper_id: int) -> None:
-        raise NotImplementedError('.nvblx serialisation: SURVEY.md 8(f) N3 (next)')
+        """Write the map's TSDF / colour / feature layers as an nvblox `.nvblx` layer cake (sqlite)."""
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        from nvblox_mindmap_b200 import disk_helpers
+        disk_helpers.save_map(self, map_fname, mapper_id)
 
     def load_from_file(self, filename: str, mapper_id: int) -> None:
-        raise NotImplementedError('.nvblx serialisation: SURVEY.md 8(f) N3 (next)')
+        """Replace the map by the layers of a `.nvblx` file and re-mesh it (reference mapper.py:271-279)."""
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        from nvblox_mindmap_b200 import disk_helpers
+        return disk_helpers.load_map(self, filename, mapper_id)
 
     def num_mappers(self) -> int:
         return int(self._lib.nvbx_num_maps(self._handle))

@@ -471,8 +471,10 @@ struct Oracle {
   std::map<I3, MeshBlock> cmesh;   // MeshBlockLayer<Color> -- a separate layer with its own geometry
   std::set<I3> mesh_dirty;   // BlocksToUpdateTracker::feature_mesh_blocks_to_update_
   std::set<I3> cmesh_dirty;  // BlocksToUpdateTracker::color_mesh_blocks_to_update_
-  // every integrator owns a ViewCalculator and with it a viewpoint cache (projective_integrator.h)
-  ViewCache raycast_cache, planes_cache, color_planes_cache;
+  // Mapper::Mapper makes its TSDF, colour and feature integrators SHARE one raycasting and one planes viewpoint
+  // cache (shareViewpointCaches, mapper.cpp:56-58, mapper_common_impl.h:20-34): a colour frame and a feature frame
+  // at (nearly) the same pose see each other's cached block list.
+  ViewCache raycast_cache, planes_cache;
   std::vector<I3> last_tsdf_list, last_feat_list, last_color_list;
   std::vector<float> synth;
   int synth_rows = 0, synth_cols = 0;
@@ -934,7 +936,7 @@ void integrate_color(Oracle& o, const uint8_t* img, int rows, int cols, const ui
   o.last_color_list.clear();
   const float trunc = o.p.appearance_truncation_distance_vox * o.voxel_size;
   std::vector<I3> cand =
-      blocks_in_view_planes(o, o.color_planes_cache, T_L_C, cam, o.p.max_integration_distance_m + trunc);
+      blocks_in_view_planes(o, o.planes_cache, T_L_C, cam, o.p.max_integration_distance_m + trunc);
   std::vector<I3> band;
   for (const I3& b : cand) {
     auto it = o.tsdf.find(b);

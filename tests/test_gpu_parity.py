@@ -298,3 +298,29 @@ def test_color_mesh_without_color_frames():
     pair.color(S.color_frame(64, 64, 5), T, K)
     assert pair.check_color_mesh() == n
     assert not bool((pair.gpu.get_color_mesh(0).vertex_colors() == 127).all())
+
+
+def test_color_and_feature_share_the_planes_viewpoint_cache():
+    """shareViewpointCaches (mapper.cpp:56-58): the colour and the feature integrator of a Mapper use ONE planes
+    cache, so a feature frame 0.5 mm away from the preceding colour frame re-uses the colour frame's block list
+    (and vice versa).  Large camera steps in between make sure a stale list would be visible."""
+    mp, op = make_params(workspace=S.WS_CUBE_STACKING, alpha=0.5)
+    pair = Pair(0.02, 16, mp, op)
+    K = S.intrinsics(64, 64)
+    for i in range(4):
+        T = S.orbit_pose(5 * i, 64)
+        depth = S.render_depth(K, 64, 64, T, **S.S_TABLE)
+        pair.depth(depth, T, K)
+        T2 = T.copy()
+        T2[0, 3] += np.float32(0.0005)                       # within the 1 mm / 0.1 deg cache tolerance
+        if i % 2:
+            pair.color(S.color_frame(64, 64, 70 + i), T, K)
+            pair.features(S.feature_frame(64, 64, 16, 80 + i), T2, K)
+        else:
+            pair.features(S.feature_frame(64, 64, 16, 80 + i), T, K)
+            pair.color(S.color_frame(64, 64, 70 + i), T2, K)
+        for which in (1, 2):
+            g, c = pair.last_block_list(which)
+            assert np.array_equal(g, c) and len(g) > 0
+        assert pair.check_color() > 0
+        assert pair.check_features() > 0
