@@ -176,6 +176,45 @@ int nvbx_integrate_frame_host(nvbx_mapper* m, int map_id, const float* depth_hos
                               const uint8_t* feature_mask_host, const float* T_L_C, float fx, float fy,
                               float cx, float cy, void* stream);
 
+/* ---- the feature extractor's up-sampling fused into the integration ----------------
+ * Replaces, for one frame, mindmap's
+ *   FeatureExtractor.compute(): scale_image(features_bchw, (H, W)) -> rearrange -> zero-pad -> .to(float16)
+ *   (mindmap/image_processing/feature_extraction.py:110-129,170-211, nvblox_mapping_helpers.py:255-261)
+ * followed by Mapper::integrateFeatures.  `lowres` is the backbone's patch-feature map (e.g. RADIO 32x32x768):
+ *   dtype  NVBX_LOWRES_F32 / _F16 / _BF16 (the dtype torch.nn.functional.interpolate would have run in);
+ *   layout NVBX_LOWRES_CHW (a contiguous [1,c,h,w] tensor) or NVBX_LOWRES_HWC (a channels-last one, which is
+ *          what RADIO / DINOv2's permuted view is: feature_extraction.py:328-330);
+ *   kernel NVBX_UPSAMPLE_TORCH_NCHW or NVBX_UPSAMPLE_TORCH_NHWC: which of PyTorch's two CUDA kernels the
+ *          chained path would have selected (they contract multiply-adds differently for fp32; see
+ *          csrc/nvbx_upsample.cuh).  torch picks NHWC iff the input is channels-last and has >= 16 channels.
+ * low_c <= nvbx_feature_channels(); missing channels are zero.  The stored features are bit-identical to the
+ * chained path's; the [H, W, C] frame is never materialised.  mask (device uint8[H*W] or NULL) and the camera
+ * refer to the up-sampled H x W frame. */
+#define NVBX_LOWRES_F32 0
+#define NVBX_LOWRES_F16 1
+#define NVBX_LOWRES_BF16 2
+#define NVBX_LOWRES_CHW 0
+#define NVBX_LOWRES_HWC 1
+#define NVBX_UPSAMPLE_TORCH_NCHW 0
+#define NVBX_UPSAMPLE_TORCH_NHWC 1
+int nvbx_integrate_features_lowres(nvbx_mapper* m, int map_id, const void* lowres, int low_h, int low_w,
+                                   int low_c, int dtype, int layout, int kernel, int height, int width,
+                                   const void* mask, const float* T_L_C, float fx, float fy, float cx,
+                                   float cy, void* stream);
+
+/* The [H, W, C] fp16 frame the chained path would have produced, written to `out` (device, 16-byte aligned):
+ * parity checks and visualisation only. */
+int nvbx_upsample_features(nvbx_mapper* m, int map_id, const void* lowres, int low_h, int low_w, int low_c,
+                           int dtype, int layout, int kernel, int height, int width, void* out, void* stream);
+
+/* integrate_depth + integrate_features_lowres from HOST buffers: depth (H*W floats) and the low-res feature
+ * map (low_h*low_w*low_c elements) are the only per-frame uploads -- 2.5 MB instead of 385 MB at 512^2 x 768. */
+int nvbx_integrate_frame_host_lowres(nvbx_mapper* m, int map_id, const float* depth_host,
+                                     const void* lowres_host, int low_h, int low_w, int low_c, int dtype,
+                                     int layout, int kernel, int height, int width,
+                                     const uint8_t* depth_mask_host, const uint8_t* feature_mask_host,
+                                     const float* T_L_C, float fx, float fy, float cx, float cy, void* stream);
+
 /* Mapper::decayTsdf, py_mapper.cu:264-273 -> mapper.cpp:466-495.  map_id -1 = all maps. */
 int nvbx_decay(nvbx_mapper* m, int map_id, void* stream);
 

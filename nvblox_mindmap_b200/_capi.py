@@ -17,7 +17,8 @@ _lib = None
 API_SYMBOLS = [
     'nvbx_default_params', 'nvbx_create', 'nvbx_destroy', 'nvbx_num_maps', 'nvbx_feature_channels',
     'nvbx_get_params', 'nvbx_last_error', 'nvbx_integrate_depth', 'nvbx_integrate_features',
-    'nvbx_integrate_color', 'nvbx_integrate_frame_host', 'nvbx_decay', 'nvbx_clear', 'nvbx_mark_all_dirty',
+    'nvbx_integrate_color', 'nvbx_integrate_frame_host', 'nvbx_integrate_features_lowres',
+    'nvbx_upsample_features', 'nvbx_integrate_frame_host_lowres', 'nvbx_decay', 'nvbx_clear', 'nvbx_mark_all_dirty',
     'nvbx_update_feature_mesh', 'nvbx_get_feature_mesh', 'nvbx_update_color_mesh', 'nvbx_get_color_mesh',
     'nvbx_export_points', 'nvbx_gather_points', 'nvbx_num_blocks', 'nvbx_num_allocated_blocks',
     'nvbx_num_allocated_bytes', 'nvbx_voxel_size', 'nvbx_get_block_indices', 'nvbx_get_block_ptr',
@@ -67,6 +68,10 @@ def load(build_if_missing: bool = True) -> C.CDLL:
                                               C.c_float, C.c_float, C.c_float, vp]
         L.nvbx_integrate_frame_host.argtypes = [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp,
                                                 C.c_float, C.c_float, C.c_float, C.c_float, vp]
+        L.nvbx_integrate_features_lowres.argtypes = [vp, C.c_int, vp] + [C.c_int] * 8 + [vp, vp] + [C.c_float] * 4 + [vp]
+        L.nvbx_upsample_features.argtypes = [vp, C.c_int, vp] + [C.c_int] * 8 + [vp, vp]
+        L.nvbx_integrate_frame_host_lowres.argtypes = [vp, C.c_int, vp, vp] + [C.c_int] * 8 + [vp, vp, vp] + \
+            [C.c_float] * 4 + [vp]
         for n in ('nvbx_decay', 'nvbx_clear', 'nvbx_mark_all_dirty', 'nvbx_update_feature_mesh',
                   'nvbx_update_color_mesh'):
             getattr(L, n).argtypes = [vp, C.c_int, vp]

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(LIB_DIR, 'libnvbx.so')
 # tuning aid (NVBX_PROFILE=1): same sources with -DNVBX_PROFILE_COUNTERS (in-kernel step / cycle counters)
 PROFILE_LIB_PATH = os.path.join(LIB_DIR, 'libnvbx_prof.so')
 SOURCES = ['nvbx.cu']
-DEPS = ['nvbx.cu', 'nvbx_kernels.cuh', 'nvbx_mesh.cuh', 'nvbx_export.cuh', 'nvbx_map.cuh', 'nvbx_math.cuh', 'mc_tables.h',
+DEPS = ['nvbx.cu', 'nvbx_kernels.cuh', 'nvbx_upsample.cuh', 'nvbx_mesh.cuh', 'nvbx_export.cuh', 'nvbx_map.cuh', 'nvbx_math.cuh', 'mc_tables.h',
         os.path.join('..', '..', 'include', 'nvbx_c_api.h')]
 
 NVCC_FLAGS = [

@@ -23,6 +23,7 @@
 #include "../../include/nvbx_c_api.h"
 #include "nvbx_export.cuh"
 #include "nvbx_mesh.cuh"
+#include "nvbx_upsample.cuh"
 
 using namespace nvbx;
 
@@ -240,6 +241,8 @@ struct Map {
   DevBuf<float> st_depth;
   DevBuf<__half> st_feat;
   DevBuf<uint8_t> st_mask_d, st_mask_f;
+  DevBuf<float> st_low;      // N4: [lh][lw][C] fp32 staged low-res feature map
+  DevBuf<uint8_t> st_low_in;  // N4: raw upload of the host low-res map
   // misc single-value device scratch
   int* d_tmp_int = nullptr;
   unsigned long long* d_tmp_ptr = nullptr;
@@ -629,6 +632,8 @@ void destroy_map(Map& mp) {
   mp.st_feat.release();
   mp.st_mask_d.release();
   mp.st_mask_f.release();
+  mp.st_low.release();
+  mp.st_low_in.release();
   mp.idx_out.release();
 }
 
@@ -682,6 +687,27 @@ int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, 
       break;
     default:
       LAUNCH((k_feature_gather<CH, 1, 4>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
+  }
+  return timing_end(m, 0, stream);
+}
+
+template <int CH>
+int launch_gather_up(nvbx_mapper* m, Map& mp, const FeatFrame& ff, const UpFrame& uf, int mode, int last_chunk,
+                     cudaStream_t stream) {
+  int rc;
+  if ((rc = timing_begin(m, 0, stream))) return rc;
+  switch (mode) {  // <CH, torch kernel flavour, resident CTAs per SM>
+    case 1:
+      LAUNCH((k_feature_gather_up<CH, 1, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items.p, ff, uf,
+             last_chunk);
+      break;
+    case 2:
+      LAUNCH((k_feature_gather_up<CH, 2, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items.p, ff, uf,
+             last_chunk);
+      break;
+    default:
+      LAUNCH((k_feature_gather_up<CH, 0, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items.p, ff, uf,
+             last_chunk);
   }
   return timing_end(m, 0, stream);
 }
@@ -1082,18 +1108,46 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
 
 }  // namespace
 
-extern "C" {
+namespace {
 
-int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, int height, int width, int channels,
-                            const void* mask, const float* T_L_C_rm, float fx, float fy, float cx, float cy,
-                            void* stream_v) {
-  int rc = check_map(m, map_id);
-  if (rc) return rc;
-  if (!features || !T_L_C_rm || height <= 0 || width <= 0) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad feature frame");
-  if (channels != m->C)
-    return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame has %d channels, the map was created with %d", channels,
-                m->C);
-  if (((uintptr_t)features) & 15) return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame must be 16-byte aligned");
+// Stage a low-res backbone feature map (device pointer) as [lh][lw][C] fp32 and describe it (N4).  A dense HWC
+// fp32 map that already has C channels is used in place.
+int prepare_lowres(nvbx_mapper* m, Map& mp, const void* lowres, int low_h, int low_w, int low_c, int dtype, int layout,
+                   int kernel, int height, int width, cudaStream_t stream, UpFrame* uf, int* mode) {
+  if (!lowres || low_h <= 0 || low_w <= 0 || low_c <= 0 || height <= 0 || width <= 0)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "bad low-res feature map");
+  if (low_c > m->C)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "low-res feature map has %d channels, the map stores %d", low_c, m->C);
+  if (dtype < NVBX_LOWRES_F32 || dtype > NVBX_LOWRES_BF16 || (layout != NVBX_LOWRES_CHW && layout != NVBX_LOWRES_HWC) ||
+      (kernel != NVBX_UPSAMPLE_TORCH_NCHW && kernel != NVBX_UPSAMPLE_TORCH_NHWC))
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "bad low-res dtype / layout / kernel selector");
+  if (low_h == height && low_w == width)  // torch copies instead of interpolating (UpSampleBilinear2d.cu)
+    return fail(NVBX_ERR_UNSUPPORTED, "low-res map already has the frame size: use nvbx_integrate_features");
+  int rc;
+  if (dtype == NVBX_LOWRES_F32 && layout == NVBX_LOWRES_HWC && low_c == m->C && !(((uintptr_t)lowres) & 15)) {
+    uf->low = (const float*)lowres;
+  } else {
+    const size_t n = (size_t)low_h * low_w * m->C;
+    if ((rc = mp.st_low.ensure(n, stream))) return rc;
+    const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)persistent_grid(m, 8));
+    LAUNCH(k_lowres_stage, grid, 256, 0, stream, lowres, dtype, layout == NVBX_LOWRES_CHW ? 1 : 0, low_h, low_w, low_c,
+           m->C, mp.st_low.p);
+    uf->low = mp.st_low.p;
+  }
+  uf->lh = low_h;
+  uf->lw = low_w;
+  uf->rh = (float)low_h / (float)height;  // area_pixel_compute_scale, align_corners = false, no scale_factor
+  uf->rw = (float)low_w / (float)width;
+  // which multiply-add contraction the chained torch kernel has (csrc/nvbx_upsample.cuh)
+  *mode = dtype == NVBX_LOWRES_BF16 ? 2 : ((dtype == NVBX_LOWRES_F32 && kernel == NVBX_UPSAMPLE_TORCH_NHWC) ? 1 : 0);
+  return NVBX_OK;
+}
+
+// features != nullptr: the [H, W, C] fp16 frame (a8).  Otherwise `uf` / `up_mode` describe the low-res map (N4).
+int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, const UpFrame* uf, int up_mode,
+                            int height, int width, const void* mask, const float* T_L_C_rm, float fx, float fy,
+                            float cx, float cy, void* stream_v) {
+  int rc;
   const nvbx_params& p = m->params;
   cudaStream_t stream = (cudaStream_t)stream_v;
   Map& mp = *m->maps[map_id];
@@ -1141,19 +1195,82 @@ int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, in
     const int ggrid = persistent_grid(m, 2);  // full grid: new feature blocks are zero-filled by all CTAs
     LAUNCH(k_feature_geometry, ggrid, 512, 0, stream, mp.dev, mp.band_slots.p, mp.newfeat_slots.p, ff, mp.items.p,
            (int)begin, (int)end);
-    if (m->C % 256 == 0 && m->C / 256 == 3)
+    const int ch = (m->C % 256 == 0 && m->C / 256 >= 1 && m->C / 256 <= 4) ? m->C / 256 : 0;
+    if (uf) {
+      if (ch == 3)
+        rc = launch_gather_up<3>(m, mp, ff, *uf, up_mode, last, stream);
+      else if (ch == 4)
+        rc = launch_gather_up<4>(m, mp, ff, *uf, up_mode, last, stream);
+      else
+        rc = launch_gather_up<0>(m, mp, ff, *uf, up_mode, last, stream);
+    } else if (ch == 3)
       rc = launch_gather<3>(m, mp, ff, last, stream);
-    else if (m->C % 256 == 0 && m->C / 256 == 4)
+    else if (ch == 4)
       rc = launch_gather<4>(m, mp, ff, last, stream);
-    else if (m->C % 256 == 0 && m->C / 256 == 2)
+    else if (ch == 2)
       rc = launch_gather<2>(m, mp, ff, last, stream);
-    else if (m->C % 256 == 0 && m->C / 256 == 1)
+    else if (ch == 1)
       rc = launch_gather<1>(m, mp, ff, last, stream);
     else
       rc = launch_gather<0>(m, mp, ff, last, stream);
     if (rc) return rc;
   }
   mp.have_band_list = true;
+  return NVBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, int height, int width, int channels,
+                            const void* mask, const float* T_L_C_rm, float fx, float fy, float cx, float cy,
+                            void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (!features || !T_L_C_rm || height <= 0 || width <= 0) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad feature frame");
+  if (channels != m->C)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame has %d channels, the map was created with %d", channels,
+                m->C);
+  if (((uintptr_t)features) & 15) return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame must be 16-byte aligned");
+  return integrate_features_impl(m, map_id, features, nullptr, 0, height, width, mask, T_L_C_rm, fx, fy, cx, cy,
+                                 stream_v);
+}
+
+int nvbx_integrate_features_lowres(nvbx_mapper* m, int map_id, const void* lowres, int low_h, int low_w, int low_c,
+                                   int dtype, int layout, int kernel, int height, int width, const void* mask,
+                                   const float* T_L_C_rm, float fx, float fy, float cx, float cy, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (!T_L_C_rm) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad feature frame");
+  UpFrame uf;
+  int mode = 0;
+  if ((rc = prepare_lowres(m, *m->maps[map_id], lowres, low_h, low_w, low_c, dtype, layout, kernel, height, width,
+                           (cudaStream_t)stream_v, &uf, &mode)))
+    return rc;
+  return integrate_features_impl(m, map_id, nullptr, &uf, mode, height, width, mask, T_L_C_rm, fx, fy, cx, cy,
+                                 stream_v);
+}
+
+int nvbx_upsample_features(nvbx_mapper* m, int map_id, const void* lowres, int low_h, int low_w, int low_c, int dtype,
+                           int layout, int kernel, int height, int width, void* out, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (!out || (((uintptr_t)out) & 15)) return fail(NVBX_ERR_INVALID_ARGUMENT, "output frame must be 16-byte aligned");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  Map& mp = *m->maps[map_id];
+  UpFrame uf;
+  int mode = 0;
+  if ((rc = prepare_lowres(m, mp, lowres, low_h, low_w, low_c, dtype, layout, kernel, height, width, stream, &uf,
+                           &mode)))
+    return rc;
+  const int grid = persistent_grid(m, 8);
+  if (mode == 1)
+    LAUNCH(k_upsample_materialise<1>, grid, 256, 0, stream, uf, height, width, m->C, (__half*)out);
+  else if (mode == 2)
+    LAUNCH(k_upsample_materialise<2>, grid, 256, 0, stream, uf, height, width, m->C, (__half*)out);
+  else
+    LAUNCH(k_upsample_materialise<0>, grid, 256, 0, stream, uf, height, width, m->C, (__half*)out);
   return NVBX_OK;
 }
 
@@ -1232,6 +1349,40 @@ int nvbx_integrate_frame_host(nvbx_mapper* m, int map_id, const float* depth_hos
     return rc;
   return nvbx_integrate_features(m, map_id, mp.st_feat.p, height, width, channels, fm, T_L_C, fx, fy, cx, cy,
                                  stream_v);
+}
+
+int nvbx_integrate_frame_host_lowres(nvbx_mapper* m, int map_id, const float* depth_host, const void* lowres_host,
+                                     int low_h, int low_w, int low_c, int dtype, int layout, int kernel, int height,
+                                     int width, const uint8_t* depth_mask_host, const uint8_t* feature_mask_host,
+                                     const float* T_L_C, float fx, float fy, float cx, float cy, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  if (!depth_host || !lowres_host || low_h <= 0 || low_w <= 0 || low_c <= 0 || dtype < 0 || dtype > 2)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "bad host frame");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  Map& mp = *m->maps[map_id];
+  const size_t px = (size_t)height * width;
+  const size_t low_bytes = (size_t)low_h * low_w * low_c * (dtype == NVBX_LOWRES_F32 ? 4 : 2);
+  if ((rc = mp.st_depth.ensure(px, stream))) return rc;
+  if ((rc = mp.st_low_in.ensure(low_bytes, stream))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(mp.st_depth.p, depth_host, px * sizeof(float), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(mp.st_low_in.p, lowres_host, low_bytes, cudaMemcpyHostToDevice, stream));
+  const uint8_t* dm = nullptr;
+  const uint8_t* fm = nullptr;
+  if (depth_mask_host) {
+    if ((rc = mp.st_mask_d.ensure(px, stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(mp.st_mask_d.p, depth_mask_host, px, cudaMemcpyHostToDevice, stream));
+    dm = mp.st_mask_d.p;
+  }
+  if (feature_mask_host) {
+    if ((rc = mp.st_mask_f.ensure(px, stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(mp.st_mask_f.p, feature_mask_host, px, cudaMemcpyHostToDevice, stream));
+    fm = mp.st_mask_f.p;
+  }
+  if ((rc = nvbx_integrate_depth(m, map_id, mp.st_depth.p, height, width, dm, T_L_C, fx, fy, cx, cy, stream_v)))
+    return rc;
+  return nvbx_integrate_features_lowres(m, map_id, mp.st_low_in.p, low_h, low_w, low_c, dtype, layout, kernel, height,
+                                        width, fm, T_L_C, fx, fy, cx, cy, stream_v);
 }
 
 // ---- decay / clear -------------------------------------------------------------------------------

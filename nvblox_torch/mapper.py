@@ -51,6 +51,41 @@ def _fxfycxcy(intrinsics: torch.Tensor):
     return k[0], k[4], k[2], k[5]
 
 
+_LOWRES_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def _strides_like_channels_last(t: torch.Tensor) -> bool:
+    """c10's `is_strides_like_channels_last` for a 4-d tensor (what `suggest_memory_format()` consults)."""
+    sizes, strides = t.shape, t.stride()
+    lo = 0
+    for d in (1, 3, 2, 0):
+        if sizes[d] == 0 or strides[d] < lo:
+            return False
+        if d == 0 and lo == strides[1]:
+            return False
+        lo = strides[d]
+        if sizes[d] > 1:
+            lo *= sizes[d]
+    return True
+
+
+def lowres_descriptor(features_bchw: torch.Tensor):
+    """(tensor to keep alive, c, h, w, dtype code, layout code, torch-kernel code) of a backbone feature map
+    shaped [1, c, h, w] or [c, h, w], decided the way `F.interpolate(..., mode='bilinear')` decides: a
+    channels-last-strided input with >= 16 channels runs torch's NHWC kernel, everything else the NCHW one."""
+    x = features_bchw if features_bchw.ndim == 4 else features_bchw[None]
+    assert x.ndim == 4 and x.shape[0] == 1, 'expected a [1, c, h, w] (or [c, h, w]) feature map'
+    assert x.dtype in _LOWRES_DTYPES, f'unsupported low-res dtype {x.dtype}'
+    _, c, h, w = x.shape
+    nhwc = _strides_like_channels_last(x)
+    kernel = 1 if (nhwc and c >= 16) else 0
+    if nhwc and x.stride() == (h * w * c, 1, w * c, c):
+        layout = 1                         # dense HWC memory: crosses zero-copy
+    else:
+        x, layout = x.contiguous(), 0      # CHW
+    return x, c, h, w, _LOWRES_DTYPES[x.dtype], layout, kernel
+
+
 class Mapper:
     """Accumulates depth (+ feature) frames into voxel-block-hashed TSDF / feature maps on one GPU.
 
@@ -173,6 +208,59 @@ class Mapper:
         _capi.check(self._lib.nvbx_integrate_frame_host(
             self._handle, mapper_id, depth.data_ptr(), features.data_ptr(), depth.shape[0], depth.shape[1],
             features.shape[2], None if depth_mask is None else depth_mask.data_ptr(),
+            None if feature_mask is None else feature_mask.data_ptr(), _pose16(t_w_c), fx, fy, cx, cy,
+            self._stream()))
+
+    def add_feature_frame_lowres(self,
+                                 features_bchw: torch.Tensor,
+                                 output_size,
+                                 t_w_c: torch.Tensor,
+                                 intrinsics: torch.Tensor,
+                                 mask_frame: Optional[torch.Tensor] = None,
+                                 mapper_id: int = 0) -> None:
+        """(ours) Integrate the backbone's [1, c, h, w] CUDA feature map as if it had gone through
+        mindmap's `FeatureExtractor.compute()` tail -- `scale_image(features_bchw, output_size)`, HWC, zero-pad to
+        `constants.feature_array_num_elements()`, `.to(float16)` (feature_extraction.py:188-196,
+        nvblox_mapping_helpers.py:255-261) -- and then `add_feature_frame`.  The stored features are bit-identical;
+        the (H, W, C) frame is never materialised.  `mask_frame`, `intrinsics` refer to the `output_size` frame."""
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        assert features_bchw.is_cuda, 'Feature frame must be on GPU'
+        assert not t_w_c.is_cuda and not intrinsics.is_cuda
+        assert t_w_c.dtype == torch.float32 and intrinsics.dtype == torch.float32
+        H, W = int(output_size[0]), int(output_size[1])
+        x, c, h, w, dtype, layout, kernel = lowres_descriptor(features_bchw)
+        assert c <= self._feature_channels
+        mask_ptr = None
+        if mask_frame is not None:
+            assert mask_frame.is_cuda and mask_frame.dtype == torch.uint8 and tuple(mask_frame.shape) == (H, W)
+            mask_frame = mask_frame if mask_frame.is_contiguous() else mask_frame.contiguous()
+            mask_ptr = mask_frame.data_ptr()
+        fx, fy, cx, cy = _fxfycxcy(intrinsics)
+        _capi.check(self._lib.nvbx_integrate_features_lowres(
+            self._handle, mapper_id, x.data_ptr(), h, w, c, dtype, layout, kernel, H, W, mask_ptr, _pose16(t_w_c),
+            fx, fy, cx, cy, self._stream()))
+
+    def upsample_features(self, features_bchw: torch.Tensor, output_size, mapper_id: int = 0) -> torch.Tensor:
+        """(ours) The (H, W, C) float16 frame `add_feature_frame_lowres` integrates, materialised (parity checks,
+        visualisation)."""
+        H, W = int(output_size[0]), int(output_size[1])
+        x, c, h, w, dtype, layout, kernel = lowres_descriptor(features_bchw)
+        out = torch.empty((H, W, self._feature_channels), dtype=torch.float16, device=x.device)
+        _capi.check(self._lib.nvbx_upsample_features(
+            self._handle, mapper_id, x.data_ptr(), h, w, c, dtype, layout, kernel, H, W, out.data_ptr(),
+            self._stream()))
+        return out
+
+    def integrate_frame_from_host_lowres(self, depth, features_bchw, t_w_c, intrinsics, depth_mask=None,
+                                         feature_mask=None, mapper_id: int = 0) -> None:
+        """(ours) depth + low-res feature map from HOST (ideally pinned) tensors: 2.5 MB of H2D per 512^2 x 768 frame
+        instead of 385 MB."""
+        assert depth.dtype == torch.float32 and not depth.is_cuda and not features_bchw.is_cuda
+        x, c, h, w, dtype, layout, kernel = lowres_descriptor(features_bchw)
+        fx, fy, cx, cy = _fxfycxcy(intrinsics)
+        _capi.check(self._lib.nvbx_integrate_frame_host_lowres(
+            self._handle, mapper_id, depth.data_ptr(), x.data_ptr(), h, w, c, dtype, layout, kernel,
+            depth.shape[0], depth.shape[1], None if depth_mask is None else depth_mask.data_ptr(),
             None if feature_mask is None else feature_mask.data_ptr(), _pose16(t_w_c), fx, fy, cx, cy,
             self._stream()))
 

@@ -1561,6 +1561,63 @@ void orc_last_synthetic_depth(void* h, float* out, int* rows, int* cols) {
 }
 
 // ---- unit hooks used to pin the restatement against the reference's own unit tests ----------------
+// ---- N4: the extractor's up-sampling (third-party algorithm: PyTorch, pinned by mindmap's environment; torch
+// 2.11.0+cu128 in this image).  Restates aten/src/ATen/native/cuda/UpSampleBilinear2d.cu
+// (upsample_bilinear2d_out_frame / upsample_bilinear2d_nhwc_out_frame) + UpSample.cuh:114-130
+// (area_pixel_compute_source_index) with the multiply-add contraction of the sm_100 build (fmaf below = one
+// rounding), then feature_extraction.py:190-210 (HWC, zero-pad to C) and nvblox_mapping_helpers.py:256
+// (.to(float16)).  low: [lh][lw][lc] fp32 (values already exact in the source dtype); mode: 0 NCHW-kernel order,
+// 1 NHWC-f32-kernel order, 2 NCHW order with the bf16 store rounding.  out: [H][W][C] binary16.
+static inline float bf16_round(float v) {
+  uint32_t u;
+  std::memcpy(&u, &v, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return v;  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  u &= 0xffff0000u;
+  std::memcpy(&v, &u, 4);
+  return v;
+}
+void orc_upsample_bilinear(const float* low, int lh, int lw, int lc, int C, int H, int W, int mode, uint16_t* out) {
+  const float rh = (float)lh / (float)H, rw = (float)lw / (float)W;
+  struct Axis {
+    int i0, i1;
+    float l0, l1;
+  };
+  auto axis = [](float scale, int dst, int n) {
+    Axis a;
+    float s = std::fmaf((float)dst + 0.5f, scale, -0.5f);
+    s = (s >= 0.0f) ? s : 0.0f;
+    a.i0 = (int)s;
+    a.i1 = a.i0 + ((a.i0 < n - 1) ? 1 : 0);
+    a.l1 = s - (float)a.i0;
+    a.l0 = 1.0f - a.l1;
+    return a;
+  };
+#pragma omp parallel for schedule(static)
+  for (int y = 0; y < H; ++y) {
+    const Axis ya = axis(rh, y, lh);
+    for (int x = 0; x < W; ++x) {
+      const Axis xa = axis(rw, x, lw);
+      const float* pa = low + ((size_t)ya.i0 * lw + xa.i0) * lc;
+      const float* pb = low + ((size_t)ya.i0 * lw + xa.i1) * lc;
+      const float* pc = low + ((size_t)ya.i1 * lw + xa.i0) * lc;
+      const float* pd = low + ((size_t)ya.i1 * lw + xa.i1) * lc;
+      uint16_t* o = out + ((size_t)y * W + x) * C;
+      for (int c = 0; c < C; ++c) {
+        if (c >= lc) {
+          o[c] = 0;
+          continue;
+        }
+        const float top = mode == 1 ? std::fmaf(xa.l1, pb[c], xa.l0 * pa[c]) : std::fmaf(xa.l0, pa[c], xa.l1 * pb[c]);
+        const float bot = std::fmaf(xa.l0, pc[c], xa.l1 * pd[c]);
+        float v = std::fmaf(ya.l0, top, ya.l1 * bot);
+        if (mode == 2) v = bf16_round(v);
+        o[c] = f2h(v);
+      }
+    }
+  }
+}
+
 uint16_t orc_f2h(float f) { return f2h(f); }
 float orc_h2f(uint16_t h) { return h2f(h); }
 uint16_t orc_hadd(uint16_t a, uint16_t b) { return hadd(a, b); }

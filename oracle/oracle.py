@@ -70,6 +70,8 @@ def lib() -> C.CDLL:
         L.orc_last_synthetic_depth.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         # unit hooks
         L.orc_f2h.restype = C.c_uint16
+        L.orc_upsample_bilinear.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]
+        L.orc_upsample_bilinear.restype = None
         L.orc_f2h.argtypes = [C.c_float]
         L.orc_h2f.restype = C.c_float
         L.orc_h2f.argtypes = [C.c_uint16]
@@ -265,3 +267,15 @@ class OracleMapper:
         if out.size:
             self.L.orc_last_synthetic_depth(self.h, _ptr(out), C.byref(r), C.byref(c))
         return out
+
+
+def upsample_bilinear(low_hwc: np.ndarray, channels: int, height: int, width: int, mode: int = 0) -> np.ndarray:
+    """N4: the [H, W, C] binary16 frame (as uint16 bits) mindmap's FeatureExtractor.compute() + `.to(float16)`
+    produce from the backbone's [lh, lw, lc] fp32 feature map (torch CUDA bilinear up-sampling, align_corners=False,
+    zero-padded to `channels`).  mode: 0 torch NCHW kernel, 1 torch NHWC fp32 kernel, 2 bf16 tensors."""
+    low = np.ascontiguousarray(low_hwc, dtype=np.float32)
+    lh, lw, lc = low.shape
+    assert lc <= channels
+    out = np.empty((height, width, channels), np.uint16)
+    lib().orc_upsample_bilinear(_ptr(low), lh, lw, lc, channels, height, width, mode, _ptr(out))
+    return out

@@ -471,3 +471,68 @@ def test_color_mesh_is_a_separate_layer():
     m.update_color_mesh()
     v_c, c, _ = m.get_color_mesh()
     assert np.array_equal(v_c, v_f) and np.all(c == 127)
+
+
+# ---- N4: the extractor's bilinear up-sampling (PyTorch's algorithm, restated in oracle.upsample_bilinear) --------
+def _torch_cpu_chained(low_bchw, size, C_feat):
+    import torch
+    import torch.nn.functional as F
+    up = F.interpolate(low_bchw, size=size, mode='bilinear', align_corners=False)[0].permute(1, 2, 0)
+    if C_feat > up.shape[2]:
+        up = torch.cat((up, torch.zeros(size[0], size[1], C_feat - up.shape[2])), dim=2)
+    return up.contiguous().to(torch.float16).numpy()
+
+
+@pytest.mark.parametrize('shape', [(32, 32, 24, 32, 512, 512), (37, 37, 16, 16, 518, 518), (7, 5, 8, 16, 64, 48)])
+@pytest.mark.parametrize('mode', [0, 1])
+def test_upsample_restatement_against_torch_cpu(shape, mode):
+    """torch's CPU kernel orders its multiply-adds differently from its CUDA kernels (which the oracle follows,
+    and which tests/test_gpu_upsample.py checks bit for bit on the GPU): > 99.9 % of the halves are identical and
+    the rest are within fp32 rounding noise of the same value."""
+    import torch
+    lh, lw, lc, C_feat, H, W = shape
+    torch.manual_seed(lh * 100 + lc)
+    low = torch.randn(1, lc, lh, lw)
+    want = _torch_cpu_chained(low, (H, W), C_feat)
+    got = O.upsample_bilinear(low[0].permute(1, 2, 0).numpy(), C_feat, H, W, mode).view(np.float16)
+    same = got.view(np.uint16) == want.view(np.uint16)
+    assert same.mean() > 0.999
+    np.testing.assert_allclose(got.astype(np.float32), want.astype(np.float32), rtol=2e-3, atol=2e-3)
+    assert not got[..., lc:].any()          # zero-padded channels
+
+
+def test_upsample_known_answers():
+    """align_corners=False semantics (UpSample.cuh:114-130): source index (dst + 0.5) * in/out - 0.5 clamped at 0,
+    right / bottom neighbour clamped at the border."""
+    low = np.array([[[0.0], [1.0]], [[2.0], [3.0]]], np.float32)       # 2 x 2 x 1
+    out = O.upsample_bilinear(low, 1, 4, 4, 0).view(np.float16)[..., 0].astype(np.float32)
+    col = np.array([0.0, 0.25, 0.75, 1.0], np.float32)                 # lambda along one axis for 2 -> 4
+    want = col[None, :] * 1.0 + col[:, None] * 2.0
+    assert np.array_equal(out, want)
+    const = np.full((3, 5, 8), 0.7, np.float32)
+    out = O.upsample_bilinear(const, 8, 24, 40, 1).view(np.float16)
+    assert np.all(out == np.float16(0.7))
+    # bf16 tensors: the kernel's bf16 store precedes the cast to fp16 (two roundings)
+    v = np.full((2, 2, 8), 1.0 + 2.0 ** -9, np.float32)               # representable in fp16, not in bf16
+    assert np.all(O.upsample_bilinear(v, 8, 4, 4, 0).view(np.float16) == np.float16(1.0 + 2.0 ** -9))
+    assert np.all(O.upsample_bilinear(v, 8, 4, 4, 2).view(np.float16) == np.float16(1.0))
+
+
+def test_lowres_descriptor_follows_torchs_kernel_choice():
+    """The wrapper must predict which CUDA kernel F.interpolate would have run (NHWC iff channels-last strides and
+    >= 16 channels) and pass channels-last memory through zero-copy."""
+    import torch
+    from torch._prims_common import suggest_memory_format
+    from nvblox_torch.mapper import _strides_like_channels_last, lowres_descriptor
+    feats = torch.randn(1, 16 * 16, 48)                                 # RADIO: [b, hw, c]
+    bchw = feats.view(1, 16, 16, -1).permute(0, 3, 1, 2)                # feature_extraction.py:328-330
+    for t in (bchw, bchw.contiguous(), torch.randn(1, 8, 4, 4), torch.randn(1, 1, 4, 4),
+              torch.randn(1, 8, 4, 4).contiguous(memory_format=torch.channels_last), torch.randn(1, 24, 1, 1)):
+        assert _strides_like_channels_last(t) == (suggest_memory_format(t) == torch.channels_last), t.stride()
+    x, c, h, w, dtype, layout, kernel = lowres_descriptor(bchw)
+    assert (c, h, w, dtype, layout, kernel) == (48, 16, 16, 0, 1, 1) and x.data_ptr() == feats.data_ptr()
+    x, c, h, w, dtype, layout, kernel = lowres_descriptor(bchw.contiguous().half())
+    assert (dtype, layout, kernel) == (1, 0, 0)
+    small = torch.randn(1, 4, 4, 8).permute(0, 3, 1, 2)                 # channels-last but < 16 channels: NCHW kernel
+    assert lowres_descriptor(small)[4:] == (0, 1, 0)
+    assert lowres_descriptor(torch.randn(24, 4, 4).bfloat16())[4:] == (2, 0, 0)
