@@ -174,7 +174,9 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
+    import ctypes as C
     from nvblox_mindmap_b200 import _capi
+    from nvblox_mindmap_b200.params import NvbxCounters
     from nvblox_torch.constants import constants
     from nvblox_torch.mapper import Mapper
 
@@ -259,25 +261,36 @@ def run_ours(args, rank, world, local_rank):
     feat_call_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
 
     # ---- end-to-end pass: HOST frames through the public API ----------------------------------------------
-    n_e2e = max(1, min(args.steps, 16))
+    # Headline e2e = the default host entry: depth copied H2D, the pinned feature frame read through its device
+    # mapping so that only the pixels the frame's voxels sample cross PCIe (nvbx_integrate_frame_host, sparse
+    # mode; identical map, tests/test_gpu_host_frames.py).  h2d_bytes_per_step is what actually crossed the bus:
+    # depth bytes + device-counted fetched pixels x 2C.  The whole-frame copy is timed next to it (`dense`).
+    n_e2e = max(1, min(args.steps, 64))
     h_depth = [d.cpu().pin_memory() for d in depths[:n_e2e]]
     h_feat = [feats[i % N_FEATURE_BUFFERS].cpu().pin_memory() for i in range(min(n_e2e, 3))]
-    for i in range(min(3, n_e2e)):
-        mapper.integrate_frame_from_host(h_depth[i], h_feat[i % len(h_feat)], poses[i], K_t)
-    barrier()
-    t0 = time.perf_counter()
-    d2h = 0
-    for i in range(n_e2e):
-        mapper.integrate_frame_from_host(h_depth[i], h_feat[i % len(h_feat)], poses[i], K_t)
-        c = mapper.counters(0)          # D2H read of the step's result (map counters) + stream sync
-        d2h = 256
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * n_e2e / e2e_s
+
+    def e2e_pass(mode, n):
+        mapper.set_host_fetch_mode(mode)
+        for i in range(min(3, n)):
+            mapper.integrate_frame_from_host(h_depth[i], h_feat[i % len(h_feat)], poses[i], K_t)
+        px0 = mapper.counters(0)['host_pixels_fetched']
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n):
+            mapper.integrate_frame_from_host(h_depth[i], h_feat[i % len(h_feat)], poses[i], K_t)
+            c = mapper.counters(0)          # D2H read of the step's result (map counters) + stream sync
+        barrier()
+        secs = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([secs], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        return world * n / secs, (c['host_pixels_fetched'] - px0) / n
+
+    dense_value, _ = e2e_pass('dense', min(n_e2e, 16))
+    e2e_value, e2e_px = e2e_pass('sparse', n_e2e)
+    d2h = C.sizeof(NvbxCounters)
+    e2e_h2d = H * W * 4 + int(round(e2e_px * 2 * C_FEAT))
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -286,6 +299,7 @@ def run_ours(args, rank, world, local_rank):
         sample_mt = oracle_sample(24, n_cores)          # ~4-20 s with every host thread
         n_upd = counters['feature_voxels_updated'] / args.steps
         px_per_voxel = sample_mt['u_px'] / max(1, sample_mt['n_upd'])
+        px_per_voxel_dev = e2e_px / max(1.0, n_upd)   # device-counted on the sparse host pass (same poses)
         # Algorithmic bytes of the dominant kernel (k_feature_gather) per launch, alpha = 1:
         # 2C bytes per DISTINCT feature pixel read + 2(C+1) bytes per voxel row written.  N_upd comes from the
         # device counters of the timed region, distinct pixels per voxel from the oracle sample.
@@ -307,8 +321,11 @@ def run_ours(args, rank, world, local_rank):
                        'l2_policy': f'inputs larger than L2: {N_FEATURE_BUFFERS} distinct 384 MiB feature frames '
                                     'cycled, a different one every step'},
             'e2e': {'value': e2e_value, 'unit': 'frames/s',
-                    'h2d_bytes_per_step': H * W * 4 + H * W * C_FEAT * 2, 'd2h_bytes_per_step': d2h,
-                    'steps': n_e2e},
+                    'h2d_bytes_per_step': e2e_h2d, 'd2h_bytes_per_step': d2h, 'steps': n_e2e,
+                    'transfer': 'depth by cudaMemcpyAsync; pinned feature frame read sparsely through its device '
+                                f'mapping ({e2e_px:.0f} of {H * W} pixels per step cross PCIe, each once)',
+                    'dense_copy': {'value': dense_value, 'unit': 'frames/s',
+                                   'h2d_bytes_per_step': H * W * 4 + H * W * C_FEAT * 2}},
             'gpu_launches': launches,
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'kernel': 'k_feature_gather<3,1,4>', 'achieved': achieved, 'peak': peak,
@@ -316,6 +333,7 @@ def run_ours(args, rank, world, local_rank):
                          'traffic_source': traffic_src,
                          'peak_source': peak_src, 'kernel_ms': kms, 'algorithmic_bytes_per_launch': b_feat,
                          'n_upd_per_frame': n_upd, 'distinct_pixels_per_voxel': px_per_voxel,
+                         'distinct_pixels_per_voxel_device_counted': px_per_voxel_dev,
                          'frac_of_nominal_8TBps': (achieved / 8000.0) if achieved else None},
             'cpu_baseline': {'value': sample_mt['fps'], 'unit': 'frames/s', 'cores': n_cores, 'kind': 'port',
                              'sample': f"first {sample_mt['frames']} frames of the workload through the CPU oracle "

@@ -121,6 +121,7 @@ typedef struct nvbx_counters {
   int64_t color_band_blocks;        /* blocks handed to the colour update                      */
   int64_t color_voxels_updated;
   int64_t color_blocks_allocated;
+  int64_t host_pixels_fetched;      /* nvbx_integrate_frame_host: feature pixels that crossed PCIe */
   int64_t reserved[4];              /* NVBX_PROFILE_COUNTERS builds only                       */
 } nvbx_counters;
 
@@ -169,8 +170,18 @@ int nvbx_integrate_color(nvbx_mapper* m, int map_id, const void* rgb, int height
                          const void* mask, const float* T_L_C, float fx, float fy, float cx, float cy,
                          void* stream);
 
-/* Same as integrate_depth + integrate_features but from HOST buffers (pinned or pageable): the H2D
- * copies are enqueued on `stream` ahead of the kernels.  This is the end-to-end entry bench.py times. */
+/* Same as integrate_depth + integrate_features but from HOST buffers: the end-to-end entry bench.py times.
+ * (The reference accepts CUDA tensors only -- mapper.py:458-490 -- so its caller pays `.cuda()` on the whole
+ * H*W*C frame first.)  Depth and masks are copied H2D on `stream`.  The feature frame:
+ *   - pinned / registered host memory (cudaHostAlloc, cudaHostRegister, torch `.pin_memory()`), 16-byte aligned,
+ *     mode NVBX_HOST_FETCH_SPARSE (default): the GPU reads it through its device mapping and fetches ONLY the
+ *     pixels this frame's voxels sample (each distinct pixel crosses PCIe once, 2C bytes); the map result is
+ *     identical to the dense copy.  The buffer must stay unchanged until `stream` has passed this call.
+ *   - pageable memory, or mode NVBX_HOST_FETCH_DENSE: one cudaMemcpyAsync of all H*W*C halves.
+ * nvbx_counters.host_pixels_fetched counts the pixels the sparse path moved. */
+#define NVBX_HOST_FETCH_SPARSE 0
+#define NVBX_HOST_FETCH_DENSE 1
+int nvbx_set_host_fetch_mode(nvbx_mapper* m, int mode);
 int nvbx_integrate_frame_host(nvbx_mapper* m, int map_id, const float* depth_host, const void* features_host,
                               int height, int width, int channels, const uint8_t* depth_mask_host,
                               const uint8_t* feature_mask_host, const float* T_L_C, float fx, float fy,

@@ -240,6 +240,7 @@ struct Map {
   // host staging for nvbx_integrate_frame_host
   DevBuf<float> st_depth;
   DevBuf<__half> st_feat;
+  DevBuf<unsigned> st_pixmap;  // one bit per feature pixel a host-frame work item reads (kept all-zero between frames)
   DevBuf<uint8_t> st_mask_d, st_mask_f;
   DevBuf<float> st_low;      // N4: [lh][lw][C] fp32 staged low-res feature map
   DevBuf<uint8_t> st_low_in;  // N4: raw upload of the host low-res map
@@ -257,6 +258,7 @@ struct nvbx_mapper {
   int device = 0;
   int C = 0;
   int sm_count = 148;
+  int host_fetch_mode = NVBX_HOST_FETCH_SPARSE;
   nvbx_params params{};
   std::vector<std::unique_ptr<Map>> maps;
 };
@@ -630,6 +632,7 @@ void destroy_map(Map& mp) {
   }
   mp.st_depth.release();
   mp.st_feat.release();
+  mp.st_pixmap.release();
   mp.st_mask_d.release();
   mp.st_mask_f.release();
   mp.st_low.release();
@@ -1144,9 +1147,15 @@ int prepare_lowres(nvbx_mapper* m, Map& mp, const void* lowres, int low_h, int l
 }
 
 // features != nullptr: the [H, W, C] fp16 frame (a8).  Otherwise `uf` / `up_mode` describe the low-res map (N4).
+struct HostFetch {  // nvbx_integrate_frame_host: `features` is a device buffer filled sparsely from this mapped host frame
+  const uint4* host_img;
+  unsigned* bitmap;
+  int n_words;
+};
+
 int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, const UpFrame* uf, int up_mode,
                             int height, int width, const void* mask, const float* T_L_C_rm, float fx, float fy,
-                            float cx, float cy, void* stream_v) {
+                            float cx, float cy, void* stream_v, const HostFetch* hf = nullptr) {
   int rc;
   const nvbx_params& p = m->params;
   cudaStream_t stream = (cudaStream_t)stream_v;
@@ -1196,6 +1205,18 @@ int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, co
     LAUNCH(k_feature_geometry, ggrid, 512, 0, stream, mp.dev, mp.band_slots.p, mp.newfeat_slots.p, ff, mp.items.p,
            (int)begin, (int)end);
     const int ch = (m->C % 256 == 0 && m->C / 256 >= 1 && m->C / 256 <= 4) ? m->C / 256 : 0;
+    if (hf) {
+      const int nvec = m->C / 8;
+      uint4* dev_img = (uint4*)const_cast<void*>(features);
+      LAUNCH(k_pixel_mark, persistent_grid(m, 2), 256, 0, stream, mp.dev, mp.items.p, hf->bitmap, width);
+      const int fgrid = std::min(persistent_grid(m, 8), (hf->n_words + 7) / 8);
+      if (ch == 3)
+        LAUNCH(k_pixel_fetch<3>, fgrid, 256, 0, stream, mp.dev, hf->bitmap, hf->n_words, hf->host_img, dev_img, nvec);
+      else if (ch == 4)
+        LAUNCH(k_pixel_fetch<4>, fgrid, 256, 0, stream, mp.dev, hf->bitmap, hf->n_words, hf->host_img, dev_img, nvec);
+      else
+        LAUNCH(k_pixel_fetch<0>, fgrid, 256, 0, stream, mp.dev, hf->bitmap, hf->n_words, hf->host_img, dev_img, nvec);
+    }
     if (uf) {
       if (ch == 3)
         rc = launch_gather_up<3>(m, mp, ff, *uf, up_mode, last, stream);
@@ -1330,9 +1351,31 @@ int nvbx_integrate_frame_host(nvbx_mapper* m, int map_id, const float* depth_hos
   Map& mp = *m->maps[map_id];
   const size_t px = (size_t)height * width;
   if ((rc = mp.st_depth.ensure(px, stream))) return rc;
+  if (channels != m->C)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame has %d channels, the map was created with %d", channels,
+                m->C);
   if ((rc = mp.st_feat.ensure(px * channels, stream))) return rc;
   CUDA_TRY(cudaMemcpyAsync(mp.st_depth.p, depth_host, px * sizeof(float), cudaMemcpyHostToDevice, stream));
-  CUDA_TRY(cudaMemcpyAsync(mp.st_feat.p, features_host, px * channels * sizeof(__half), cudaMemcpyHostToDevice, stream));
+  // A pinned (device-mapped) frame is read sparsely by the GPU: only the pixels this frame's work items touch
+  // cross PCIe (k_pixel_mark / k_pixel_fetch).  A pageable frame, or host_fetch_mode = dense, is copied whole.
+  HostFetch hf{nullptr, nullptr, 0};
+  if (m->host_fetch_mode == NVBX_HOST_FETCH_SPARSE && !(((uintptr_t)features_host) & 15)) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, features_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+        attr.devicePointer != nullptr) {
+      const size_t n_words = (px + 31) / 32;
+      const size_t had = mp.st_pixmap.cap;
+      if ((rc = mp.st_pixmap.ensure(n_words, stream))) return rc;
+      if (mp.st_pixmap.cap != had) CUDA_TRY(cudaMemsetAsync(mp.st_pixmap.p, 0, mp.st_pixmap.cap * sizeof(unsigned), stream));
+      hf.host_img = (const uint4*)attr.devicePointer;
+      hf.bitmap = mp.st_pixmap.p;
+      hf.n_words = (int)n_words;
+    } else {
+      (void)cudaGetLastError();  // an unregistered pointer is not an error here
+    }
+  }
+  if (!hf.host_img)
+    CUDA_TRY(cudaMemcpyAsync(mp.st_feat.p, features_host, px * channels * sizeof(__half), cudaMemcpyHostToDevice, stream));
   const uint8_t* dm = nullptr;
   const uint8_t* fm = nullptr;
   if (depth_mask_host) {
@@ -1347,8 +1390,16 @@ int nvbx_integrate_frame_host(nvbx_mapper* m, int map_id, const float* depth_hos
   }
   if ((rc = nvbx_integrate_depth(m, map_id, mp.st_depth.p, height, width, dm, T_L_C, fx, fy, cx, cy, stream_v)))
     return rc;
-  return nvbx_integrate_features(m, map_id, mp.st_feat.p, height, width, channels, fm, T_L_C, fx, fy, cx, cy,
-                                 stream_v);
+  return integrate_features_impl(m, map_id, mp.st_feat.p, nullptr, 0, height, width, fm, T_L_C, fx, fy, cx, cy,
+                                 stream_v, hf.host_img ? &hf : nullptr);
+}
+
+int nvbx_set_host_fetch_mode(nvbx_mapper* m, int mode) {
+  if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper");
+  if (mode != NVBX_HOST_FETCH_SPARSE && mode != NVBX_HOST_FETCH_DENSE)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "bad host fetch mode %d", mode);
+  m->host_fetch_mode = mode;
+  return NVBX_OK;
 }
 
 int nvbx_integrate_frame_host_lowres(nvbx_mapper* m, int map_id, const float* depth_host, const void* lowres_host,
@@ -1782,6 +1833,7 @@ int nvbx_get_counters(nvbx_mapper* m, int map_id, nvbx_counters* out, void* stre
   out->color_band_blocks = (int64_t)c[kCntColorBandBlocks];
   out->color_voxels_updated = (int64_t)c[kCntColorVoxelsUpdated];
   out->color_blocks_allocated = (int64_t)c[kCntColorBlocksAllocated];
+  out->host_pixels_fetched = (int64_t)c[kCntHostPixelsFetched];
   for (int i = 0; i < 4; ++i) out->reserved[i] = (int64_t)c[kCntProfile0 + i];  // NVBX_PROFILE_COUNTERS builds only
   return NVBX_OK;
 }

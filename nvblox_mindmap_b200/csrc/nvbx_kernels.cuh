@@ -944,6 +944,82 @@ __global__ void __launch_bounds__(256, CTAS) k_feature_gather(MapDev m, const Fe
 }
 
 // ================================================================================================
+// Host-resident feature frames (nvbx_integrate_frame_host).  The reference only accepts CUDA tensors, so a
+// caller with a host frame pays `.cuda()` on all H*W*C halves (384 MiB at 512^2 x 768) although the frame's
+// work items read ~20 % of the pixels.  With a pinned (device-mapped) host frame the pixels cross PCIe
+// sparsely instead: k_pixel_mark sets one bit per pixel any work item reads, k_pixel_fetch copies exactly
+// those 2C-byte rows from the mapped host pointer to their natural place in the device frame buffer (every
+// distinct pixel crosses the bus once), and k_feature_gather then runs unchanged on the device buffer.  The
+// pixels that are not fetched keep stale bytes that no work item reads.
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_pixel_mark(MapDev m, const FeatItem* __restrict__ items,
+                                                    unsigned* __restrict__ bitmap, int cols) {
+  pdl_prologue();
+  const int n = m.ctrl->item_count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int pix = __ldg(&items[i].pix);
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int p0 = pix + r * cols, p1 = p0 + 1;
+      const unsigned b0 = 1u << (p0 & 31), b1 = 1u << (p1 & 31);
+      if ((p0 >> 5) == (p1 >> 5)) {
+        if ((bitmap[p0 >> 5] & (b0 | b1)) != (b0 | b1)) atomicOr(&bitmap[p0 >> 5], b0 | b1);
+      } else {
+        if (!(bitmap[p0 >> 5] & b0)) atomicOr(&bitmap[p0 >> 5], b0);
+        if (!(bitmap[p1 >> 5] & b1)) atomicOr(&bitmap[p1 >> 5], b1);
+      }
+    }
+  }
+}
+
+// warp = one 32-pixel bitmap word; lanes stride over the pixel row in 16-byte vectors.  NV > 0: the row is
+// exactly NV * 32 vectors (C = 256 * NV) and all NV loads of a pixel are in flight together.
+template <int NV>
+__global__ void __launch_bounds__(256) k_pixel_fetch(MapDev m, unsigned* __restrict__ bitmap, int n_words,
+                                                     const uint4* __restrict__ host_img, uint4* __restrict__ dev_img,
+                                                     int nvec) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  unsigned fetched = 0;
+  for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_words; w += warps_total) {
+    unsigned bits = bitmap[w];
+    if (!bits) continue;
+    __syncwarp();
+    if (lane == 0) bitmap[w] = 0u;  // clean for the next frame
+    fetched += __popc(bits);
+    while (bits) {
+      const int b0 = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const size_t o0 = (size_t)(w * 32 + b0) * nvec;
+      if (NV > 0) {
+        // two pixels (2 * NV independent 512-byte warp loads) in flight per iteration
+        const bool two = bits != 0;
+        const int b1 = two ? __ffs(bits) - 1 : b0;
+        bits &= bits - 1;
+        const size_t o1 = (size_t)(w * 32 + b1) * nvec;
+        uint4 r0[NV > 0 ? NV : 1], r1[NV > 0 ? NV : 1];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) r0[k] = __ldcs(host_img + o0 + k * 32 + lane);
+        if (two) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) r1[k] = __ldcs(host_img + o1 + k * 32 + lane);
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) dev_img[o0 + k * 32 + lane] = r0[k];
+        if (two) {
+#pragma unroll
+          for (int k = 0; k < NV; ++k) dev_img[o1 + k * 32 + lane] = r1[k];
+        }
+      } else {
+        for (int v = lane; v < nvec; v += 32) dev_img[o0 + v] = __ldcs(host_img + o0 + v);
+      }
+    }
+  }
+  if (lane == 0 && fetched) count_add(m, kCntHostPixelsFetched, (unsigned long long)fetched);
+}
+
+// ================================================================================================
 // N1. Colour integration: integrateBlocksKernel<UpdateAppearanceVoxelFunctor<ColorVoxel>>
 // (projective_integrator_impl.cuh:156-214, projective_appearance_integrator.cu:277-353).  Same geometry
 // as the feature path (projection, bilinear synthetic depth, band test, image bounds, mask); the payload

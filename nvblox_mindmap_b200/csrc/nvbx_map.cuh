@@ -62,6 +62,7 @@ enum CounterId {
   kCntColorVoxelsUpdated,
   kCntColorBlocksAllocated,
   kCntProfile0 = 16,  // NVBX_PROFILE_COUNTERS builds: 16..19
+  kCntHostPixelsFetched = 20,  // nvbx_integrate_frame_host: feature pixels read from the mapped host frame
   kCntNum = 24
 };
 

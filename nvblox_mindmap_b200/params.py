@@ -59,6 +59,7 @@ class NvbxCounters(C.Structure):
         ('color_band_blocks', C.c_int64),
         ('color_voxels_updated', C.c_int64),
         ('color_blocks_allocated', C.c_int64),
+        ('host_pixels_fetched', C.c_int64),
         ('reserved', C.c_int64 * 4),
     ]
 

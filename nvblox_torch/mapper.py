@@ -202,7 +202,8 @@ class Mapper:
 
     def integrate_frame_from_host(self, depth, features, t_w_c, intrinsics, depth_mask=None, feature_mask=None,
                                   mapper_id: int = 0) -> None:
-        """(ours) depth + feature frame from HOST (ideally pinned) tensors; H2D copies ride the stream."""
+        """(ours) depth + feature frame from HOST tensors.  A pinned feature frame is fetched sparsely over PCIe
+        (see `set_host_fetch_mode`) and must not be modified until the stream has passed this call."""
         assert depth.dtype == torch.float32 and features.dtype == torch.float16 and not depth.is_cuda
         fx, fy, cx, cy = _fxfycxcy(intrinsics)
         _capi.check(self._lib.nvbx_integrate_frame_host(
@@ -210,6 +211,11 @@ class Mapper:
             features.shape[2], None if depth_mask is None else depth_mask.data_ptr(),
             None if feature_mask is None else feature_mask.data_ptr(), _pose16(t_w_c), fx, fy, cx, cy,
             self._stream()))
+
+    def set_host_fetch_mode(self, mode: str) -> None:
+        """(ours) 'sparse' (default): a pinned host feature frame is read through its device mapping and only the
+        pixels the frame's voxels sample cross PCIe; 'dense': the whole frame is copied."""
+        _capi.check(self._lib.nvbx_set_host_fetch_mode(self._handle, {'sparse': 0, 'dense': 1}[mode]))
 
     def add_feature_frame_lowres(self,
                                  features_bchw: torch.Tensor,
