@@ -239,6 +239,11 @@ def run_ours(args, rank, world, local_rank):
         ms = float(t.item())
     value = world * args.steps / (ms / 1000.0)
 
+    if args.sweep_gather:
+        if rank == 0:
+            sweep_gather(args, lib, mapper, depths, poses, feats, K_t, step)
+        return
+
     if args.quick:
         if rank == 0:
             kms = kernel_time_ms(args, mapper, depths, poses, feats, K_t)
@@ -328,7 +333,7 @@ def run_ours(args, rank, world, local_rank):
                                    'h2d_bytes_per_step': H * W * 4 + H * W * C_FEAT * 2}},
             'gpu_launches': launches,
             'clocks': clocks,
-            'roofline': {'bound': 'hbm', 'kernel': 'k_feature_gather<3,1,4>', 'achieved': achieved, 'peak': peak,
+            'roofline': {'bound': 'hbm', 'kernel': 'k_feature_gather_dyn<3,256,4> (static deal, item prefetch)', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None, 'traffic': traffic,
                          'traffic_source': traffic_src,
                          'peak_source': peak_src, 'kernel_ms': kms, 'algorithmic_bytes_per_launch': b_feat,
@@ -370,6 +375,32 @@ def kernel_time_ms(args, mapper, depths, poses, feats, K_t):
     lib.nvbx_get_kernel_timing(mapper._handle, 0, C.byref(ms), C.byref(n))
     lib.nvbx_set_kernel_timing(mapper._handle, 0)
     return (ms.value / n.value) if n.value else None
+
+
+def sweep_gather(args, lib, mapper, depths, poses, feats, K_t, step):
+    """Tuning aid (not a bench line): every schedule of the feature gather in ONE process, on the bench
+    workload -- live kernel duration (library-placed CUDA events) and whole-frame device time."""
+    import torch
+    n_total = args.warmup + args.steps
+    grid = [(0, 0, 1), (1, 0, 1), (2, 0, 1), (4, 0, 1), (5, 0, 1), (6, 0, 1), (4, 50, 4), (6, 50, 4)]
+    rows = []
+    for rep in range(2):
+        for (v, pm, tk) in grid:
+            assert lib.nvbx_set_gather_tuning(v, pm, tk) == 0
+            for i in range(8):
+                step(i)
+            kms = kernel_time_ms(args, mapper, depths, poses, feats, K_t)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(args.warmup, n_total):
+                step(i)
+            e1.record()
+            torch.cuda.synchronize()
+            rows.append({'rep': rep, 'variant': v, 'dyn_permille': pm, 'ticket': tk, 'gather_us': 1000.0 * kms,
+                         'frame_us': 1000.0 * e0.elapsed_time(e1) / args.steps})
+            print(json.dumps(rows[-1]), flush=True)
+    lib.nvbx_set_gather_tuning(4, 0, 4)
 
 
 def ncu_traffic_bytes():
@@ -505,6 +536,7 @@ def main():
     ap.add_argument('--steps', type=int, default=1024)
     ap.add_argument('--warmup', type=int, default=64)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--sweep-gather', action='store_true', help='tuning aid: time every gather schedule')
     ap.add_argument('--quick', action='store_true', help='tuning aid: device-timed pass + kernel timing only')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

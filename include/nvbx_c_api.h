@@ -326,6 +326,10 @@ int nvbx_set_kernel_timing(nvbx_mapper* m, int enabled);
  * resets the records. */
 int64_t nvbx_kernel_timing_report(nvbx_mapper* m, char* json, int64_t capacity);
 int nvbx_get_kernel_timing(nvbx_mapper* m, int which, double* total_ms, int64_t* launches);
+/* Process-wide schedule of the feature gather kernel (tuning aid; results are identical for every setting):
+ * variant 0..3 = static round-robin deal <units in flight, CTAs/SM>, 4..6 = k_feature_gather_dyn with
+ * `dyn_permille`/1000 of the units handed out by atomic ticket, `ticket_units` per grab. */
+int nvbx_set_gather_tuning(int variant, int dyn_permille, int ticket_units);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t nvbx_kernel_launch_count(void);
 /* Debug / parity hooks: copy the last frame's intermediate products to HOST memory.

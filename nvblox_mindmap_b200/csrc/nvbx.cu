@@ -18,6 +18,7 @@
 #include <memory>
 #include <string>
 #include <utility>
+#include <functional>
 #include <vector>
 
 #include "../../include/nvbx_c_api.h"
@@ -439,7 +440,15 @@ bool slots_fit(const nvbx_mapper* m, const Map& mp, long long need) {
   const long long v = mp.slot_used_ub + need;
   return (ws >= 0 ? std::min(v, ws) : v) <= mp.slot_capacity;
 }
-int ensure_feats(nvbx_mapper* m, Map& mp, long long need, cudaStream_t stream) {
+// Feature blocks are ~1 MB each (512 x (C + 8) halves), so the pessimistic bound "every candidate block of the
+// view gets one" is only affordable for small maps: past kFeatPessimisticBytes the arena grows by the EXACT
+// number of feature blocks the frame will allocate, counted on the device by `count_new` (k_band_count) and read
+// back -- two synchronisations per frame, paid only by maps of that size while their bound does not fit.
+constexpr long long kFeatPessimisticBytes = 8LL << 30;
+constexpr long long kFeatExactSlackBytes = 1LL << 30;
+
+int ensure_feats(nvbx_mapper* m, Map& mp, long long need, cudaStream_t stream,
+                 const std::function<int()>& count_new = nullptr) {
   need = std::min(need, mp.slot_used_ub);  // a feature block needs a TSDF block
   auto bound = [&](long long v) { return std::min(v, mp.slot_used_ub); };
   if (bound(mp.feat_used_ub + need) <= mp.feat_capacity) {
@@ -451,11 +460,30 @@ int ensure_feats(nvbx_mapper* m, Map& mp, long long need, cudaStream_t stream) {
   mp.feat_used_ub = (long long)mp.h_ctrl->feat_high - mp.h_ctrl->feat_free_top;
   mp.slot_used_ub = (long long)mp.h_ctrl->slot_high - mp.h_ctrl->slot_free_top;
   need = std::min(need, mp.slot_used_ub);
-  const long long want = bound(mp.feat_used_ub + need);
+  long long want = bound(mp.feat_used_ub + need);
   if (want > mp.feat_capacity) {
-    long long ncap = std::max(want, (long long)(mp.feat_capacity * 1.5f));
-    ncap = std::min(ncap, std::max(want, mp.slot_used_ub));
-    if ((rc = grow_feats(m, mp, (int)ncap, stream))) return rc;
+    const long long block_bytes = (long long)kVoxelsPerBlock * mp.dev.row * (long long)sizeof(__half);
+    long long ncap;
+    if (count_new && want * block_bytes > kFeatPessimisticBytes) {
+      CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->list_count, 0, sizeof(int), stream));
+      if ((rc = count_new())) return rc;
+      if ((rc = read_ctrl(mp, stream))) return rc;
+      want = mp.feat_used_ub + (long long)mp.h_ctrl->list_count;
+      ncap = std::max(want, std::min((long long)(mp.feat_capacity * 1.25f), want + kFeatExactSlackBytes / block_bytes));
+      ncap = std::min(ncap, std::max(want, mp.slot_used_ub));
+    } else {
+      ncap = std::max(want, (long long)(mp.feat_capacity * 1.5f));
+      ncap = std::min(ncap, std::max(want, mp.slot_used_ub));
+    }
+    if (ncap > mp.feat_capacity) {
+      size_t free_b = 0, total_b = 0;
+      CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+      const long long grow_bytes = (ncap - mp.feat_capacity) * block_bytes;
+      if (grow_bytes + (1LL << 30) > (long long)free_b)
+        return fail(NVBX_ERR_OUT_OF_MEMORY, "feature arena: %lld more blocks (%.1f GiB) do not fit the %.1f GiB free",
+                    ncap - mp.feat_capacity, grow_bytes / 1073741824.0, free_b / 1073741824.0);
+      if ((rc = grow_feats(m, mp, (int)ncap, stream))) return rc;
+    }
   }
   mp.feat_used_ub = want;
   return NVBX_OK;
@@ -666,12 +694,25 @@ int timing_end(nvbx_mapper* m, int which, cudaStream_t stream) {
   return NVBX_OK;
 }
 
-int gather_variant() {  // tuning hook: NVBX_GATHER_VARIANT=0..3 (default 0; see profiles/r01b_gather_variants.md)
-  static const int v = [] {
-    const char* e = getenv("NVBX_GATHER_VARIANT");
-    return e ? atoi(e) : 0;
-  }();
-  return v;
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+// Schedule of the feature gather (tuning hooks; profiles/r01b_gather_variants.md, r01i_gather_schedule.md):
+// NVBX_GATHER_VARIANT / NVBX_GATHER_DYN / NVBX_GATHER_TICKET at load, nvbx_set_gather_tuning at run time.
+constexpr int kDefaultGatherVariant = 4;  // static deal + item prefetch (profiles/r01i_gather_schedule.md)
+int g_gather_tuning[3] = {-1, -1, -1};
+int gather_variant() {
+  if (g_gather_tuning[0] < 0) g_gather_tuning[0] = std::max(0, env_int("NVBX_GATHER_VARIANT", kDefaultGatherVariant));
+  return g_gather_tuning[0];
+}
+int gather_dyn_permille() {  // share of the units handed out by ticket (k_feature_gather_dyn)
+  if (g_gather_tuning[1] < 0) g_gather_tuning[1] = std::min(1000, std::max(0, env_int("NVBX_GATHER_DYN", 0)));
+  return g_gather_tuning[1];
+}
+int gather_ticket_units() {
+  if (g_gather_tuning[2] < 0) g_gather_tuning[2] = std::min(64, std::max(1, env_int("NVBX_GATHER_TICKET", 4)));
+  return g_gather_tuning[2];
 }
 
 template <int CH>
@@ -688,8 +729,20 @@ int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, 
     case 3:
       LAUNCH((k_feature_gather<CH, 1, 8>), persistent_grid(m, 8), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
       break;
-    default:
+    case 5:
+      LAUNCH((k_feature_gather_dyn<CH, 512, 2>), persistent_grid(m, 2), 512, 0, stream, mp.dev, mp.items.p,
+             (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
+      break;
+    case 6:
+      LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 5), 256, 0, stream, mp.dev, mp.items.p,
+             (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
+      break;
+    case 0:
       LAUNCH((k_feature_gather<CH, 1, 4>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
+      break;
+    default:
+      LAUNCH((k_feature_gather_dyn<CH, 256, 4>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p,
+             (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
   }
   return timing_end(m, 0, stream);
 }
@@ -1053,7 +1106,15 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
   out->cand_bound = cand_bound;
   int* band_list;
   if (color_parity < 0) {
-    if ((rc = ensure_feats(m, mp, cand_bound, stream))) return rc;
+    int tile_cells = 32;  // the tiling of the band-select launch below
+    while (tile_cells < 256 && (entry->bound + tile_cells - 1) / tile_cells > 2 * m->sm_count) tile_cells <<= 1;
+    const int n_tiles = (entry->bound + tile_cells - 1) / tile_cells;
+    auto count_new = [&]() -> int {
+      LAUNCH(k_band_count, std::max(1, std::min(n_tiles, persistent_grid(m, 4))), 256, 0, stream, mp.dev, pv, trunc,
+             tile_cells, n_tiles);
+      return NVBX_OK;
+    };
+    if ((rc = ensure_feats(m, mp, cand_bound, stream, count_new))) return rc;
     if ((rc = mp.band_slots.ensure((size_t)cand_bound, stream))) return rc;
     if ((rc = mp.newfeat_slots.ensure((size_t)cand_bound, stream))) return rc;
     const long long chunk_blocks = std::min<long long>(cand_bound, kFeatureChunkBlocks);
@@ -1842,6 +1903,15 @@ int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream_v) {
   if (rc) return rc;
   Map& mp = *m->maps[map_id];
   CUDA_TRY(cudaMemsetAsync(mp.d_ctrl->counters, 0, sizeof(unsigned long long) * kCntNum, (cudaStream_t)stream_v));
+  return NVBX_OK;
+}
+
+int nvbx_set_gather_tuning(int variant, int dyn_permille, int ticket_units) {
+  if (variant < 0 || variant > 6 || dyn_permille < 0 || dyn_permille > 1000 || ticket_units < 1 || ticket_units > 64)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "gather tuning out of range (variant 0..6, permille 0..1000, ticket 1..64)");
+  g_gather_tuning[0] = variant;
+  g_gather_tuning[1] = dyn_permille;
+  g_gather_tuning[2] = ticket_units;
   return NVBX_OK;
 }
 

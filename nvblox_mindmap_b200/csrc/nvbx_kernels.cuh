@@ -30,9 +30,11 @@ __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 // in griddepcontrol.wait); wait blocks until the PREVIOUS kernel has completed and its writes are
 // visible.  Net effect: the ~2-3 us launch latency of each of the 6 kernels of a frame is hidden behind
 // its predecessor.  Nothing produced by an earlier kernel may be read before pdl_prologue().
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() {
-  asm volatile("griddepcontrol.launch_dependents;");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_trigger();
+  pdl_wait();
 }
 
 __device__ __forceinline__ void count_add(const MapDev& m, int id, unsigned long long v) {
@@ -92,7 +94,13 @@ struct RaycastFrame {
 
 template <bool SMEM>
 __global__ void __launch_bounds__(256) k_raycast_mark(RaycastFrame f, unsigned* gbits, int* entry_count) {
-  pdl_prologue();
+  // SMEM: the rays are marched BEFORE griddepcontrol.wait, i.e. while the previous kernels of the stream (the
+  // last frame's feature gather) drain.  Until the wait this kernel reads only its arguments and the caller's
+  // depth image and writes only shared memory; the depth image was produced by an operation that is not one of
+  // this library's programmatic launches (a copy, a torch kernel), and such an operation is fully ordered with
+  // respect to the launches on either side of it.  Every global write happens after the wait.
+  pdl_trigger();
+  if (!SMEM) pdl_wait();
   extern __shared__ unsigned s_bits[];
   const ViewGrid& g = f.g;
   const int n_words = (g.n_cells + 31) >> 5;
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(256) k_raycast_mark(RaycastFrame f, unsigned* 
     for (int w = threadIdx.x; w < n_words; w += 256) s_bits[w] = 0u;
     __syncthreads();
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *entry_count = 0;  // consumed by k_view_compact_alloc (next launch)
+  if (!SMEM && blockIdx.x == 0 && threadIdx.x == 0) *entry_count = 0;  // consumed by k_view_compact_alloc (next launch)
   const int stride_y = g.sx, stride_z = g.sx * g.sy;
 
   for (int tile = blockIdx.x; tile < f.n_tiles; tile += gridDim.x) {
@@ -157,6 +165,8 @@ __global__ void __launch_bounds__(256) k_raycast_mark(RaycastFrame f, unsigned* 
   }
   if (SMEM) {
     __syncthreads();
+    pdl_wait();
+    if (blockIdx.x == 0 && threadIdx.x == 0) *entry_count = 0;
     for (int w = threadIdx.x; w < n_words; w += 256) {
       const unsigned v = s_bits[w];
       if (v && (__ldcg(&gbits[w]) & v) != v) atomicOr(&gbits[w], v);
@@ -437,6 +447,7 @@ struct PlanesView {
   Pose T_C_L;
   float vmin_x, vmin_y, vmax_x, vmax_y;
 };
+constexpr int kBandCountOnly = -2;  // band_select_tile mode: count the band blocks that have no feature block yet
 
 // One tile = `tile_cells` consecutive cells of the AABB (a multiple of 32, <= 256): phase 1 tests one cell
 // per thread and compacts the surviving slots into shared memory, phase 2 deals them to the CTA's warps.
@@ -491,6 +502,10 @@ __device__ __forceinline__ void band_select_tile(const MapDev& m, const PlanesVi
     for (int j = 0; j < 8; ++j)
       hit |= (q[j].y > 0.0f && fabsf(q[j].x) < trunc) || (q[j].w > 0.0f && fabsf(q[j].z) < trunc);
     if (!__any_sync(0xffffffffu, hit)) continue;
+    if (color_parity == kBandCountOnly) {  // k_band_count: how many feature blocks would this frame allocate?
+      if (lane == 0 && m.blk_feat[s] < 0) atomicAdd(&m.ctrl->list_count, 1);
+      continue;
+    }
     if (lane == 0 && color_parity >= 0) {
       int flag = 0;
       const uint8_t layers = m.blk_layers[s];
@@ -518,7 +533,7 @@ __device__ __forceinline__ void band_select_tile(const MapDev& m, const PlanesVi
       if (m.blk_feat[s] >= 0) band_slots[atomicAdd(&m.ctrl->band_count, 1)] = s | flag;
     }
   }
-  if (threadIdx.x == 0 && n_cand && color_parity < 0) count_add(m, kCntFeatCandidateBlocks, (unsigned)n_cand);
+  if (threadIdx.x == 0 && n_cand && color_parity == -1) count_add(m, kCntFeatCandidateBlocks, (unsigned)n_cand);
   __syncthreads();  // s_cand / s_ncand are reused by the CTA's next tile
 }
 
@@ -704,6 +719,19 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
 #endif
 }
 
+// The read-only twin of the band selection: ctrl->list_count += band blocks of this view that have no feature
+// block yet.  Launched only when the pessimistic bound of the frame (every candidate block gets a feature
+// block) would not fit the feature arena and is too large to simply allocate (ensure_feats): the arena then
+// grows by the exact figure.
+__global__ void __launch_bounds__(256) k_band_count(MapDev m, PlanesView view, float trunc, int tile_cells,
+                                                    int n_tiles) {
+  pdl_prologue();
+  __shared__ int s_cand[256];
+  __shared__ int s_ncand;
+  for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x)
+    band_select_tile(m, view, trunc, nullptr, nullptr, tile, tile_cells, s_cand, &s_ncand, kBandCountOnly);
+}
+
 // ================================================================================================
 // a8. Feature integration -- THE hot path, in two kernels.
 //
@@ -795,6 +823,7 @@ __global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* _
   const int vx = t >> 6, vy = (t >> 3) & 7, vz = t & 7;
   const int C = m.C;
   unsigned long long n_updated = 0;
+  if (blockIdx.x == 0 && t == 0) m.ctrl->gather_ticket = 0;  // consumed by k_feature_gather_dyn (next launch)
 
   // Zero-fill the feature blocks allocated by this frame (blox_impl.h:92-97), every CTA taking an equal
   // slice of each, so that a 794 KB block costs each SM a few KB; the gather kernel runs after us.
@@ -935,6 +964,98 @@ __global__ void __launch_bounds__(256, CTAS) k_feature_gather(MapDev m, const Fe
         if (cvec[k] == 0) dst[nvec] = make_uint4((unsigned)it[k].wnew, 0u, 0u, 0u);  // weight + zero padding
       }
     }
+  }
+  if (last_chunk && blockIdx.x == 0 && threadIdx.x == 0) {
+    m.ctrl->last_band_count = m.ctrl->band_count;
+    m.ctrl->band_count = 0;  // ready for the next frame's band_select_tile
+    m.ctrl->newfeat_count = 0;
+  }
+}
+
+// Same units, same arithmetic, different SCHEDULE: the first `n_static` units are dealt round-robin as above,
+// the rest are handed out through an atomic ticket (`tk` units per grab) so that no warp idles while others
+// still drain their share -- under a saturated HBM queue the per-warp finishing times of a static deal spread
+// by a few microseconds, which is a sixth of a 24 us kernel.  The next unit's work item (and, in the dynamic
+// part, its ticket) is fetched while the current unit's four pixel loads are in flight, and the first item
+// load does not wait for item_count (clamped to the list's capacity, discarded if past the end).
+// `ticket` is m.ctrl->gather_ticket, zeroed by k_feature_geometry (the launch before us in stream order).
+template <int CH, int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS) k_feature_gather_dyn(MapDev m, const FeatItem* __restrict__ items,
+                                                                      int items_cap, FeatFrame f, int last_chunk,
+                                                                      int dyn_permille, int tk) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int warps_total = gridDim.x * (THREADS >> 5);
+  const int warp = blockIdx.x * (THREADS >> 5) + (threadIdx.x >> 5);
+  const int C = m.C;
+  const int nvec = C >> 3;
+  const int ch_per_item = CH > 0 ? CH : ((nvec + 31) >> 5);
+  FeatItem cur;  // speculative: issued together with the item_count load
+  *reinterpret_cast<uint4*>(&cur) =
+      __ldg(reinterpret_cast<const uint4*>(items + min(warp / ch_per_item, items_cap - 1)));
+  const int n_items = m.ctrl->item_count;
+  const long long n_units = (long long)n_items * ch_per_item;
+  const long long rounds = (n_units * (1000 - dyn_permille) / 1000) / warps_total;
+  const long long n_static = dyn_permille == 0 ? n_units : rounds * warps_total;  // 0: no ticket at all
+  const __half2 w1 = __half2half2(__ushort_as_half(f.h_w1));
+  const __half2 w2 = __half2half2(__ushort_as_half(f.h_w2));
+  const size_t row_vecs = (size_t)(m.row >> 3);
+  int* ticket = &m.ctrl->gather_ticket;
+
+  long long q = warp;
+  int left = 0;  // units of the current ticket not yet started
+  if (q >= n_static) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(ticket, tk);
+    q = n_static + __shfl_sync(0xffffffffu, t, 0);
+    left = tk - 1;
+    if (q < n_units) *reinterpret_cast<uint4*>(&cur) = __ldg(reinterpret_cast<const uint4*>(items + q / ch_per_item));
+  }
+  while (q < n_units) {
+    const int item = (int)(q / ch_per_item);
+    const int cvec = (int)(q - (long long)item * ch_per_item) * 32 + lane;
+    const bool live = CH != 0 || cvec < nvec;
+    uint4 a00, a01, a10, a11;
+    if (live) {
+      const uint4* p00 = reinterpret_cast<const uint4*>(f.img + (size_t)cur.pix * C) + cvec;
+      const uint4* p01 = p00 + (size_t)f.cols * nvec;
+      a00 = ldg_nc(p00);
+      a10 = ldg_nc(p00 + nvec);
+      a01 = ldg_nc(p01);
+      a11 = ldg_nc(p01 + nvec);
+    }
+    // next unit (and its item) while the pixel loads fly
+    long long qn;
+    if (q + warps_total < n_static) {
+      qn = q + warps_total;
+    } else if (dyn_permille == 0) {
+      qn = n_units;
+    } else if (q >= n_static && left > 0) {
+      qn = q + 1;
+      --left;
+    } else {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(ticket, tk);
+      qn = n_static + __shfl_sync(0xffffffffu, t, 0);
+      left = tk - 1;
+    }
+    FeatItem nxt;
+    *reinterpret_cast<uint4*>(&nxt) = make_uint4(0u, 0u, 0u, 0u);
+    if (qn < n_units) *reinterpret_cast<uint4*>(&nxt) = __ldg(reinterpret_cast<const uint4*>(items + qn / ch_per_item));
+    if (live) {
+      const int fslot = cur.row >> 9, vox = cur.row & 511;
+      uint4* dst = reinterpret_cast<uint4*>(feat_block(m, fslot)) + (size_t)vox * row_vecs;
+      const bool blend = (!cur.first) && f.read_old;
+      uint4 old;
+      if (blend) old = dst[cvec];
+      const __half hx = __ushort_as_half(cur.hx), hy = __ushort_as_half(cur.hy);
+      uint4 o = interp_vec(__half2half2(hx), __half2half2(hy), __half2half2(__hmul_rn(hx, hy)), a00, a01, a10, a11);
+      if (blend) o = blend_vec(old, o, w1, w2);
+      dst[cvec] = o;
+      if (cvec == 0) dst[nvec] = make_uint4((unsigned)cur.wnew, 0u, 0u, 0u);  // weight + zero padding
+    }
+    cur = nxt;
+    q = qn;
   }
   if (last_chunk && blockIdx.x == 0 && threadIdx.x == 0) {
     m.ctrl->last_band_count = m.ctrl->band_count;

@@ -90,7 +90,8 @@ struct Ctrl {
   int cband_count[2];  // colour band list length, double-buffered by frame parity (the consumer of one frame
                        // clears the other half, so no kernel both reads and resets the same counter)
   int last_cband_count;
-  int pad[2];
+  int gather_ticket;  // k_feature_gather_dyn's work ticket; zeroed by k_feature_geometry
+  int pad;
   unsigned long long counters[kCntNum];
 };
 

@@ -67,6 +67,29 @@ def test_c768_features_bit_exact():
     assert pair.check_mesh() > 0
 
 
+@pytest.mark.parametrize('variant,permille,ticket', [(0, 0, 1), (1, 300, 2), (4, 300, 2), (4, 1000, 1), (4, 0, 3), (5, 500, 4),
+                                                    (6, 150, 2)])
+@pytest.mark.parametrize('C,alpha', [(768, 1.0), (40, 0.3)])
+def test_gather_schedules_are_result_identical(variant, permille, ticket, C, alpha):
+    """Every schedule of the feature gather (static deal / ticketed tail, nvbx_set_gather_tuning) writes the
+    same bytes: strict-mode features stay bit-exact against the oracle, blended (alpha < 1) frames included."""
+    from nvblox_mindmap_b200 import _capi
+    lib = _capi.load()
+    assert lib.nvbx_set_gather_tuning(variant, permille, ticket) == 0
+    try:
+        mp, op = make_params(workspace=S.WS_CUBE_STACKING, alpha=alpha, strict=True)
+        pair = Pair(0.02, C, mp, op)
+        for i, T, K, depth, feat in orbit_frames(3, 80, 80, C, S.S_TABLE):
+            pair.depth(depth, T, K)
+            pair.features(feat, T, K)
+            assert pair.check_features(max_ulp=0) > 0
+        g, c = pair.gpu.counters(0), pair.cpu.counters()
+        assert g['feature_voxels_updated'] == c['feature_voxels_updated'] > 0
+    finally:
+        assert lib.nvbx_set_gather_tuning(4, 0, 4) == 0
+    assert lib.nvbx_set_gather_tuning(7, 0, 1) != 0 and lib.nvbx_set_gather_tuning(4, 1001, 1) != 0
+
+
 def test_decay_until_removed():
     """test_tsdf_decay.cpp DecayUntilRemoved: repeated decay frees every block (and its feature block)."""
     mp, op = make_params(workspace=S.WS_CUBE_STACKING, decay=0.5)

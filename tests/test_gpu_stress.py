@@ -1,0 +1,118 @@
+"""BASELINE configs[4] ("stress": 4 cameras 1024x1024, 1024-channel features, 1 cm voxels, a 20 x 20 x 4 m
+workspace) as parity-test cases:
+
+  * scaled down (192^2 images) against the oracle, bit for bit -- exercises the 3.1 M-cell level-1 index, the
+    C = 1024 (4 x 512-byte chunks) gather and several cameras per step;
+  * at the FULL frame size through size-independent properties, which check every voxel a 2 GiB frame touches
+    without an oracle run: the reference's known-answer `feature[c] = c` (NB/tests/test_feature_integrator.cpp:
+    131-158: every voxel with weight > 0 stores exactly c), alpha = 1 idempotence, weight saturation at
+    max_weight, the export holding exactly the meshed surface voxels inside the workspace.
+"""
+import numpy as np
+import pytest
+
+from tests import scenes as S
+from tests.parity_utils import Pair, make_params
+
+pytestmark = pytest.mark.gpu
+
+WS_STRESS = ((-10.0, -10.0, -0.5), (10.0, 10.0, 3.5))
+SCENE = dict(plane_z=0.0, boxes=[((0.5 * i - 1.0, 0.3 * i - 0.6, 0.0), (0.5 * i - 0.8, 0.3 * i - 0.4, 0.25))
+                                 for i in range(5)])
+
+
+def rig_poses(step, height=1.4, out=0.9):
+    """Four cameras on a rig that advances 5 cm per step, each looking down and outwards."""
+    c = np.array([0.05 * step, 0.0, height])
+    return [S.look_at(c, c + np.array([out * dx, out * dy, -height]), up=(0.0, 0.0, 1.0))
+            for dx, dy in ((1, 0), (0, 1), (-1, 0), (0, -1))]
+
+
+def test_stress_shape_scaled_bit_exact():
+    mp, op = make_params(workspace=WS_STRESS, max_dist=1.5)
+    pair = Pair(0.01, 1024, mp, op)
+    H = W = 192
+    K = S.intrinsics(W, H)
+    for step in range(2):
+        if step:
+            pair.decay()
+        for cam, T in enumerate(rig_poses(step, height=0.45, out=0.3)[:3]):
+            depth = S.render_depth(K, H, W, T, **SCENE)
+            pair.depth(depth, T, K)
+            g, c = pair.last_block_list(0)
+            assert np.array_equal(g, c) and len(g) > 0
+            pair.features(S.feature_frame(H, W, 1024, 90 + 4 * step + cam), T, K)
+            g, c = pair.last_block_list(1)
+            assert np.array_equal(g, c) and len(g) > 0
+    assert pair.check_tsdf() > 1000
+    assert pair.check_features(max_ulp=1) > 100
+    assert pair.check_mesh() > 1000
+    gc, cc = pair.gpu.counters(0), pair.cpu.counters()
+    for k in ('tsdf_voxels_updated', 'feature_voxels_updated', 'feature_band_blocks', 'tsdf_blocks_allocated',
+              'feature_blocks_allocated', 'blocks_deallocated', 'mesh_vertices'):
+        assert gc[k] == cc[k], (k, gc[k], cc[k])
+
+
+def test_stress_full_size_frame_properties():
+    import torch
+    from nvblox_torch.constants import constants
+    from nvblox_torch.mapper import Mapper
+    C_FEAT, H, W = 1024, 1024, 1024
+    if torch.cuda.mem_get_info()[0] < 40 * 2 ** 30:
+        pytest.skip('needs 40 GiB of free HBM')
+    constants.set_feature_array_num_elements(C_FEAT)
+    mp, _ = make_params(workspace=WS_STRESS)
+    m = Mapper(voxel_sizes_m=0.01, mapper_parameters=mp)
+    K = S.intrinsics(W, H)
+    K_t = torch.from_numpy(K)
+    # feature[c] = c, exactly representable in fp16 up to 2048: any convex combination of equal values is exact
+    ramp = torch.arange(C_FEAT, device='cuda', dtype=torch.float16)
+    frame = ramp.expand(H, W, C_FEAT).contiguous()
+    poses = rig_poses(0)[:2]
+    depths = [torch.from_numpy(S.render_depth(K, H, W, T, **SCENE)).cuda() for T in poses]
+    upd = []
+    for T, d in zip(poses, depths):            # both depth frames first: every feature pass sees the same TSDF
+        m.add_depth_frame(d, torch.from_numpy(T), K_t)
+    for rep in range(7):                       # max_weight = 5: the weight saturates on the 5th pass
+        m.reset_counters(0)
+        for T in poses:
+            m.add_feature_frame(frame, torch.from_numpy(T), K_t)
+        upd.append(m.counters(0)['feature_voxels_updated'])
+    assert upd[0] > 300000 and len(set(upd)) == 1, upd       # same voxels every pass
+    # the pessimistic arena bound of these views (one ~1 MB feature block per candidate TSDF block) is far
+    # beyond kFeatPessimisticBytes: the arena must have grown by exact device counts instead
+    n_tsdf = m.tsdf_layer_view(0).num_blocks()
+    layer = m.feature_layer_view(0)
+    n_feat = layer.num_blocks()
+    assert n_feat <= layer.num_allocated_blocks() <= 1.25 * n_feat + 1100   # arena grew by exact counts
+    assert n_tsdf > 12000 and 1000 < n_feat < n_tsdf // 2, (n_tsdf, n_feat)
+    assert torch.cuda.mem_get_info()[0] > 100 * 2 ** 30, 'feature arena over-allocated'
+    blocks, _ = layer.get_all_blocks()
+    assert len(blocks) == n_feat
+    n_seen = n_sat = 0
+    for b0 in range(0, n_feat, 256):            # checked on the device, 256 blocks (268 MB) at a time
+        blk = torch.stack(blocks[b0:b0 + 256])  # [n, 8, 8, 8, C + 1]
+        w, f = blk[..., C_FEAT].float(), blk[..., :C_FEAT]
+        seen = w > 0
+        n_seen += int(seen.sum())
+        n_sat += int((w == 5.0).sum())
+        # weights are integers 1..5 (alpha = 1 per pass, two overlapping cameras), saturated after 5 passes
+        assert bool(((w == w.round()) & (w >= 0) & (w <= 5))[seen].all())
+        assert bool((f[seen] == ramp).all())    # the known answer: feature[c] == c exactly
+        assert not bool(f[~seen].any())         # untouched voxels of a feature block stay zero
+    assert n_seen > 300000 and n_sat > 0.9 * n_seen, (n_seen, n_sat)
+    del blocks, blk, w, f, seen
+
+    # export: every vertex inside the workspace, one feature row per vertex, rows are the ramp or zero
+    m.update_feature_mesh(0)
+    mesh = m.get_feature_mesh(0)
+    v, vf = mesh.vertices(), mesh.vertex_features()
+    assert v.shape[0] == vf.shape[0] > 100000 and vf.shape[1] == C_FEAT
+    lo = torch.tensor(WS_STRESS[0], device=v.device)
+    hi = torch.tensor(WS_STRESS[1], device=v.device)
+    assert bool(((v >= lo) & (v <= hi)).all())
+    assert abs(float(v[:, 2].median())) < 0.011  # the floor
+    nz = vf.abs().sum(1) > 0
+    assert float(nz.float().mean()) > 0.2     # far floor is meshed but beyond the sphere-traced range
+    assert bool((vf[nz] == ramp).all())
+    assert m.counters(0)['mesh_vertices'] == v.shape[0]
