@@ -333,7 +333,7 @@ def run_ours(args, rank, world, local_rank):
                                    'h2d_bytes_per_step': H * W * 4 + H * W * C_FEAT * 2}},
             'gpu_launches': launches,
             'clocks': clocks,
-            'roofline': {'bound': 'hbm', 'kernel': 'k_feature_gather_dyn<3,256,4> (static deal, item prefetch)', 'achieved': achieved, 'peak': peak,
+            'roofline': {'bound': 'hbm', 'kernel': 'k_feature_gather_dyn<3,256,5> on 4 CTAs/SM (static deal, item prefetch)', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None, 'traffic': traffic,
                          'traffic_source': traffic_src,
                          'peak_source': peak_src, 'kernel_ms': kms, 'algorithmic_bytes_per_launch': b_feat,
@@ -382,7 +382,7 @@ def sweep_gather(args, lib, mapper, depths, poses, feats, K_t, step):
     workload -- live kernel duration (library-placed CUDA events) and whole-frame device time."""
     import torch
     n_total = args.warmup + args.steps
-    grid = [(0, 0, 1), (1, 0, 1), (2, 0, 1), (4, 0, 1), (5, 0, 1), (6, 0, 1), (4, 50, 4), (6, 50, 4)]
+    grid = [(0, 0, 1), (4, 0, 1), (5, 0, 1), (6, 0, 1), (7, 0, 1), (8, 0, 1), (9, 0, 1)]
     rows = []
     for rep in range(2):
         for (v, pm, tk) in grid:
@@ -400,13 +400,13 @@ def sweep_gather(args, lib, mapper, depths, poses, feats, K_t, step):
             rows.append({'rep': rep, 'variant': v, 'dyn_permille': pm, 'ticket': tk, 'gather_us': 1000.0 * kms,
                          'frame_us': 1000.0 * e0.elapsed_time(e1) / args.steps})
             print(json.dumps(rows[-1]), flush=True)
-    lib.nvbx_set_gather_tuning(4, 0, 4)
+    lib.nvbx_set_gather_tuning(7, 0, 4)
 
 
 def ncu_traffic_bytes():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary
-    (profiles/r01f_feature_gather.md: dram__bytes_read.sum + dram__bytes_write.sum, first capture)."""
-    path = os.path.join(ROOT, 'profiles', 'r01f_feature_gather.md')
+    (profiles/r01l_feature_gather.md: dram__bytes_read.sum + dram__bytes_write.sum, first capture)."""
+    path = os.path.join(ROOT, 'profiles', 'r01l_feature_gather.md')
     try:
         rd = wr = None
         for line in open(path):
@@ -416,7 +416,7 @@ def ncu_traffic_bytes():
             if len(cells) > 3 and cells[1] == 'dram__bytes_write.sum' and wr is None:
                 wr = float(cells[2]) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}[cells[3]]
         if rd is not None and wr is not None:
-            return rd + wr, 'profiles/r01f_feature_gather.md (ncu --set full, one launch of the same workload)'
+            return rd + wr, 'profiles/r01l_feature_gather.md (ncu --set full, one launch of the same workload)'
     except Exception:
         pass
     return None, None

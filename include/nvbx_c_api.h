@@ -327,7 +327,7 @@ int nvbx_set_kernel_timing(nvbx_mapper* m, int enabled);
 int64_t nvbx_kernel_timing_report(nvbx_mapper* m, char* json, int64_t capacity);
 int nvbx_get_kernel_timing(nvbx_mapper* m, int which, double* total_ms, int64_t* launches);
 /* Process-wide schedule of the feature gather kernel (tuning aid; results are identical for every setting):
- * variant 0..3 = static round-robin deal <units in flight, CTAs/SM>, 4..6 = k_feature_gather_dyn with
+ * variant 0..3 = static round-robin deal <units in flight, CTAs/SM>, 4..9 = k_feature_gather_dyn with
  * `dyn_permille`/1000 of the units handed out by atomic ticket, `ticket_units` per grab. */
 int nvbx_set_gather_tuning(int variant, int dyn_permille, int ticket_units);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
@@ -341,6 +341,11 @@ int64_t nvbx_debug_last_block_list(nvbx_mapper* m, int map_id, int which, int32_
                                    void* stream);
 /* last synthetic depth image (device float[rows*cols], sphere_tracer.cu:191-236) */
 int nvbx_debug_last_synthetic_depth(nvbx_mapper* m, int map_id, const void** ptr, int* rows, int* cols);
+/* Profile build only (NVBX_PROFILE=1 -> libnvbx_prof.so; NVBX_ERR_UNSUPPORTED otherwise): the pipeline timeline.
+ * out[64][8][2] uint64 = (%globaltimer ns when the first CTA passed griddepcontrol.wait, ns when the last CTA
+ * ended) of kernel k = 0 raycast, 1 tsdf, 2 trace+band, 3 geometry, 4 gather, 5 raycast's pre-wait march, for
+ * frame (n mod 64).  Synchronises the device; reset != 0 re-arms the stamps.  tools/pipeline_timeline.py. */
+int nvbx_debug_profile_stamps(nvbx_mapper* m, uint64_t* out, int reset);
 
 const char* nvbx_version(void);
 

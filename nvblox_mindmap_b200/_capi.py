@@ -23,7 +23,7 @@ API_SYMBOLS = [
     'nvbx_export_points', 'nvbx_gather_points', 'nvbx_num_blocks', 'nvbx_num_allocated_blocks',
     'nvbx_num_allocated_bytes', 'nvbx_voxel_size', 'nvbx_get_block_indices', 'nvbx_get_block_ptr',
     'nvbx_allocate_block', 'nvbx_query_tsdf', 'nvbx_query_features', 'nvbx_get_counters',
-    'nvbx_reset_counters', 'nvbx_set_gather_tuning', 'nvbx_set_kernel_timing', 'nvbx_get_kernel_timing', 'nvbx_kernel_timing_report', 'nvbx_kernel_launch_count', 'nvbx_debug_last_block_list',
+    'nvbx_reset_counters', 'nvbx_set_gather_tuning', 'nvbx_set_kernel_timing', 'nvbx_get_kernel_timing', 'nvbx_kernel_timing_report', 'nvbx_kernel_launch_count', 'nvbx_debug_last_block_list', 'nvbx_debug_profile_stamps',
     'nvbx_debug_last_synthetic_depth', 'nvbx_version',
 ]
 
@@ -105,6 +105,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         L.nvbx_debug_last_block_list.restype = C.c_int64
         L.nvbx_debug_last_synthetic_depth.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int),
                                                       C.POINTER(C.c_int)]
+        L.nvbx_debug_profile_stamps.argtypes = [vp, C.POINTER(C.c_uint64), C.c_int]
         L.nvbx_version.restype = C.c_char_p
         _lib = L
         return _lib

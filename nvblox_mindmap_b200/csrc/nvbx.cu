@@ -700,7 +700,7 @@ int env_int(const char* name, int dflt) {
 }
 // Schedule of the feature gather (tuning hooks; profiles/r01b_gather_variants.md, r01i_gather_schedule.md):
 // NVBX_GATHER_VARIANT / NVBX_GATHER_DYN / NVBX_GATHER_TICKET at load, nvbx_set_gather_tuning at run time.
-constexpr int kDefaultGatherVariant = 4;  // static deal + item prefetch (profiles/r01i_gather_schedule.md)
+constexpr int kDefaultGatherVariant = 7;  // 48-register static deal + item prefetch on 4 CTAs / SM (profiles/r01k_gather_schedule.md)
 int g_gather_tuning[3] = {-1, -1, -1};
 int gather_variant() {
   if (g_gather_tuning[0] < 0) g_gather_tuning[0] = std::max(0, env_int("NVBX_GATHER_VARIANT", kDefaultGatherVariant));
@@ -739,6 +739,18 @@ int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, 
       break;
     case 0:
       LAUNCH((k_feature_gather<CH, 1, 4>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
+      break;
+    case 7:  // the 48-register build on 4 CTAs / SM: leaves registers for two CTAs of the next frame's raycast
+      LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p,
+             (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
+      break;
+    case 8:
+      LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items.p,
+             (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
+      break;
+    case 9:
+      LAUNCH((k_feature_gather_dyn<CH, 256, 6>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p,
+             (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
       break;
     default:
       LAUNCH((k_feature_gather_dyn<CH, 256, 4>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p,
@@ -972,6 +984,7 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
                     (unsigned)(rf.start[2] - gs.g.mn.z) * (unsigned)gs.g.sx * (unsigned)gs.g.sy);
     rf.tiles_x = tiles_x;
     rf.n_tiles = n_tiles;
+    rf.ctrl = mp.d_ctrl;
     if (n_words <= (size_t)kRayBitmapWords) {
       LAUNCH(k_raycast_mark<true>, rgrid, 256, n_words * sizeof(unsigned), stream, rf, bits, entry->d_count);
     } else {
@@ -1158,8 +1171,24 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
     const int n_trace = reuse ? 0 : trace_tiles_x * ((srows + 15) / 16);
     const int n_band = std::max(1, std::min(n_tiles, persistent_grid(m, 4)));
     key.valid = false;  // a failed launch leaves no valid image behind
-    LAUNCH(k_trace_and_band, n_trace + n_band, 256, 0, stream, mp.dev, tp, mp.synth.p, trace_tiles_x, n_trace, pv,
-           trunc, band_list, mp.newfeat_slots.p, tile_cells, n_tiles, color_parity);
+    static const int spec = env_int("NVBX_TRACE_SPEC", 1), ilp = env_int("NVBX_BAND_ILP", 2);
+#define NVBX_TB(S, I)                                                                                                \
+  LAUNCH((k_trace_and_band<S, I>), n_trace + n_band, 256, 0, stream, mp.dev, tp, mp.synth.p, trace_tiles_x, n_trace, \
+         pv, trunc, band_list, mp.newfeat_slots.p, tile_cells, n_tiles, color_parity)
+    if (spec == 1 && ilp == 1) {
+      NVBX_TB(1, 1);
+    } else if (spec == 1) {
+      NVBX_TB(1, 2);
+    } else if (spec == 2 && ilp == 1) {
+      NVBX_TB(2, 1);
+    } else if (spec == 2) {
+      NVBX_TB(2, 2);
+    } else if (ilp == 1) {
+      NVBX_TB(4, 1);
+    } else {
+      NVBX_TB(4, 2);
+    }
+#undef NVBX_TB
     key.T = T_L_C;
     key.cam = cam;
     key.trunc = trunc;
@@ -1907,8 +1936,8 @@ int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream_v) {
 }
 
 int nvbx_set_gather_tuning(int variant, int dyn_permille, int ticket_units) {
-  if (variant < 0 || variant > 6 || dyn_permille < 0 || dyn_permille > 1000 || ticket_units < 1 || ticket_units > 64)
-    return fail(NVBX_ERR_INVALID_ARGUMENT, "gather tuning out of range (variant 0..6, permille 0..1000, ticket 1..64)");
+  if (variant < 0 || variant > 9 || dyn_permille < 0 || dyn_permille > 1000 || ticket_units < 1 || ticket_units > 64)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "gather tuning out of range (variant 0..9, permille 0..1000, ticket 1..64)");
   g_gather_tuning[0] = variant;
   g_gather_tuning[1] = dyn_permille;
   g_gather_tuning[2] = ticket_units;
@@ -2011,6 +2040,26 @@ int64_t nvbx_debug_last_block_list(nvbx_mapper* m, int map_id, int which, int32_
     }
   }
   return n;
+}
+
+int nvbx_debug_profile_stamps(nvbx_mapper* m, uint64_t* out, int reset) {
+  if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper handle");
+#ifdef NVBX_PROFILE_COUNTERS
+  CUDA_TRY(cudaSetDevice(m->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  constexpr int n = 64 * 2 * kProfKernels;
+  if (out) CUDA_TRY(cudaMemcpyFromSymbol(out, g_prof, n * sizeof(unsigned long long)));
+  if (reset) {
+    std::vector<unsigned long long> init(n);
+    for (int i = 0; i < n; ++i) init[i] = (i & 1) ? 0ULL : ~0ULL;  // (min begin, max end) pairs
+    CUDA_TRY(cudaMemcpyToSymbol(g_prof, init.data(), n * sizeof(unsigned long long)));
+  }
+  return 64 * kProfKernels;
+#else
+  (void)out;
+  (void)reset;
+  return fail(NVBX_ERR_UNSUPPORTED, "timeline stamps need the NVBX_PROFILE=1 build (libnvbx_prof.so)");
+#endif
 }
 
 int nvbx_debug_last_synthetic_depth(nvbx_mapper* m, int map_id, const void** ptr, int* rows, int* cols) {

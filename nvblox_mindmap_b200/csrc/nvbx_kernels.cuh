@@ -41,6 +41,44 @@ __device__ __forceinline__ void count_add(const MapDev& m, int id, unsigned long
   atomicAdd(&m.ctrl->counters[id], v);
 }
 
+// ---- pipeline timeline (NVBX_PROFILE_COUNTERS builds; tools/pipeline_timeline.py) ------------------
+// Every kernel of a frame stamps %globaltimer when its first CTA passes griddepcontrol.wait and when its last
+// CTA ends, into g_prof[frame & 63][kernel]: what the PDL-chained pipeline really looks like in steady state,
+// which neither isolated event timings nor a serialising profiler can show.  The frame number is read from
+// counters that are stable while the stamping kernel runs (see prof_seq_*).
+enum { kProfRaycast = 0, kProfTsdf, kProfTrace, kProfGeometry, kProfGather, kProfRaycastPre, kProfKernels = 8 };
+#ifdef NVBX_PROFILE_COUNTERS
+__device__ unsigned long long g_prof[64 * 2 * kProfKernels];
+__device__ __forceinline__ unsigned long long prof_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int prof_seq_early(const Ctrl* c) {  // raycast / tsdf / trace of frame i: i feature frames done
+  return (int)*reinterpret_cast<const volatile unsigned long long*>(&c->counters[kCntFeatureFrames]);
+}
+__device__ __forceinline__ int prof_seq_late(const Ctrl* c) {  // geometry / gather of frame i: i + 1 depth frames done
+  return (int)*reinterpret_cast<const volatile unsigned long long*>(&c->counters[kCntDepthFrames]) - 1;
+}
+__device__ __forceinline__ void prof_begin(int seq, int k, unsigned long long t) {
+  atomicMin(&g_prof[((seq & 63) * kProfKernels + k) * 2], t);
+}
+__device__ __forceinline__ void prof_end(int seq, int k, unsigned long long t) {
+  atomicMax(&g_prof[((seq & 63) * kProfKernels + k) * 2 + 1], t);
+}
+#define PROF_BEGIN(seq, k)                       \
+  const int prof_seq_ = (seq);                   \
+  if (threadIdx.x == 0) prof_begin(prof_seq_, (k), prof_now())
+#define PROF_END(k)                              \
+  do {                                           \
+    __syncthreads();                             \
+    if (threadIdx.x == 0) prof_end(prof_seq_, (k), prof_now()); \
+  } while (0)
+#else
+#define PROF_BEGIN(seq, k)
+#define PROF_END(k)
+#endif
+
 // ================================================================================================
 // a2. Blocks in view by ray casting -- one thread per (subsampled) depth pixel, 3-D DDA over the view
 // AABB.  Follows combinedBlockIndicesInImageKernel (NB/src/integrators/view_calculator.cu:196-248) and
@@ -90,6 +128,7 @@ struct RaycastFrame {
   float shifted[3];  // s - start
   int lin0;          // linear (aliased) grid index of the start block
   int tiles_x, n_tiles;
+  const Ctrl* ctrl;  // profile builds: frame number for the timeline stamps
 };
 
 template <bool SMEM>
@@ -100,6 +139,9 @@ __global__ void __launch_bounds__(256) k_raycast_mark(RaycastFrame f, unsigned* 
   // this library's programmatic launches (a copy, a torch kernel), and such an operation is fully ordered with
   // respect to the launches on either side of it.  Every global write happens after the wait.
   pdl_trigger();
+#ifdef NVBX_PROFILE_COUNTERS
+  const unsigned long long prof_entry = prof_now();
+#endif
   if (!SMEM) pdl_wait();
   extern __shared__ unsigned s_bits[];
   const ViewGrid& g = f.g;
@@ -163,14 +205,25 @@ __global__ void __launch_bounds__(256) k_raycast_mark(RaycastFrame f, unsigned* 
       t_next[2] += z_min ? t_step[2] : 0.0f;
     }
   }
+#ifdef NVBX_PROFILE_COUNTERS
+  const unsigned long long prof_marched = prof_now();
+#endif
   if (SMEM) {
     __syncthreads();
     pdl_wait();
+    PROF_BEGIN(prof_seq_early(f.ctrl), kProfRaycast);
+#ifdef NVBX_PROFILE_COUNTERS
+    if (threadIdx.x == 0) {
+      prof_begin(prof_seq_, kProfRaycastPre, prof_entry);
+      prof_end(prof_seq_, kProfRaycastPre, prof_marched);
+    }
+#endif
     if (blockIdx.x == 0 && threadIdx.x == 0) *entry_count = 0;
     for (int w = threadIdx.x; w < n_words; w += 256) {
       const unsigned v = s_bits[w];
       if (v && (__ldcg(&gbits[w]) & v) != v) atomicOr(&gbits[w], v);
     }
+    PROF_END(kProfRaycast);
   }
 }
 
@@ -332,6 +385,7 @@ struct ViewSource {
 template <int MODE>
 __global__ void __launch_bounds__(512, 3) k_tsdf_update(MapDev m, ViewSource src, DepthFrame f) {
   pdl_prologue();
+  PROF_BEGIN(prof_seq_early(m.ctrl), kProfTsdf);
   __shared__ int s_off[513];
   __shared__ int s_warp[17];
   __shared__ int s_slot;
@@ -430,6 +484,7 @@ __global__ void __launch_bounds__(512, 3) k_tsdf_update(MapDev m, ViewSource src
     count_add(m, kCntTsdfBlocksInView, (unsigned long long)n);
     count_add(m, kCntDepthFrames, 1);
   }
+  PROF_END(kProfTsdf);
 }
 
 // ================================================================================================
@@ -455,12 +510,17 @@ constexpr int kBandCountOnly = -2;  // band_select_tile mode: count the band blo
 // color_parity < 0: feature frame (band blocks get a feature slot).  color_parity = 0 / 1: colour frame -- band
 // blocks get the colour layer bit (their ColorVoxel payload lives at the slot id, like the TSDF payload) and are
 // appended to the colour band list counted by ctrl->cband_count[color_parity].
+template <int ILP>
 __device__ __forceinline__ void band_select_tile(const MapDev& m, const PlanesView& view, float trunc,
                                                  int* band_slots, int* newfeat_slots, int tile, int tile_cells,
-                                                 int* s_cand, int* s_ncand, int color_parity) {
+                                                 int* s_cand, int* s_ncand, int* s_band, int* s_nband,
+                                                 int color_parity) {
   const ViewGrid& g = view.g;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) *s_ncand = 0;
+  if (threadIdx.x == 0) {
+    *s_ncand = 0;
+    *s_nband = 0;
+  }
   __syncthreads();
   const int i = tile * tile_cells + threadIdx.x;
   int slot = -1;
@@ -491,46 +551,85 @@ __device__ __forceinline__ void band_select_tile(const MapDev& m, const PlanesVi
   }
   __syncthreads();
   const int n_cand = *s_ncand;
-  for (int k = warp; k < n_cand; k += (blockDim.x >> 5)) {
-    const int s = s_cand[k];
-    const float4* p = reinterpret_cast<const float4*>(tsdf_block(m, s));
-    float4 q[8];
+  // phase 2a: one warp per candidate, two candidates (sixteen 128-bit loads per lane) in flight; band blocks are
+  // collected in shared memory so that nothing below waits on a global atomic per block
+  const int nwarps = blockDim.x >> 5;
+  for (int k = warp; k < n_cand; k += ILP * nwarps) {
+    const int s0 = s_cand[k];
+    const bool two = ILP == 2 && k + nwarps < n_cand;
+    const int s1 = two ? s_cand[k + nwarps] : s0;
+    const float4* p0 = reinterpret_cast<const float4*>(tsdf_block(m, s0));
+    const float4* p1 = reinterpret_cast<const float4*>(tsdf_block(m, s1));
+    float4 q0[8], q1[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) q[j] = p[j * 32 + lane];  // two voxels each: (d, w, d, w)
-    bool hit = false;
+    for (int j = 0; j < 8; ++j) q0[j] = p0[j * 32 + lane];  // two voxels each: (d, w, d, w)
+    if (two) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q1[j] = p1[j * 32 + lane];
+    }
+    bool hit0 = false, hit1 = false;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      hit |= (q[j].y > 0.0f && fabsf(q[j].x) < trunc) || (q[j].w > 0.0f && fabsf(q[j].z) < trunc);
-    if (!__any_sync(0xffffffffu, hit)) continue;
-    if (color_parity == kBandCountOnly) {  // k_band_count: how many feature blocks would this frame allocate?
-      if (lane == 0 && m.blk_feat[s] < 0) atomicAdd(&m.ctrl->list_count, 1);
-      continue;
+      hit0 |= (q0[j].y > 0.0f && fabsf(q0[j].x) < trunc) || (q0[j].w > 0.0f && fabsf(q0[j].z) < trunc);
+    if (two) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        hit1 |= (q1[j].y > 0.0f && fabsf(q1[j].x) < trunc) || (q1[j].w > 0.0f && fabsf(q1[j].z) < trunc);
     }
-    if (lane == 0 && color_parity >= 0) {
-      int flag = 0;
-      const uint8_t layers = m.blk_layers[s];
-      if (!(layers & kLayerColorBit)) {
-        m.blk_layers[s] = layers | kLayerColorBit;
-        atomicAdd(&m.ctrl->n_color, 1);
-        count_add(m, kCntColorBlocksAllocated, 1);
-        flag = kNewFlag;  // k_color_update writes all 512 voxels of such a block (gray, weight 0 where not fused)
-      }
-      band_slots[atomicAdd(&m.ctrl->cband_count[color_parity], 1)] = s | flag;
-    } else if (lane == 0) {
-      int flag = 0;
-      if (m.blk_feat[s] < 0) {
-        const int fs =
-            pop_id(&m.ctrl->feat_free_top, &m.ctrl->feat_high, m.feat_free, m.feat_capacity, &m.ctrl->overflow);
-        if (fs >= 0) {
-          m.blk_feat[s] = fs;
-          m.blk_layers[s] |= kLayerFeatBit;
-          atomicAdd(&m.ctrl->n_feat, 1);
-          count_add(m, kCntFeatBlocksAllocated, 1);
-          newfeat_slots[atomicAdd(&m.ctrl->newfeat_count, 1)] = fs;
-          flag = kNewFlag;  // zero-filled (cooperatively, by all CTAs) in k_feature_geometry
+    const bool any0 = __any_sync(0xffffffffu, hit0), any1 = __any_sync(0xffffffffu, hit1);
+    if (lane == 0) {
+      if (any0) s_band[atomicAdd(s_nband, 1)] = s0;
+      if (any1) s_band[atomicAdd(s_nband, 1)] = s1;
+    }
+  }
+  __syncthreads();
+  // phase 2b: one THREAD per band block -- layer bookkeeping and feature-slot allocation of all blocks of the
+  // tile proceed in parallel, and each warp appends its blocks to the global list with one atomic
+  const int n_band = *s_nband;
+  for (int j0 = 0; j0 < n_band; j0 += blockDim.x) {
+    const int j = j0 + threadIdx.x;
+    bool has = false;
+    int out = 0;
+    if (j < n_band) {
+      const int s = s_band[j];
+      if (color_parity == kBandCountOnly) {  // k_band_count: how many feature blocks would this frame allocate?
+        if (m.blk_feat[s] < 0) atomicAdd(&m.ctrl->list_count, 1);
+      } else if (color_parity >= 0) {
+        int flag = 0;
+        const uint8_t layers = m.blk_layers[s];
+        if (!(layers & kLayerColorBit)) {
+          m.blk_layers[s] = layers | kLayerColorBit;
+          atomicAdd(&m.ctrl->n_color, 1);
+          count_add(m, kCntColorBlocksAllocated, 1);
+          flag = kNewFlag;  // k_color_update writes all 512 voxels of such a block (gray, weight 0 where not fused)
         }
+        has = true;
+        out = s | flag;
+      } else {
+        int flag = 0;
+        int fs = m.blk_feat[s];
+        if (fs < 0) {
+          fs = pop_id(&m.ctrl->feat_free_top, &m.ctrl->feat_high, m.feat_free, m.feat_capacity, &m.ctrl->overflow);
+          if (fs >= 0) {
+            m.blk_feat[s] = fs;
+            m.blk_layers[s] |= kLayerFeatBit;
+            atomicAdd(&m.ctrl->n_feat, 1);
+            count_add(m, kCntFeatBlocksAllocated, 1);
+            newfeat_slots[atomicAdd(&m.ctrl->newfeat_count, 1)] = fs;
+            flag = kNewFlag;  // zero-filled (cooperatively, by all CTAs) in k_feature_geometry
+          }
+        }
+        has = fs >= 0;
+        out = s | flag;
       }
-      if (m.blk_feat[s] >= 0) band_slots[atomicAdd(&m.ctrl->band_count, 1)] = s | flag;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, has);
+    if (ballot) {
+      int* counter = color_parity >= 0 ? &m.ctrl->cband_count[color_parity] : &m.ctrl->band_count;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(counter, __popc(ballot));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (has) band_slots[base + __popc(ballot & ((1u << lane) - 1u))] = out;
     }
   }
   if (threadIdx.x == 0 && n_cand && color_parity == -1) count_add(m, kCntFeatCandidateBlocks, (unsigned)n_cand);
@@ -569,6 +668,7 @@ __device__ __forceinline__ int floor_div_exact(float p, float bs, float bs_inv) 
 
 constexpr int kTraceSmemCells = 4096;  // workspace grids up to this many cells are staged in shared memory
 
+template <int kSpec>
 __device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TraceParams& tp, int r, int c,
                                                 float* __restrict__ image, const int* s_ws) {
   const float pu = (float)(c * tp.sub) + 0.5f * (float)tp.sub * 1.0f;
@@ -590,17 +690,17 @@ __device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TracePara
   const float bs = m.block_size, bs_inv = 1.0f / m.block_size;
   float2* const slab0 = m.tsdf_slabs[0];
 
-  int first = 0;
-  float t = 0.0f;
-  bool ok = false;
-  int n_steps = 0;
-  for (int i = 0; (i < tp.max_steps) && (t < tp.max_ray_length); ++i) {
-    n_steps = i + 1;
+  // One sample of the march: which TSDF voxel does position o + t * d read (nullptr: no block there), and has the
+  // ray left a closed world for good?  getBlockAndVoxelIndexFromPositionInLayer (indexing_impl.h:37-49).
+  struct Loc {
+    const float2* addr;
+    bool gone;
+  };
+  auto locate = [&](float tt) -> Loc {
     V3 p;
-    p.x = ox + t * dl.x;
-    p.y = oy + t * dl.y;
-    p.z = oz + t * dl.z;
-    // getBlockAndVoxelIndexFromPositionInLayer (indexing_impl.h:37-49)
+    p.x = ox + tt * dl.x;
+    p.y = oy + tt * dl.y;
+    p.z = oz + tt * dl.z;
     I3 b, v;
     b.x = floor_div_exact(p.x, bs, bs_inv);
     b.y = floor_div_exact(p.y, bs, bs_inv);
@@ -613,55 +713,106 @@ __device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TracePara
     // payload (k_allocate_one), i.e. reads as unobserved, so the layer bits need not be consulted here.
     const int cell = ws_cell(m, b.x, b.y, b.z);
     int slot = -1;
+    Loc l;
+    l.gone = false;
     if (cell >= 0) {
       slot = s_ws ? s_ws[cell] : m.ws_slot[cell];
     } else if (!closed_world) {
       slot = hash_find(m, b.x, b.y, b.z);
     } else {
       // t only grows (steps are >= 0), so each coordinate of p moves monotonically along sign(dl)
-      const bool gone = (b.x > ws_mx.x && dl.x >= 0.0f) || (b.x < m.ws_mn.x && dl.x <= 0.0f) ||
-                        (b.y > ws_mx.y && dl.y >= 0.0f) || (b.y < m.ws_mn.y && dl.y <= 0.0f) ||
-                        (b.z > ws_mx.z && dl.z >= 0.0f) || (b.z < m.ws_mn.z && dl.z <= 0.0f);
-      if (gone) break;  // miss
+      l.gone = (b.x > ws_mx.x && dl.x >= 0.0f) || (b.x < m.ws_mn.x && dl.x <= 0.0f) ||
+               (b.y > ws_mx.y && dl.y >= 0.0f) || (b.y < m.ws_mn.y && dl.y <= 0.0f) ||
+               (b.z > ws_mx.z && dl.z >= 0.0f) || (b.z < m.ws_mn.z && dl.z <= 0.0f);
     }
-    const float2* cached_ptr = nullptr;
+    l.addr = nullptr;
     if (slot >= 0)
-      cached_ptr = (slot < (1 << kTsdfSlabShift)) ? slab0 + (size_t)slot * kVoxelsPerBlock : tsdf_block(m, slot);
-    bool valid = false;
-    float dist = 0.0f;
-    if (cached_ptr) {
-      const float2 q = cached_ptr[(v.x * 8 + v.y) * 8 + v.z];
-      if (q.y > 1e-4f) {
-        valid = true;
-        dist = q.x;
+      l.addr = ((slot < (1 << kTsdfSlabShift)) ? slab0 + (size_t)slot * kVoxelsPerBlock : tsdf_block(m, slot)) +
+               ((v.x * 8 + v.y) * 8 + v.z);
+    return l;
+  };
+
+  // The reference marches one dependent TSDF read per step (sphere_tracer.cu:31-131): <= 24 steps x one L2 round
+  // trip each on the slowest rays, which set the kernel's duration.  Here each round trip carries kSpec samples:
+  // the true position plus kSpec - 1 positions predicted with the last step length (the truncation distance in
+  // unobserved space, the TSDF distance -- nearly constant in observed free space -- otherwise).  A predicted
+  // sample is consumed only if the TRUE next position reads the very same voxel address, so the sequence of
+  // (t, value) pairs, the step count and the result are exactly those of the one-read-per-step march.
+  int first = 0;
+  float t = 0.0f;
+  bool ok = false;
+  int n_steps = 0;
+  int i = 0;
+  float guess = tp.trunc;
+  bool run = (i < tp.max_steps) && (t < tp.max_ray_length);
+  while (run) {
+    float tk[kSpec];
+    Loc loc[kSpec];
+    float2 val[kSpec];
+    tk[0] = t;
+#pragma unroll
+    for (int j = 1; j < kSpec; ++j) tk[j] = tk[j - 1] + guess;
+#pragma unroll
+    for (int j = 0; j < kSpec; ++j) loc[j] = locate(tk[j]);
+#pragma unroll
+    for (int j = 0; j < kSpec; ++j) val[j] = loc[j].addr ? *loc[j].addr : make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int k = 0; k < kSpec; ++k) {
+      Loc cur = loc[k];
+      if (k > 0) {
+        cur = locate(t);
+        if (cur.addr != nullptr && cur.addr != loc[k].addr) break;  // predicted another voxel: refill from t
       }
-    }
-    float step;
-    if (!valid) {
-      if (first == 0) {
-        step = tp.trunc;
-      } else {
-        break;  // left observed space: fail
+      n_steps = i + 1;
+      if (cur.gone) {  // miss
+        run = false;
+        break;
       }
-    } else {
-      if (first == 0) first = (dist >= 0.0f) ? 1 : -1;
-      if (first == 1) {
-        if (dist < tp.eps) {
-          t += dist;
-          ok = true;
+      bool valid = false;
+      float dist = 0.0f;
+      if (cur.addr) {
+        const float2 q = val[k];
+        if (q.y > 1e-4f) {
+          valid = true;
+          dist = q.x;
+        }
+      }
+      float step;
+      if (!valid) {
+        if (first == 0) {
+          step = tp.trunc;
+        } else {
+          run = false;  // left observed space: fail
           break;
         }
-        step = dist;
       } else {
-        if (dist > -tp.eps) {
-          t -= dist;
-          ok = true;
-          break;
+        if (first == 0) first = (dist >= 0.0f) ? 1 : -1;
+        if (first == 1) {
+          if (dist < tp.eps) {
+            t += dist;
+            ok = true;
+            run = false;
+            break;
+          }
+          step = dist;
+        } else {
+          if (dist > -tp.eps) {
+            t -= dist;
+            ok = true;
+            run = false;
+            break;
+          }
+          step = -dist;
         }
-        step = -dist;
+      }
+      t += step;
+      ++i;
+      guess = step;
+      if (!((i < tp.max_steps) && (t < tp.max_ray_length))) {
+        run = false;
+        break;
       }
     }
-    t += step;
   }
   image[(size_t)r * tp.cols + c] = ok ? t * dc.z : -1.0f;
   return n_steps;
@@ -670,17 +821,19 @@ __device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TracePara
 // The two independent, latency-bound preparations of a feature frame in ONE launch: CTAs
 // [0, n_trace_ctas) sphere-trace 16x16 tiles of the synthetic depth image, the remaining CTAs run
 // band_select_tile.  Both only read the TSDF layer; they overlap instead of queueing.
+template <int SPEC, int ILP>
 __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp, float* __restrict__ image,
                                                         int trace_tiles_x, int n_trace_ctas, PlanesView view,
                                                         float trunc, int* band_slots, int* newfeat_slots,
                                                         int tile_cells, int n_tiles, int color_parity) {
   pdl_prologue();
-  __shared__ int s_cand[256];
-  __shared__ int s_ncand;
+  __shared__ int s_cand[256], s_band[256];
+  __shared__ int s_ncand, s_nband;
   __shared__ int s_ws[kTraceSmemCells];
 #ifdef NVBX_PROFILE_COUNTERS
   const long long t0 = clock64();
 #endif
+  PROF_BEGIN(prof_seq_early(m.ctrl), kProfTrace);
   if (blockIdx.x == 0 && threadIdx.x == 0) m.ctrl->item_count = 0;  // consumed by k_feature_geometry
   // n_trace_ctas == 0: the synthetic depth image of this pose / camera / TSDF state is already in `image`
   if ((int)blockIdx.x < n_trace_ctas) {
@@ -692,7 +845,7 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
       __syncthreads();
     }
     [[maybe_unused]] int n_steps = 0;
-    if (r < tp.rows && c < tp.cols) n_steps = sphere_trace_ray(m, tp, r, c, image, stage_ws ? s_ws : nullptr);
+    if (r < tp.rows && c < tp.cols) n_steps = sphere_trace_ray<SPEC>(m, tp, r, c, image, stage_ws ? s_ws : nullptr);
 #ifdef NVBX_PROFILE_COUNTERS
     {  // tuning aid: steps (sum / max over rays) and the slowest warp's cycles, one atomic set per warp
       const long long dt = clock64() - t0;
@@ -710,13 +863,16 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
 #else
     (void)n_steps;
 #endif
+    PROF_END(kProfTrace);
     return;
   }
   for (int tile = (int)blockIdx.x - n_trace_ctas; tile < n_tiles; tile += (int)gridDim.x - n_trace_ctas)
-    band_select_tile(m, view, trunc, band_slots, newfeat_slots, tile, tile_cells, s_cand, &s_ncand, color_parity);
+    band_select_tile<ILP>(m, view, trunc, band_slots, newfeat_slots, tile, tile_cells, s_cand, &s_ncand, s_band,
+                          &s_nband, color_parity);
 #ifdef NVBX_PROFILE_COUNTERS
   if (threadIdx.x == 0) atomicMax(&m.ctrl->counters[kCntProfile0 + 3], (unsigned long long)(clock64() - t0));
 #endif
+  PROF_END(kProfTrace);
 }
 
 // The read-only twin of the band selection: ctrl->list_count += band blocks of this view that have no feature
@@ -726,10 +882,11 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
 __global__ void __launch_bounds__(256) k_band_count(MapDev m, PlanesView view, float trunc, int tile_cells,
                                                     int n_tiles) {
   pdl_prologue();
-  __shared__ int s_cand[256];
-  __shared__ int s_ncand;
+  __shared__ int s_cand[256], s_band[256];
+  __shared__ int s_ncand, s_nband;
   for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x)
-    band_select_tile(m, view, trunc, nullptr, nullptr, tile, tile_cells, s_cand, &s_ncand, kBandCountOnly);
+    band_select_tile<1>(m, view, trunc, nullptr, nullptr, tile, tile_cells, s_cand, &s_ncand, s_band, &s_nband,
+                        kBandCountOnly);
 }
 
 // ================================================================================================
@@ -824,6 +981,7 @@ __global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* _
   const int C = m.C;
   unsigned long long n_updated = 0;
   if (blockIdx.x == 0 && t == 0) m.ctrl->gather_ticket = 0;  // consumed by k_feature_gather_dyn (next launch)
+  PROF_BEGIN(prof_seq_late(m.ctrl), kProfGeometry);
 
   // Zero-fill the feature blocks allocated by this frame (blox_impl.h:92-97), every CTA taking an equal
   // slice of each, so that a 794 KB block costs each SM a few KB; the gather kernel runs after us.
@@ -905,6 +1063,7 @@ __global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* _
       count_add(m, kCntFeatureFrames, 1);
     }
   }
+  PROF_END(kProfGeometry);
 }
 
 // CH: 512-byte chunks (32 lanes x 16 B) per channel vector, C = 256 * CH; 0 = any C (multiple of 8).
@@ -912,6 +1071,7 @@ template <int CH, int U, int CTAS>  // U: units in flight per warp; CTAS: reside
 __global__ void __launch_bounds__(256, CTAS) k_feature_gather(MapDev m, const FeatItem* __restrict__ items,
                                                               FeatFrame f, int last_chunk) {
   pdl_prologue();
+  PROF_BEGIN(prof_seq_late(m.ctrl), kProfGather);
   const int n_items = m.ctrl->item_count;
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
@@ -970,6 +1130,7 @@ __global__ void __launch_bounds__(256, CTAS) k_feature_gather(MapDev m, const Fe
     m.ctrl->band_count = 0;  // ready for the next frame's band_select_tile
     m.ctrl->newfeat_count = 0;
   }
+  PROF_END(kProfGather);
 }
 
 // Same units, same arithmetic, different SCHEDULE: the first `n_static` units are dealt round-robin as above,
@@ -984,6 +1145,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_feature_gather_dyn(MapDev m, 
                                                                       int items_cap, FeatFrame f, int last_chunk,
                                                                       int dyn_permille, int tk) {
   pdl_prologue();
+  PROF_BEGIN(prof_seq_late(m.ctrl), kProfGather);
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * (THREADS >> 5);
   const int warp = blockIdx.x * (THREADS >> 5) + (threadIdx.x >> 5);
@@ -1062,6 +1224,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_feature_gather_dyn(MapDev m, 
     m.ctrl->band_count = 0;  // ready for the next frame's band_select_tile
     m.ctrl->newfeat_count = 0;
   }
+  PROF_END(kProfGather);
 }
 
 // ================================================================================================
