@@ -316,6 +316,8 @@ def run_ours(args, rank, world, local_rank):
         per_kernel = per_kernel_us(sub, mapper, depths, poses, feats, K_t)
         export = export_stage(mapper)
         fused = fused_upsample_stage(sub, mapper, depths, poses, K_t, dev)
+        batched = batched_maps_stage(depths, poses, feats, K_t, local_rank)
+        drill = drill_in_box_stage(lib, feats, h_feat, local_rank, peak)
         line = {
             'metric': 'feature frames integrated/s (C=768, 512^2)', 'value': value, 'unit': 'frames/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
@@ -346,7 +348,7 @@ def run_ours(args, rank, world, local_rank):
                                        f"1 thread, first {sample['frames']} frames: {sample['fps']:.3f} frames/s"},
             'extra': {'feature_call_ms': feat_call_ms, 'host_enqueue_ms_per_step': 1000.0 * t_host / args.steps,
                       'per_kernel_us_in_pipeline': per_kernel, 'export_stage': export,
-                      'fused_upsample': fused,
+                      'fused_upsample': fused, 'batched_maps_one_gpu': batched, 'drill_in_box': drill,
                       'counters_per_step': {k: v / args.steps for k, v in counters.items()
                                             if isinstance(v, (int, float))}},
         }
@@ -382,7 +384,7 @@ def sweep_gather(args, lib, mapper, depths, poses, feats, K_t, step):
     workload -- live kernel duration (library-placed CUDA events) and whole-frame device time."""
     import torch
     n_total = args.warmup + args.steps
-    grid = [(0, 0, 1), (4, 0, 1), (5, 0, 1), (6, 0, 1), (7, 0, 1), (8, 0, 1), (9, 0, 1)]
+    grid = [(0, 0, 1), (4, 0, 1), (6, 0, 1), (7, 0, 1), (4, -1, 1), (6, -1, 1), (7, -1, 1), (9, -1, 1)]
     rows = []
     for rep in range(2):
         for (v, pm, tk) in grid:
@@ -400,7 +402,116 @@ def sweep_gather(args, lib, mapper, depths, poses, feats, K_t, step):
             rows.append({'rep': rep, 'variant': v, 'dyn_permille': pm, 'ticket': tk, 'gather_us': 1000.0 * kms,
                          'frame_us': 1000.0 * e0.elapsed_time(e1) / args.steps})
             print(json.dumps(rows[-1]), flush=True)
+    h_feat = [feats[i].cpu().pin_memory() for i in range(2)]
+    peak, _ = measured_peak_gbs()
+    for (v, pm, tk) in [(7, 0, 1), (7, -1, 1), (4, -1, 1), (6, -1, 1), (9, -1, 1)]:
+        assert lib.nvbx_set_gather_tuning(v, pm, tk) == 0
+        d = drill_in_box_stage(lib, feats, h_feat, 0, peak)
+        print(json.dumps({'drill_in_box': True, 'variant': v, 'dyn_permille': pm, 'frames_per_s': d['frames_per_s'],
+                          'gather_us': 1000.0 * d['gather_kernel_ms'], 'gather_GBps': d['gather_GBps']}), flush=True)
     lib.nvbx_set_gather_tuning(7, 0, 4)
+
+
+def drill_in_box_stage(lib, feats, h_feat, local_rank, peak):
+    """BASELINE configs[2] as an extra data point (not the headline): head (static: viewpoint-cache hits) + wrist
+    camera per step, 512x512, C = 768, 1 cm voxels, drill-in-box workspace.  ~4x the voxels per frame of the
+    headline workload, i.e. what the gather reaches when a launch is long enough to amortise its ramp."""
+    import ctypes as C
+    import torch
+    from nvblox_torch.mapper import Mapper
+    from tests.parity_utils import make_params
+    mp, _ = make_params(workspace=S.WS_DRILL_IN_BOX, decay=0.999)
+    mapper = Mapper(voxel_sizes_m=0.01, mapper_parameters=mp, device=local_rank)
+    dev = f'cuda:{local_rank}'
+    K = S.intrinsics(W, H)
+    K_t = torch.from_numpy(K)
+    n_pose, n_warm, n_timed = 16, 8, 32
+    T_head = S.look_at((-0.2, 0.0, 0.6), (0.4, 0.0, 0.05))
+    cams = [(torch.from_numpy(T_head), torch.from_numpy(S.render_depth(K, H, W, T_head, **S.S_TABLE)))]
+    for i in range(n_pose):
+        T = S.orbit_pose(i, 64, 0.4, 0.45)
+        cams.append((torch.from_numpy(T), torch.from_numpy(S.render_depth(K, H, W, T, **S.S_TABLE))))
+    d_dev = [d.to(dev) for _, d in cams]
+    d_pin = [d.pin_memory() for _, d in cams]
+
+    def step(i, host=False):
+        for c in (0, 1 + i % n_pose):
+            f = (i + c) % len(h_feat if host else feats)
+            if host:
+                mapper.integrate_frame_from_host(d_pin[c], h_feat[f], cams[c][0], K_t)
+            else:
+                mapper.add_depth_frame(d_dev[c], cams[c][0], K_t)
+                mapper.add_feature_frame(feats[f], cams[c][0], K_t)
+
+    for i in range(n_warm):
+        step(i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    mapper.reset_counters(0)
+    e0.record()
+    for i in range(n_warm, n_warm + n_timed):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    n_upd = mapper.counters(0)['feature_voxels_updated'] / (2 * n_timed)
+    lib.nvbx_set_kernel_timing(mapper._handle, 1)
+    for i in range(n_warm, n_warm + n_timed):
+        step(i)
+    kms, n = C.c_double(), C.c_int64()
+    lib.nvbx_get_kernel_timing(mapper._handle, 0, C.byref(kms), C.byref(n))
+    lib.nvbx_set_kernel_timing(mapper._handle, 0)
+    kms = kms.value / max(1, n.value)
+    px0 = mapper.counters(0)['host_pixels_fetched']
+    for i in range(n_warm, n_warm + 4):          # distinct pixels per frame, device-counted by the sparse host path
+        step(i, host=True)
+    px = (mapper.counters(0)['host_pixels_fetched'] - px0) / 8
+    b = 2 * C_FEAT * px + 2 * (C_FEAT + 1) * n_upd
+    gbs = b / (kms * 1e-3) / 1e9 if kms else None
+    return {'workload': 'drill_in_box: head (static) + wrist cam 512x512, C=768, 1 cm voxels', 'frames_per_s':
+            2 * n_timed / (ms / 1e3), 'ms_per_camera_frame': ms / (2 * n_timed), 'n_upd_per_frame': n_upd,
+            'distinct_pixels_per_frame': px, 'gather_kernel_ms': kms, 'gather_algorithmic_bytes': b,
+            'gather_GBps': gbs, 'gather_frac_of_measured_peak': (gbs / peak) if gbs else None,
+            'feature_blocks': mapper.feature_layer_view(0).num_blocks(),
+            'note': 'extra data point, same kernels and event-timing method as the headline roofline'}
+
+
+def batched_maps_stage(depths, poses, feats, K_t, local_rank, n_maps=4, n_timed=128):
+    """BASELINE configs[3] on one GPU: n_maps independent episode maps, one Mapper handle and one CUDA stream each,
+    fed round-robin by this one host thread (the latency-bound kernels of one map run under another map's gather).
+    Bounded by the host's enqueue rate, which is reported beside it."""
+    import torch
+    from nvblox_torch.mapper import Mapper
+    mp, _ = mapper_params()
+    mappers = [Mapper(voxel_sizes_m=VOXEL, mapper_parameters=mp, device=local_rank) for _ in range(n_maps)]
+    streams = [torch.cuda.Stream(device=local_rank) for _ in range(n_maps)]
+    n = len(depths)
+
+    def step(i):
+        for k in range(n_maps):
+            j = (i + 7 * k) % n
+            with torch.cuda.stream(streams[k]):
+                mappers[k].add_depth_frame(depths[j], poses[j], K_t)
+                mappers[k].add_feature_frame(feats[(i + k) % len(feats)], poses[j], K_t)
+
+    for i in range(16):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for i in range(16, 16 + n_timed):
+        step(i)
+    host = time.perf_counter() - t0
+    for s in streams:
+        torch.cuda.current_stream().wait_stream(s)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {'maps': n_maps, 'frames_per_s': n_maps * n_timed / (ms / 1e3),
+            'host_enqueue_us_per_frame': 1e6 * host / (n_maps * n_timed),
+            'device_us_per_frame': 1e3 * ms / (n_maps * n_timed),
+            'note': 'all maps on one GPU, one stream each, one host thread'}
 
 
 def ncu_traffic_bytes():

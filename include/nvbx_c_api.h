@@ -328,7 +328,8 @@ int64_t nvbx_kernel_timing_report(nvbx_mapper* m, char* json, int64_t capacity);
 int nvbx_get_kernel_timing(nvbx_mapper* m, int which, double* total_ms, int64_t* launches);
 /* Process-wide schedule of the feature gather kernel (tuning aid; results are identical for every setting):
  * variant 0..3 = static round-robin deal <units in flight, CTAs/SM>, 4..9 = k_feature_gather_dyn with
- * `dyn_permille`/1000 of the units handed out by atomic ticket, `ticket_units` per grab. */
+ * `dyn_permille`/1000 of the units handed out by atomic ticket, `ticket_units` per grab; dyn_permille = -1: each
+ * CTA owns a contiguous range of the work-item list (L1 reuse between neighbouring voxels). */
 int nvbx_set_gather_tuning(int variant, int dyn_permille, int ticket_units);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t nvbx_kernel_launch_count(void);

@@ -701,13 +701,13 @@ int env_int(const char* name, int dflt) {
 // Schedule of the feature gather (tuning hooks; profiles/r01b_gather_variants.md, r01i_gather_schedule.md):
 // NVBX_GATHER_VARIANT / NVBX_GATHER_DYN / NVBX_GATHER_TICKET at load, nvbx_set_gather_tuning at run time.
 constexpr int kDefaultGatherVariant = 7;  // 48-register static deal + item prefetch on 4 CTAs / SM (profiles/r01k_gather_schedule.md)
-int g_gather_tuning[3] = {-1, -1, -1};
+int g_gather_tuning[3] = {-1, -2, -1};
 int gather_variant() {
   if (g_gather_tuning[0] < 0) g_gather_tuning[0] = std::max(0, env_int("NVBX_GATHER_VARIANT", kDefaultGatherVariant));
   return g_gather_tuning[0];
 }
 int gather_dyn_permille() {  // share of the units handed out by ticket (k_feature_gather_dyn)
-  if (g_gather_tuning[1] < 0) g_gather_tuning[1] = std::min(1000, std::max(0, env_int("NVBX_GATHER_DYN", 0)));
+  if (g_gather_tuning[1] < -1) g_gather_tuning[1] = std::min(1000, std::max(-1, env_int("NVBX_GATHER_DYN", 0)));
   return g_gather_tuning[1];
 }
 int gather_ticket_units() {
@@ -1936,8 +1936,8 @@ int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream_v) {
 }
 
 int nvbx_set_gather_tuning(int variant, int dyn_permille, int ticket_units) {
-  if (variant < 0 || variant > 9 || dyn_permille < 0 || dyn_permille > 1000 || ticket_units < 1 || ticket_units > 64)
-    return fail(NVBX_ERR_INVALID_ARGUMENT, "gather tuning out of range (variant 0..9, permille 0..1000, ticket 1..64)");
+  if (variant < 0 || variant > 9 || dyn_permille < -1 || dyn_permille > 1000 || ticket_units < 1 || ticket_units > 64)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "gather tuning out of range (variant 0..9, permille -1..1000, ticket 1..64)");
   g_gather_tuning[0] = variant;
   g_gather_tuning[1] = dyn_permille;
   g_gather_tuning[2] = ticket_units;

@@ -1157,16 +1157,31 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_feature_gather_dyn(MapDev m, 
       __ldg(reinterpret_cast<const uint4*>(items + min(warp / ch_per_item, items_cap - 1)));
   const int n_items = m.ctrl->item_count;
   const long long n_units = (long long)n_items * ch_per_item;
-  const long long rounds = (n_units * (1000 - dyn_permille) / 1000) / warps_total;
-  const long long n_static = dyn_permille == 0 ? n_units : rounds * warps_total;  // 0: no ticket at all
+  // dyn_permille < 0: CTA-blocked deal -- CTA c owns the contiguous units [c * n / G, (c + 1) * n / G), i.e. work
+  // items of neighbouring voxels (the list is in block / voxel order), whose bilinear footprints overlap: the
+  // repeated pixel rows then hit in this SM's L1 instead of travelling from L2 again.
+  const bool blocked = dyn_permille < 0;
+  const long long rounds = (n_units * (1000 - max(dyn_permille, 0)) / 1000) / warps_total;
+  const long long n_static = dyn_permille <= 0 ? n_units : rounds * warps_total;  // 0: no ticket at all
   const __half2 w1 = __half2half2(__ushort_as_half(f.h_w1));
   const __half2 w2 = __half2half2(__ushort_as_half(f.h_w2));
   const size_t row_vecs = (size_t)(m.row >> 3);
   int* ticket = &m.ctrl->gather_ticket;
 
   long long q = warp;
+  long long stride = warps_total, end = n_static;
   int left = 0;  // units of the current ticket not yet started
-  if (q >= n_static) {
+  if (blocked) {
+    const long long lo = ((long long)blockIdx.x * n_units) / gridDim.x;
+    end = ((long long)(blockIdx.x + 1) * n_units) / gridDim.x;
+    stride = THREADS >> 5;
+    q = lo + (threadIdx.x >> 5);
+    if (q < end) {
+      *reinterpret_cast<uint4*>(&cur) = __ldg(reinterpret_cast<const uint4*>(items + q / ch_per_item));
+    } else {
+      q = n_units;
+    }
+  } else if (q >= n_static) {
     int t = 0;
     if (lane == 0) t = atomicAdd(ticket, tk);
     q = n_static + __shfl_sync(0xffffffffu, t, 0);
@@ -1188,9 +1203,9 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_feature_gather_dyn(MapDev m, 
     }
     // next unit (and its item) while the pixel loads fly
     long long qn;
-    if (q + warps_total < n_static) {
-      qn = q + warps_total;
-    } else if (dyn_permille == 0) {
+    if (q + stride < end) {
+      qn = q + stride;
+    } else if (dyn_permille <= 0) {
       qn = n_units;
     } else if (q >= n_static && left > 0) {
       qn = q + 1;
