@@ -384,7 +384,7 @@ def sweep_gather(args, lib, mapper, depths, poses, feats, K_t, step):
     workload -- live kernel duration (library-placed CUDA events) and whole-frame device time."""
     import torch
     n_total = args.warmup + args.steps
-    grid = [(0, 0, 1), (4, 0, 1), (6, 0, 1), (7, 0, 1), (4, -1, 1), (6, -1, 1), (7, -1, 1), (9, -1, 1)]
+    grid = [(0, 0, 1), (4, 0, 1), (6, 0, 1), (7, 0, 1), (7, -1, 1), (9, 0, 1), (10, 0, 1)]
     rows = []
     for rep in range(2):
         for (v, pm, tk) in grid:
@@ -404,7 +404,7 @@ def sweep_gather(args, lib, mapper, depths, poses, feats, K_t, step):
             print(json.dumps(rows[-1]), flush=True)
     h_feat = [feats[i].cpu().pin_memory() for i in range(2)]
     peak, _ = measured_peak_gbs()
-    for (v, pm, tk) in [(7, 0, 1), (7, -1, 1), (4, -1, 1), (6, -1, 1), (9, -1, 1)]:
+    for (v, pm, tk) in [(7, 0, 1), (7, -1, 1), (10, 0, 1)]:
         assert lib.nvbx_set_gather_tuning(v, pm, tk) == 0
         d = drill_in_box_stage(lib, feats, h_feat, 0, peak)
         print(json.dumps({'drill_in_box': True, 'variant': v, 'dyn_permille': pm, 'frames_per_s': d['frames_per_s'],

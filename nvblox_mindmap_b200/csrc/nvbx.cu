@@ -740,6 +740,21 @@ int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, 
     case 0:
       LAUNCH((k_feature_gather<CH, 1, 4>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
       break;
+    case 10:  // cp.async.bulk + mbarrier staging, one 8-warp CTA per SM (C = 256 * CH only)
+      if constexpr (CH > 0) {
+        static const bool once = [] {
+          cudaFuncSetAttribute(k_feature_gather_tma<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               TmaGather<CH>::kSmemBytes);
+          return true;
+        }();
+        (void)once;
+        LAUNCH((k_feature_gather_tma<CH>), persistent_grid(m, 1), kTmaWarps * 32, TmaGather<CH>::kSmemBytes, stream,
+               mp.dev, mp.items.p, ff, last_chunk);
+      } else {
+        LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p,
+               (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
+      }
+      break;
     case 7:  // the 48-register build on 4 CTAs / SM: leaves registers for two CTAs of the next frame's raycast
       LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p,
              (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
@@ -1936,8 +1951,8 @@ int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream_v) {
 }
 
 int nvbx_set_gather_tuning(int variant, int dyn_permille, int ticket_units) {
-  if (variant < 0 || variant > 9 || dyn_permille < -1 || dyn_permille > 1000 || ticket_units < 1 || ticket_units > 64)
-    return fail(NVBX_ERR_INVALID_ARGUMENT, "gather tuning out of range (variant 0..9, permille -1..1000, ticket 1..64)");
+  if (variant < 0 || variant > 10 || dyn_permille < -1 || dyn_permille > 1000 || ticket_units < 1 || ticket_units > 64)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "gather tuning out of range (variant 0..10, permille -1..1000, ticket 1..64)");
   g_gather_tuning[0] = variant;
   g_gather_tuning[1] = dyn_permille;
   g_gather_tuning[2] = ticket_units;

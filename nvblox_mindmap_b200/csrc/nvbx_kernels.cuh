@@ -1242,6 +1242,130 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_feature_gather_dyn(MapDev m, 
   PROF_END(kProfGather);
 }
 
+// ---- bulk-copy (TMA 1-D) variant of the gather --------------------------------------------------------
+// The two pixel PAIRS of a voxel's bilinear footprint are 2 x 2C contiguous bytes each in the HWC frame (px and
+// px + 1 of one image row).  Here they travel as two cp.async.bulk copies (3 KB each at C = 768) straight into
+// shared memory, completion counted by an mbarrier; every warp runs its own ring of stages, the elected lane
+// keeps NST voxels (NST x 6 KB) in flight per warp without holding a register for them, and the lanes read the
+// landed rows back as conflict-free 128-bit shared loads.  Same arithmetic and stores as k_feature_gather.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
+constexpr int kTmaWarps = 8;
+template <int CH>
+struct TmaGather {
+  static constexpr int kRowBytes = 512 * CH;          // one pixel: C halves
+  static constexpr int kStageBytes = 4 * kRowBytes;   // (px, px + 1) of the top row, then of the bottom row
+  static constexpr int kStages = (24576 / kStageBytes) < 8 ? (24576 / kStageBytes) : 8;
+  static constexpr int kSmemBytes = kTmaWarps * kStages * kStageBytes;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(kTmaWarps * 32, 1) k_feature_gather_tma(MapDev m, const FeatItem* __restrict__ items,
+                                                                          FeatFrame f, int last_chunk) {
+  using G = TmaGather<CH>;
+  constexpr int NST = G::kStages;
+  extern __shared__ __align__(128) unsigned char s_stage[];
+  __shared__ __align__(8) unsigned long long s_bar[kTmaWarps][NST];
+  pdl_prologue();
+  PROF_BEGIN(prof_seq_late(m.ctrl), kProfGather);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long warps_total = (long long)gridDim.x * kTmaWarps;
+  const long long warp = (long long)blockIdx.x * kTmaWarps + wid;
+  const int n_items = m.ctrl->item_count;
+  const int nvec = m.C >> 3;
+  const size_t row_vecs = (size_t)(m.row >> 3);
+  const __half2 w1 = __half2half2(__ushort_as_half(f.h_w1));
+  const __half2 w2 = __half2half2(__ushort_as_half(f.h_w2));
+  unsigned char* wstage = s_stage + (size_t)wid * NST * G::kStageBytes;
+  const unsigned stage0 = smem_u32(wstage), bar0 = smem_u32(&s_bar[wid][0]);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) mbar_init(bar0 + 8u * s, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  FeatItem it[NST];
+  long long j = warp;  // next item to put in flight
+  auto issue = [&](int s, FeatItem& slot_item) {
+    if (j < n_items) {
+      *reinterpret_cast<uint4*>(&slot_item) = __ldg(reinterpret_cast<const uint4*>(items + j));
+      if (lane == 0) {
+        const unsigned bar = bar0 + 8u * s, dst = stage0 + (unsigned)(s * G::kStageBytes);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(f.img) + (size_t)slot_item.pix * G::kRowBytes;
+        mbar_expect_tx(bar, (unsigned)G::kStageBytes);
+        bulk_g2s(dst, src, 2u * G::kRowBytes, bar);
+        bulk_g2s(dst + 2u * G::kRowBytes, src + (size_t)f.cols * G::kRowBytes, 2u * G::kRowBytes, bar);
+      }
+    }
+    j += warps_total;
+  };
+#pragma unroll
+  for (int s = 0; s < NST; ++s) issue(s, it[s]);
+
+  unsigned parity = 0;
+  for (long long k = warp; k < n_items;) {
+#pragma unroll
+    for (int s = 0; s < NST; ++s) {
+      if (k < n_items) {  // warp-uniform
+        mbar_wait(bar0 + 8u * s, parity);
+        const FeatItem cur = it[s];
+        const uint4* st = reinterpret_cast<const uint4*>(wstage + (size_t)s * G::kStageBytes);
+        const int fslot = cur.row >> 9, vox = cur.row & 511;
+        uint4* dst = reinterpret_cast<uint4*>(feat_block(m, fslot)) + (size_t)vox * row_vecs;
+        const bool blend = (!cur.first) && f.read_old;
+        const __half hx = __ushort_as_half(cur.hx), hy = __ushort_as_half(cur.hy);
+        const __half2 x2 = __half2half2(hx), y2 = __half2half2(hy), xy2 = __half2half2(__hmul_rn(hx, hy));
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int v = c * 32 + lane;
+          const uint4 a00 = st[v], a10 = st[nvec + v], a01 = st[2 * nvec + v], a11 = st[3 * nvec + v];
+          uint4 o = interp_vec(x2, y2, xy2, a00, a01, a10, a11);
+          if (blend) o = blend_vec(dst[v], o, w1, w2);
+          dst[v] = o;
+        }
+        if (lane == 0) dst[nvec] = make_uint4((unsigned)cur.wnew, 0u, 0u, 0u);  // weight + zero padding
+        __syncwarp();  // every lane has read stage s: it may be overwritten
+        issue(s, it[s]);
+      }
+      k += warps_total;
+    }
+    parity ^= 1u;
+  }
+  if (last_chunk && blockIdx.x == 0 && threadIdx.x == 0) {
+    m.ctrl->last_band_count = m.ctrl->band_count;
+    m.ctrl->band_count = 0;  // ready for the next frame's band_select_tile
+    m.ctrl->newfeat_count = 0;
+  }
+  PROF_END(kProfGather);
+}
+
 // ================================================================================================
 // Host-resident feature frames (nvbx_integrate_frame_host).  The reference only accepts CUDA tensors, so a
 // caller with a host frame pays `.cuda()` on all H*W*C halves (384 MiB at 512^2 x 768) although the frame's

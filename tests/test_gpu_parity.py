@@ -68,7 +68,7 @@ def test_c768_features_bit_exact():
 
 
 @pytest.mark.parametrize('variant,permille,ticket', [(0, 0, 1), (1, 300, 2), (4, 300, 2), (4, 1000, 1), (4, 0, 3), (5, 500, 4),
-                                                    (6, 150, 2), (7, 0, 1), (8, 0, 1), (7, -1, 1), (4, -1, 1)])
+                                                    (6, 150, 2), (7, 0, 1), (8, 0, 1), (7, -1, 1), (4, -1, 1), (10, 0, 1)])
 @pytest.mark.parametrize('C,alpha', [(768, 1.0), (40, 0.3)])
 def test_gather_schedules_are_result_identical(variant, permille, ticket, C, alpha):
     """Every schedule of the feature gather (static deal / ticketed tail, nvbx_set_gather_tuning) writes the
@@ -87,7 +87,7 @@ def test_gather_schedules_are_result_identical(variant, permille, ticket, C, alp
         assert g['feature_voxels_updated'] == c['feature_voxels_updated'] > 0
     finally:
         assert lib.nvbx_set_gather_tuning(7, 0, 4) == 0
-    assert lib.nvbx_set_gather_tuning(10, 0, 1) != 0 and lib.nvbx_set_gather_tuning(4, 1001, 1) != 0 and lib.nvbx_set_gather_tuning(4, -2, 1) != 0
+    assert lib.nvbx_set_gather_tuning(11, 0, 1) != 0 and lib.nvbx_set_gather_tuning(4, 1001, 1) != 0 and lib.nvbx_set_gather_tuning(4, -2, 1) != 0
 
 
 def test_decay_until_removed():
