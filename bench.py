@@ -476,42 +476,56 @@ def drill_in_box_stage(lib, feats, h_feat, local_rank, peak):
             'note': 'extra data point, same kernels and event-timing method as the headline roofline'}
 
 
-def batched_maps_stage(depths, poses, feats, K_t, local_rank, n_maps=4, n_timed=128):
-    """BASELINE configs[3] on one GPU: n_maps independent episode maps, one Mapper handle and one CUDA stream each,
-    fed round-robin by this one host thread (the latency-bound kernels of one map run under another map's gather).
-    Bounded by the host's enqueue rate, which is reported beside it."""
+def batched_maps_stage(depths, poses, feats, K_t, local_rank, n_maps=8, n_timed=96):
+    """BASELINE configs[3] on one GPU: n_maps independent episode maps (what one rank of the 64-map datagen job
+    holds at 8 GPUs), one frame per map per step through MapBatch -> nvbx_integrate_frames_batch: one stream per
+    map, launches issued by a pool of host threads, so that the latency-bound kernels of one map run under another
+    map's gather.  The single-thread Python loop over the same maps is timed beside it."""
     import torch
-    from nvblox_torch.mapper import Mapper
+    from nvblox_mindmap_b200.replicas import MapBatch
     mp, _ = mapper_params()
-    mappers = [Mapper(voxel_sizes_m=VOXEL, mapper_parameters=mp, device=local_rank) for _ in range(n_maps)]
-    streams = [torch.cuda.Stream(device=local_rank) for _ in range(n_maps)]
+    batch = MapBatch(n_maps, VOXEL, mp, device=local_rank)
     n = len(depths)
 
-    def step(i):
-        for k in range(n_maps):
-            j = (i + 7 * k) % n
-            with torch.cuda.stream(streams[k]):
-                mappers[k].add_depth_frame(depths[j], poses[j], K_t)
-                mappers[k].add_feature_frame(feats[(i + k) % len(feats)], poses[j], K_t)
+    def frames(i):
+        idx = [(i + 7 * k) % n for k in range(n_maps)]
+        return ([depths[j] for j in idx], [feats[(i + k) % len(feats)] for k in range(n_maps)],
+                [poses[j] for j in idx])
 
-    for i in range(16):
-        step(i)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    t0 = time.perf_counter()
-    for i in range(16, 16 + n_timed):
-        step(i)
-    host = time.perf_counter() - t0
-    for s in streams:
-        torch.cuda.current_stream().wait_stream(s)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    return {'maps': n_maps, 'frames_per_s': n_maps * n_timed / (ms / 1e3),
-            'host_enqueue_us_per_frame': 1e6 * host / (n_maps * n_timed),
-            'device_us_per_frame': 1e3 * ms / (n_maps * n_timed),
-            'note': 'all maps on one GPU, one stream each, one host thread'}
+    def timed(step_fn):
+        for i in range(8):
+            step_fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        batch.wait_for_current_stream()
+        t0 = time.perf_counter()
+        for i in range(8, 8 + n_timed):
+            step_fn(i)
+        host = time.perf_counter() - t0
+        batch.join_current_stream()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        return n_maps * n_timed / (ms / 1e3), 1e6 * host / (n_maps * n_timed)
+
+    def step_batch(i):
+        d, f, p = frames(i)
+        batch.integrate_frames(d, f, p, K_t)
+
+    def step_loop(i):
+        d, f, p = frames(i)
+        for k in range(n_maps):
+            with torch.cuda.stream(batch.streams[k]):
+                batch.mappers[k].add_depth_frame(d[k], p[k], K_t)
+                batch.mappers[k].add_feature_frame(f[k], p[k], K_t)
+
+    fps_loop, host_loop = timed(step_loop)
+    fps_batch, host_batch = timed(step_batch)
+    return {'maps': n_maps, 'frames_per_s': fps_batch, 'host_us_per_frame': host_batch,
+            'python_loop': {'frames_per_s': fps_loop, 'host_us_per_frame': host_loop},
+            'note': 'all maps on one GPU, one stream each; nvbx_integrate_frames_batch (host launch pool) vs a '
+                    'single-thread Python loop over the same Mapper handles'}
 
 
 def ncu_traffic_bytes():

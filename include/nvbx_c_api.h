@@ -187,6 +187,32 @@ int nvbx_integrate_frame_host(nvbx_mapper* m, int map_id, const float* depth_hos
                               const uint8_t* feature_mask_host, const float* T_L_C, float fx, float fy,
                               float cx, float cy, void* stream);
 
+/* ---- batched datagen (BASELINE configs[3]): many independent maps per GPU ------------------------
+ * mindmap's datagen steps N environments and integrates one frame per environment per step
+ * (mindmap/run_isaaclab_datagen.py:194-235, one IsaacLabNvbloxMapper per env).  The frame of a single map is five
+ * latency-bound launches around one memory-bound one, so one map leaves most of a B200 idle; maps are independent,
+ * so their frames can overlap.  nvbx_integrate_frames_batch integrates one frame (depth, then features when
+ * `features` is not NULL: exactly nvbx_integrate_depth + nvbx_integrate_features) for each job, each on the job's own
+ * stream, with the jobs of DIFFERENT mapper handles issued concurrently by an internal pool of `n_threads` host
+ * threads (jobs of one handle keep their order on one thread).  Returns when every job has been ENQUEUED (not
+ * executed); job[i].status holds each job's status, the return value is the first failure (its message in
+ * nvbx_last_error()).  A handle must not appear in two concurrent batch calls. */
+typedef struct nvbx_frame_job {
+  nvbx_mapper* mapper;
+  int32_t map_id;
+  int32_t height, width, channels;
+  const void* depth;        /* device float[H*W] */
+  const void* depth_mask;   /* device uint8[H*W] or NULL */
+  const void* features;     /* device fp16[H*W*C] or NULL (depth only) */
+  const void* feature_mask; /* device uint8[H*W] or NULL */
+  float T_L_C[16];
+  float fx, fy, cx, cy;
+  void* stream;
+  int32_t status; /* out */
+  int32_t reserved;
+} nvbx_frame_job;
+int nvbx_integrate_frames_batch(nvbx_frame_job* jobs, int n_jobs, int n_threads);
+
 /* ---- the feature extractor's up-sampling fused into the integration ----------------
  * Replaces, for one frame, mindmap's
  *   FeatureExtractor.compute(): scale_image(features_bchw, (H, W)) -> rearrange -> zero-pad -> .to(float16)

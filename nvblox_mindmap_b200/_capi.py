@@ -8,7 +8,7 @@ import os
 import threading
 
 from nvblox_mindmap_b200 import build as _build
-from nvblox_mindmap_b200.params import NvbxCounters, NvbxParams
+from nvblox_mindmap_b200.params import NvbxFrameJob, NvbxCounters, NvbxParams
 
 _lock = threading.Lock()
 _lib = None
@@ -23,7 +23,7 @@ API_SYMBOLS = [
     'nvbx_export_points', 'nvbx_gather_points', 'nvbx_num_blocks', 'nvbx_num_allocated_blocks',
     'nvbx_num_allocated_bytes', 'nvbx_voxel_size', 'nvbx_get_block_indices', 'nvbx_get_block_ptr',
     'nvbx_allocate_block', 'nvbx_query_tsdf', 'nvbx_query_features', 'nvbx_get_counters',
-    'nvbx_reset_counters', 'nvbx_set_gather_tuning', 'nvbx_set_kernel_timing', 'nvbx_get_kernel_timing', 'nvbx_kernel_timing_report', 'nvbx_kernel_launch_count', 'nvbx_debug_last_block_list', 'nvbx_debug_profile_stamps',
+    'nvbx_reset_counters', 'nvbx_integrate_frames_batch', 'nvbx_set_gather_tuning', 'nvbx_set_kernel_timing', 'nvbx_get_kernel_timing', 'nvbx_kernel_timing_report', 'nvbx_kernel_launch_count', 'nvbx_debug_last_block_list', 'nvbx_debug_profile_stamps',
     'nvbx_debug_last_synthetic_depth', 'nvbx_version',
 ]
 
@@ -96,6 +96,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         L.nvbx_get_counters.argtypes = [vp, C.c_int, C.POINTER(NvbxCounters), vp]
         L.nvbx_reset_counters.argtypes = [vp, C.c_int, vp]
         L.nvbx_set_gather_tuning.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.nvbx_integrate_frames_batch.argtypes = [C.POINTER(NvbxFrameJob), C.c_int, C.c_int]
         L.nvbx_set_kernel_timing.argtypes = [vp, C.c_int]
         L.nvbx_get_kernel_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_double), i64p]
         L.nvbx_kernel_timing_report.argtypes = [vp, C.c_char_p, C.c_int64]

@@ -16,7 +16,10 @@
 #include <cstring>
 #include <deque>
 #include <memory>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <functional>
 #include <vector>
@@ -1947,6 +1950,111 @@ int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream_v) {
   if (rc) return rc;
   Map& mp = *m->maps[map_id];
   CUDA_TRY(cudaMemsetAsync(mp.d_ctrl->counters, 0, sizeof(unsigned long long) * kCntNum, (cudaStream_t)stream_v));
+  return NVBX_OK;
+}
+
+// ---- batched frames: a small persistent pool of host threads issues the launches of different maps concurrently
+namespace {
+class LaunchPool {
+ public:
+  // Runs fn(0) .. fn(n - 1), fn(0) on the calling thread; returns when all have returned.
+  void run(int n, const std::function<void(int)>& fn) {
+    if (n <= 1) {
+      if (n == 1) fn(0);
+      return;
+    }
+    std::unique_lock<std::mutex> lk(mu_);
+    while ((int)workers_.size() < n - 1) {
+      const int id = (int)workers_.size() + 1;
+      workers_.emplace_back([this, id] { loop(id); });
+    }
+    fn_ = &fn;
+    n_active_ = n;
+    pending_ = n - 1;
+    ++epoch_;
+    lk.unlock();
+    cv_work_.notify_all();
+    fn(0);
+    lk.lock();
+    cv_done_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void loop(int id) {
+    unsigned seen = 0;
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+      cv_work_.wait(lk, [&] { return epoch_ != seen; });
+      seen = epoch_;
+      if (id >= n_active_) continue;
+      const std::function<void(int)>* fn = fn_;
+      lk.unlock();
+      (*fn)(id);
+      lk.lock();
+      if (--pending_ == 0) cv_done_.notify_one();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_work_, cv_done_;
+  std::vector<std::thread> workers_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int n_active_ = 0, pending_ = 0;
+  unsigned epoch_ = 0;
+};
+LaunchPool& launch_pool() {
+  static LaunchPool* pool = new LaunchPool;  // never destroyed: its threads sleep until the process exits
+  return *pool;
+}
+std::mutex g_batch_mu;  // one batch at a time per process (the pool's dispatch state is single-batch)
+}  // namespace
+
+static_assert(sizeof(nvbx_frame_job) == 152, "nvbx_frame_job layout is part of the ABI (params.py: NvbxFrameJob)");
+
+int nvbx_integrate_frames_batch(nvbx_frame_job* jobs, int n_jobs, int n_threads) {
+  if (n_jobs < 0 || (n_jobs > 0 && !jobs)) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad job list");
+  if (n_jobs == 0) return NVBX_OK;
+  // distinct handles in order of first appearance; every job of a handle goes to the same worker, in job order
+  std::vector<nvbx_mapper*> handles;
+  std::vector<int> owner(n_jobs);
+  for (int i = 0; i < n_jobs; ++i) {
+    if (!jobs[i].mapper) return fail(NVBX_ERR_INVALID_ARGUMENT, "job %d: null mapper handle", i);
+    size_t k = 0;
+    while (k < handles.size() && handles[k] != jobs[i].mapper) ++k;
+    if (k == handles.size()) handles.push_back(jobs[i].mapper);
+    owner[i] = (int)k;
+    jobs[i].status = NVBX_OK;
+  }
+  const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+  const int n_workers = std::max(1, std::min({n_threads <= 0 ? hw : n_threads, (int)handles.size(), 64}));
+  std::mutex err_mu;
+  std::string first_error;
+  int first_rc = NVBX_OK, first_job = n_jobs;
+  auto work = [&](int w) {
+    for (int i = 0; i < n_jobs; ++i) {
+      if (owner[i] % n_workers != w) continue;
+      nvbx_frame_job& j = jobs[i];
+      int rc = nvbx_integrate_depth(j.mapper, j.map_id, j.depth, j.height, j.width, j.depth_mask, j.T_L_C, j.fx, j.fy,
+                                    j.cx, j.cy, j.stream);
+      if (rc == NVBX_OK && j.features)
+        rc = nvbx_integrate_features(j.mapper, j.map_id, j.features, j.height, j.width, j.channels, j.feature_mask,
+                                     j.T_L_C, j.fx, j.fy, j.cx, j.cy, j.stream);
+      j.status = rc;
+      if (rc < 0) {
+        std::lock_guard<std::mutex> g(err_mu);
+        if (i < first_job) {
+          first_job = i;
+          first_rc = rc;
+          first_error = g_last_error;  // this worker's thread-local message
+        }
+      }
+    }
+  };
+  {
+    std::lock_guard<std::mutex> g(g_batch_mu);
+    launch_pool().run(n_workers, work);
+  }
+  if (first_rc < 0) return fail(first_rc, "job %d: %s", first_job, first_error.c_str());
   return NVBX_OK;
 }
 

@@ -79,3 +79,26 @@ WEIGHTING_MODES = {
     'kLinearWithMax': 5,
 }
 WORKSPACE_BOUNDS_TYPES = {'kUnbounded': 0, 'kHeightBounds': 1, 'kBoundingBox': 2}
+
+
+class NvbxFrameJob(C.Structure):
+    """`nvbx_frame_job` of include/nvbx_c_api.h (one map's frame inside nvbx_integrate_frames_batch)."""
+    _fields_ = [
+        ('mapper', C.c_void_p),
+        ('map_id', C.c_int32),
+        ('height', C.c_int32),
+        ('width', C.c_int32),
+        ('channels', C.c_int32),
+        ('depth', C.c_void_p),
+        ('depth_mask', C.c_void_p),
+        ('features', C.c_void_p),
+        ('feature_mask', C.c_void_p),
+        ('T_L_C', C.c_float * 16),
+        ('fx', C.c_float),
+        ('fy', C.c_float),
+        ('cx', C.c_float),
+        ('cy', C.c_float),
+        ('stream', C.c_void_p),
+        ('status', C.c_int32),
+        ('reserved', C.c_int32),
+    ]

@@ -178,3 +178,17 @@ def test_replica_partitioning():
         assert all(len(o) == 64 // world for o in owned)
         assert all(owner_of_map(m, world) == r for r, o in enumerate(owned) for m in o)
     assert aggregate_throughput([10, 10], [1.0, 2.0]) == 10.0
+
+
+def test_frames_batch_argument_errors_without_gpu():
+    """nvbx_integrate_frames_batch validates its job list before touching the device."""
+    import ctypes as C
+    from nvblox_mindmap_b200 import _capi
+    from nvblox_mindmap_b200.params import NvbxFrameJob
+    lib = _capi.load()
+    assert C.sizeof(NvbxFrameJob) == 152
+    assert lib.nvbx_integrate_frames_batch(None, 0, 0) == 0
+    assert lib.nvbx_integrate_frames_batch(None, 2, 0) < 0
+    jobs = (NvbxFrameJob * 2)()
+    assert lib.nvbx_integrate_frames_batch(jobs, 2, 4) < 0
+    assert b'null mapper handle' in lib.nvbx_last_error()

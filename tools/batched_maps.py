@@ -59,6 +59,38 @@ def main():
         rows.append({'maps': M, 'frames_per_s': M * n_timed / (ms / 1e3), 'us_per_frame': 1e3 * ms / (M * n_timed),
                      'host_enqueue_us_per_frame': 1e6 * host / (M * n_timed), 'feature_voxels_updated': upd})
         print(json.dumps(rows[-1]), flush=True)
+        # the same M maps, one HOST THREAD per map (ctypes releases the GIL inside the C ABI, so the launches of
+        # different maps are issued concurrently; only the thin Python wrappers serialise)
+        import threading
+        start = threading.Barrier(M + 1)
+
+        def worker(k):
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(streams[k]):
+                start.wait()
+                for i in range(n_warm, n):
+                    j = (i + 7 * k) % n
+                    mappers[k].add_depth_frame(depths[j], poses[j], K_t)
+                    mappers[k].add_feature_frame(feats[(i + k) % len(feats)], poses[j], K_t)
+
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(M)]
+        for t in threads:
+            t.start()
+        torch.cuda.synchronize()
+        e0.record()
+        t0 = time.perf_counter()
+        start.wait()
+        for t in threads:
+            t.join()
+        host = time.perf_counter() - t0
+        for s in streams:
+            torch.cuda.current_stream().wait_stream(s)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        rows.append({'maps': M, 'host_threads': M, 'frames_per_s': M * n_timed / (ms / 1e3),
+                     'us_per_frame': 1e3 * ms / (M * n_timed), 'host_enqueue_us_per_frame': 1e6 * host / (M * n_timed)})
+        print(json.dumps(rows[-1]), flush=True)
         del mappers
     return rows
 
