@@ -263,7 +263,9 @@ def run_ours(args, rank, world, local_rank):
         mapper.add_feature_frame(feats[i % N_FEATURE_BUFFERS], poses[i], K_t)
         ev[j][1].record()
     torch.cuda.synchronize()
-    feat_call_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    feat_calls = np.array([a.elapsed_time(b) for a, b in ev])
+    feat_call_ms = float(np.mean(feat_calls))
+    feat_call_pct = [float(np.percentile(feat_calls, q)) for q in (10, 50, 90)]   # median, p10 / p90
 
     # ---- end-to-end pass: HOST frames through the public API ----------------------------------------------
     # Headline e2e = the default host entry: depth copied H2D, the pinned feature frame read through its device
@@ -346,7 +348,7 @@ def run_ours(args, rank, world, local_rank):
                              'sample': f"first {sample_mt['frames']} frames of the workload through the CPU oracle "
                                        f"(OpenMP over blocks, {n_cores} threads, {sample_mt['seconds']:.1f} s); "
                                        f"1 thread, first {sample['frames']} frames: {sample['fps']:.3f} frames/s"},
-            'extra': {'feature_call_ms': feat_call_ms, 'host_enqueue_ms_per_step': 1000.0 * t_host / args.steps,
+            'extra': {'feature_call_ms': feat_call_ms, 'feature_call_ms_p10_p50_p90': feat_call_pct, 'host_enqueue_ms_per_step': 1000.0 * t_host / args.steps,
                       'per_kernel_us_in_pipeline': per_kernel, 'export_stage': export,
                       'fused_upsample': fused, 'batched_maps_one_gpu': batched, 'drill_in_box': drill,
                       'counters_per_step': {k: v / args.steps for k, v in counters.items()
