@@ -177,8 +177,27 @@ def scenario_threedmatch(drv_cls):
     return out
 
 
+def scenario_two_cameras_1cm_c1024(drv_cls):
+    """Drill-in-box / stress shape: head (static: viewpoint-cache hit on step 1) + wrist camera per step, 1 cm
+    voxels, 1024 channels (the 4 x 512-byte chunk path), drill-in-box workspace, decay 0.999."""
+    mp, op = make_params(workspace=S.WS_DRILL_IN_BOX, decay=0.999, strict=True)
+    drv = drv_cls(0.01, 1024, mp, op)
+    out = []
+    K = S.intrinsics(80, 80)
+    T_head = S.look_at((-0.2, 0.0, 0.6), (0.4, 0.0, 0.05))
+    for i in range(2):
+        if i:
+            drv.decay()
+        for cam, T in enumerate((T_head, S.orbit_pose(i, 64, 0.4, 0.45))):
+            drv.depth(S.render_depth(K, 80, 80, T, **S.S_TABLE), T, K)
+            drv.features(S.feature_frame(80, 80, 1024, 5000 + 2 * i + cam), T, K)
+            out.append(_record(drv, with_mesh=(i == 1 and cam == 1)))
+    return out
+
+
 SCENARIOS = {
     'table_orbit': scenario_table_orbit,
     'blend_alpha03': scenario_blend_alpha03,
     'threedmatch': scenario_threedmatch,
+    'two_cameras_1cm_c1024': scenario_two_cameras_1cm_c1024,
 }
