@@ -145,7 +145,13 @@ const char* nvbx_last_error(void);
 /* ---- frame integration -------------------------------------------------------------------------- */
 
 /* Mapper::integrateDepth, py_mapper.cu:85-113 -> nvblox::Mapper::integrateDepth mapper.cpp:358-407.
- * depth: device float[H*W] row-major; mask: device uint8[H*W] or NULL (non-zero = active). */
+ * depth: device float[H*W] row-major; mask: device uint8[H*W] or NULL (non-zero = active).
+ * Stream contract: the depth image must be complete in stream order, as for any kernel argument.  The ray-casting
+ * kernel is a programmatic dependent launch that reads the image (and nothing else in memory) BEFORE its
+ * griddepcontrol.wait, to overlap the previous frame's feature kernel; this is invisible as long as the image's
+ * producer is an ordinary stream operation (memcpy, any kernel that does not itself execute
+ * griddepcontrol.launch_dependents before its last write to the image) -- true of torch, cuBLAS/cuDNN and this
+ * library's own outputs.  NVBX_PDL=0 disables programmatic launches altogether. */
 int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int height, int width,
                          const void* mask, const float* T_L_C, float fx, float fy, float cx, float cy,
                          void* stream);
