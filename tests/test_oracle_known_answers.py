@@ -536,3 +536,181 @@ def test_lowres_descriptor_follows_torchs_kernel_choice():
     small = torch.randn(1, 4, 4, 8).permute(0, 3, 1, 2)                 # channels-last but < 16 channels: NCHW kernel
     assert lowres_descriptor(small)[4:] == (0, 1, 0)
     assert lowres_descriptor(torch.randn(24, 4, 4).bfloat16())[4:] == (2, 0, 0)
+
+
+# ---- test_tsdf_integrator.cpp:359-474 (WeightingFunction), integration level ----------------------------------
+def _cam_640x480_f300():
+    return np.array([[300, 0, 320], [0, 300, 240], [0, 0, 1]], np.float32)
+
+
+def _voxel_centres(idx, voxel):
+    """[N, 8, 8, 8, 3] voxel centre positions of blocks `idx` (getCenterPositionFromBlockIndexAndVoxelIndex)."""
+    g = (np.arange(8, dtype=np.float32) + np.float32(0.5)) * np.float32(voxel)
+    o = idx.astype(np.float32)[:, None, None, None, :] * np.float32(8 * voxel)
+    X, Y, Z = np.meshgrid(g, g, g, indexing='ij')
+    return o + np.stack([X, Y, Z], -1)[None]
+
+
+def test_tsdf_weights_constant_and_inverse_square_on_a_plane():
+    K, T = _cam_640x480_f300(), np.eye(4, dtype=np.float32)
+    depth = np.full((480, 640), 5.0, np.float32)       # plane z = 5 seen from the origin: depth == 5 everywhere
+    for mode, name in ((0, 'constant'), (2, 'inverse_square')):
+        p = O.default_params()
+        p.max_weight = 100.0
+        p.weighting_mode = mode
+        m = O.OracleMapper(0.2, 8, p)
+        m.add_depth_frame(depth, T, K)
+        idx, data = m.all_blocks(0)
+        assert len(idx) > 0
+        w = data[..., 1]
+        seen = w > 1e-4
+        assert seen.sum() > 1000
+        if name == 'constant':
+            assert np.abs(w[seen] - 1.0).max() < 1e-4
+        else:
+            z = _voxel_centres(idx, 0.2)[..., 2]
+            assert np.abs(w[seen] - 1.0 / (z[seen] * z[seen])).max() < 1e-4      # hand-computed 1 / depth^2
+
+
+# ---- test_workspace_bounds.cpp:40-118 (CheckAllocatedBlocks) --------------------------------------------------
+def test_workspace_bounds_restrict_the_allocated_blocks():
+    K, T = _cam_640x480_f300(), np.eye(4, dtype=np.float32)
+    depth = np.full((480, 640), 5.0, np.float32)
+    lo, hi = np.float32([-3, -3, 2]), np.float32([3, 3, 4])
+    counts = {}
+    for kind, name in ((0, 'unbounded'), (1, 'height'), (2, 'box')):
+        p = O.default_params()
+        p.workspace_bounds_type = kind
+        for i in range(3):
+            p.workspace_min[i], p.workspace_max[i] = float(lo[i]), float(hi[i])
+        m = O.OracleMapper(0.1, 8, p)
+        m.add_depth_frame(depth, T, K)
+        idx, _ = m.all_blocks(0)
+        assert len(idx) > 0
+        # every allocated block has at least one voxel (corner position, as the reference test computes it)
+        # inside the bounds
+        g = np.arange(8, dtype=np.float32) * np.float32(0.1)
+        pos_lo = idx.astype(np.float32) * np.float32(0.8)
+        pos_hi = pos_lo + g[-1]
+        if name == 'height':
+            assert np.all((pos_hi[:, 2] >= lo[2]) & (pos_lo[:, 2] <= hi[2]))
+        elif name == 'box':
+            assert np.all((pos_hi >= lo).all(1) & (pos_lo <= hi).all(1))
+        counts[name] = len(idx)
+    assert counts['box'] > 0
+    assert counts['height'] > counts['box'] and counts['unbounded'] > counts['box']
+
+
+# ---- test_mesh.cpp:101-155 (PlaneMesh) and :423-462 (WeldingTest) ---------------------------------------------
+def _plane_x0_layer(m, voxel, weld_scene=False):
+    """generateLayerFromScene for the tests' scenes inside the 6 x 6 x 3 m AABB: plane x = 0 with normal -x
+    (distance = -x); WeldingTest adds the plane y = 0.1 (normal -y) and the sphere c = (-2, -2, 0), r = 2."""
+    trunc = np.float32(4 * voxel)
+    bs = 8 * voxel
+    nb = int(round(3.0 / bs)) + 1
+    g = (np.arange(8, dtype=np.float32) + np.float32(0.5)) * np.float32(voxel)
+    n = 0
+    for bx in range(-nb, nb):
+        for by in range(-nb, nb):
+            for bz in range(0, nb):
+                o = np.float32([bx, by, bz]) * np.float32(bs)
+                X, Y, Z = np.meshgrid(o[0] + g, o[1] + g, o[2] + g, indexing='ij')
+                d = -X
+                if weld_scene:
+                    d = np.minimum(d, -(Y - np.float32(0.1)))
+                    d = np.minimum(d, np.sqrt((X + 2) ** 2 + (Y + 2) ** 2 + Z ** 2) - np.float32(2.0))
+                if np.abs(d).min() > trunc + bs:
+                    continue
+                blk = np.zeros((8, 8, 8, 2), np.float32)
+                blk[..., 0] = np.clip(d, -trunc, trunc)
+                blk[..., 1] = 1.0
+                m.set_tsdf_block((bx, by, bz), blk)
+                n += 1
+    return n
+
+
+def test_plane_mesh_vertices_lie_on_the_plane():
+    p = O.default_params()
+    p.mesh_weld_vertices = 0
+    m = O.OracleMapper(0.1, 8, p)
+    n_sdf = _plane_x0_layer(m, 0.1)
+    m.mark_all_dirty()
+    m.update_feature_mesh()
+    v, _, t, vb = m.get_feature_mesh(with_block_index=True)
+    n_mesh_blocks = len(np.unique(vb, axis=0))
+    assert 0 < n_mesh_blocks <= n_sdf
+    assert len(v) > 0 and len(v) == 3 * len(t)          # unwelded: one vertex per triangle corner
+    assert np.abs(v[:, 0]).max() < 1e-4                   # EXPECT_NEAR(vertex.x(), 0.0, kFloatEpsilon)
+
+
+def test_welding_removes_duplicate_vertices_in_every_block():
+    counts = {}
+    for weld in (0, 1):
+        p = O.default_params()
+        p.mesh_weld_vertices = weld
+        m = O.OracleMapper(0.1, 8, p)
+        _plane_x0_layer(m, 0.1, weld_scene=True)
+        m.mark_all_dirty()
+        m.update_feature_mesh()
+        v, _, t, vb = m.get_feature_mesh(with_block_index=True)
+        blocks, n_per_block = np.unique(vb, axis=0, return_counts=True)
+        counts[weld] = {tuple(b): int(c) for b, c in zip(blocks, n_per_block)}
+        counts[weld, 'tris'] = len(t)
+    assert counts[0, 'tris'] == counts[1, 'tris'] > 0     # welding re-indexes, it does not drop triangles
+    assert counts[0].keys() == counts[1].keys() and len(counts[0]) > 0
+    for b, pre in counts[0].items():                       # EXPECT_LT(num_vertices_postweld, num_vertices_preweld)
+        assert counts[1][b] < pre, b
+
+
+# ---- test_tsdf_integrator.cpp:168-263 (SphereSceneTest) -------------------------------------------------------
+def _sphere_in_box_depth(K, T, H, W, max_dist=10.0):
+    """Depth image of test_utils::getSphereInBox(): sphere c = (0, 0, 2), r = 2 inside the box
+    [-5, 5] x [-5, 5] x [0, 5] seen from INSIDE the box (generateDepthImageFromScene, rays cut at 10 m)."""
+    u = (np.arange(W, dtype=np.float64) + 0.5 - K[0, 2]) / K[0, 0]
+    v = (np.arange(H, dtype=np.float64) + 0.5 - K[1, 2]) / K[1, 1]
+    uu, vv = np.meshgrid(u, v)
+    d = np.stack([uu, vv, np.ones_like(uu)], -1) @ T[:3, :3].astype(np.float64).T
+    o = T[:3, 3].astype(np.float64)
+    lo, hi = np.array([-5.0, -5.0, 0.0]), np.array([5.0, 5.0, 5.0])
+    with np.errstate(divide='ignore', invalid='ignore'):
+        t_wall = np.where(d > 0, (hi - o) / d, np.where(d < 0, (lo - o) / d, np.inf)).min(-1)
+    oc = o - np.array([0.0, 0.0, 2.0])
+    a, b, c = (d * d).sum(-1), 2.0 * (d * oc).sum(-1), (oc * oc).sum() - 4.0
+    disc = b * b - 4 * a * c
+    with np.errstate(invalid='ignore'):
+        t_s = (-b - np.sqrt(disc)) / (2 * a)
+    t_s[~(disc >= 0) | ~(t_s > 1e-6)] = np.inf
+    t = np.minimum(t_wall, t_s)
+    norm = np.sqrt((d * d).sum(-1))                         # ray length per unit of depth
+    t[t * norm > max_dist] = 0.0
+    return t.astype(np.float32)
+
+
+def test_sphere_in_box_orbit_matches_the_analytic_tsdf():
+    K = _cam_640x480_f300()
+    voxel, trunc = 0.2, 0.4
+    p = O.default_params()
+    p.truncation_distance_vox = 2.0
+    m = O.OracleMapper(voxel, 8, p)
+    base = np.array([[0, 0, 1], [1, 0, 0], [0, 1, 0]], np.float64)      # quaternion (w, x, y, z) = (.5, .5, .5, .5)
+    n_poses = 80
+    for i in range(n_poses):
+        th = 2 * np.pi / n_poses * i
+        a = np.pi + th
+        Rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+        T = np.eye(4, dtype=np.float32)
+        T[:3, :3] = (Rz @ base).astype(np.float32)
+        T[:3, 3] = np.float32([4 * np.cos(th), 4 * np.sin(th), 2.0])
+        m.add_depth_frame(_sphere_in_box_depth(K, T, 480, 640), T, K)
+    idx, data = m.all_blocks(0)
+    c = _voxel_centres(idx, voxel).astype(np.float64)
+    inside = ((c >= [-5, -5, 0]) & (c <= [5, 5, 5])).all(-1)           # the ground-truth layer covers the scene AABB
+    gt = np.minimum.reduce([np.sqrt(c[..., 0] ** 2 + c[..., 1] ** 2 + (c[..., 2] - 2) ** 2) - 2.0,
+                            c[..., 2], 5 - c[..., 2], c[..., 0] + 5, 5 - c[..., 0], c[..., 1] + 5, 5 - c[..., 1]])
+    gt = np.clip(gt, -trunc, trunc)
+    sel = (data[..., 1] >= 1.0) & inside                               # kMinWeight = 1.0
+    assert sel.sum() > 20000
+    big = np.abs(data[..., 0][sel] - gt[sel]) > trunc                  # kDistanceErrorTolerance = truncation
+    assert 100.0 * big.mean() < 0.4                                    # kAcceptablePercentageOverThreshold
+    # tighter than the reference asks: the fused distances are unbiased estimates of the analytic field
+    assert np.abs(data[..., 0][sel] - gt[sel]).mean() < 0.25 * voxel
