@@ -347,3 +347,25 @@ def test_color_and_feature_share_the_planes_viewpoint_cache():
             assert np.array_equal(g, c) and len(g) > 0
         assert pair.check_color() > 0
         assert pair.check_features() > 0
+
+
+@pytest.mark.parametrize('bounds,weighting', [('kHeightBounds', 'kConstantWeight'),
+                                              ('kBoundingBox', 'kInverseSquareDropoffWeight'),
+                                              ('kUnbounded', 'kConstantDropoffWeight')])
+def test_workspace_bound_types_and_weighting_modes(bounds, weighting):
+    """The reference's other WorkspaceBoundsType / WeightingFunctionType values (test_workspace_bounds.cpp,
+    test_weighting_function.cpp): same block sets and bit-exact TSDF / features as the oracle."""
+    from tests.parity_utils import oracle_params_from
+    mp, _ = make_params(workspace=((-0.3, -0.5, 0.02), (0.9, 0.5, 0.3)), weighting=weighting, max_dist=3.0, strict=True)
+    vc = mp._view_calculator_params
+    vc.workspace_bounds_type = bounds
+    mp._projective_integrator_params.projective_integrator_max_weight = 100.0
+    pair = Pair(0.04, 16, mp, oracle_params_from(mp))
+    for i, T, K, depth, feat in orbit_frames(3, 96, 128, 16, S.S_TABLE, radius=0.8, height=0.7):
+        pair.depth(depth, T, K)
+        g, c = pair.last_block_list(0)
+        assert np.array_equal(g, c) and len(g) > 0
+        pair.features(feat, T, K)
+    assert pair.check_tsdf() > 0
+    assert pair.check_features(max_ulp=0) > 0
+    assert pair.check_mesh() > 0
