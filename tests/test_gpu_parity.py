@@ -369,3 +369,43 @@ def test_workspace_bound_types_and_weighting_modes(bounds, weighting):
     assert pair.check_tsdf() > 0
     assert pair.check_features(max_ulp=0) > 0
     assert pair.check_mesh() > 0
+
+
+def test_empty_and_degenerate_inputs():
+    """Edge cases the reference's tests touch (test_mesh.cpp BlankMap, test_mesh.py empty shapes, masks that hide
+    everything, invalid depth): nothing is allocated, nothing crashes, shapes are empty, and the map still works
+    afterwards.  Each step is mirrored on the oracle."""
+    mp, op = make_params(workspace=S.WS_CUBE_STACKING)
+    pair = Pair(0.02, 24, mp, op)
+    H, W = 72, 104                                   # non-square, not a multiple of 16
+    K = S.intrinsics(W, H)
+    T = S.orbit_pose(3)
+    feat = S.feature_frame(H, W, 24, 11)
+    # blank map: features / decay / mesh / export on nothing
+    pair.features(feat, T, K)
+    pair.decay()
+    assert pair.check_mesh() == 0
+    mesh = pair.gpu.get_feature_mesh(0)
+    assert tuple(mesh.vertices().shape) == (0, 3) and tuple(mesh.vertex_features().shape) == (0, 24)
+    assert tuple(mesh.triangles().shape) == (0, 3)
+    assert pair.gpu.tsdf_layer_view(0).num_blocks() == 0 and pair.gpu.feature_layer_view(0).num_blocks() == 0
+    # invalid depth everywhere (0 = no return; NaN) and a mask that hides a valid frame
+    depth = S.render_depth(K, H, W, T, **S.S_TABLE)
+    pair.depth(np.zeros((H, W), np.float32), T, K)
+    pair.depth(np.full((H, W), np.nan, np.float32), T, K)
+    assert pair.check_tsdf() == 0
+    pair.depth(depth, T, K, mask=np.zeros((H, W), np.uint8))
+    pair.check_tsdf()
+    pair.features(feat, T, K, mask=np.zeros((H, W), np.uint8))
+    pair.check_features(max_ulp=1)
+    assert pair.gpu.counters(0)['feature_voxels_updated'] == pair.cpu.counters()['feature_voxels_updated'] == 0
+    # ... and the same map keeps working.  (From the SAME pose it would not: the viewpoint cache holds the empty
+    # block list of the zero-depth frame for that pose -- view_calculator.cu:256-265 -- on both sides.)
+    assert pair.check_tsdf() == 0
+    T = S.orbit_pose(9)
+    depth = S.render_depth(K, H, W, T, **S.S_TABLE)
+    pair.depth(depth, T, K)
+    pair.features(feat, T, K)
+    assert pair.check_tsdf() > 0 and pair.check_features(max_ulp=1) > 0 and pair.check_mesh() > 0
+    pair.clear()
+    assert pair.check_tsdf() == 0 and pair.check_mesh() == 0
