@@ -5,22 +5,29 @@
 // mesh.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load this library; the product (libnvbx.so) never links, imports or calls it.
 //
-// PARITY STATUS: "pinned by known-answer tests only".  The reference (nvblox @ 9be399a) cannot be
-// compiled in the authoring container (Eigen, stdgpu, glog are fetched at CMake time and absent), and
-// the repo holds no stored numeric goldens for this path (mindmap's baselines are Git-LFS stubs).  The
-// oracle is therefore pinned against the reference's own known-answer tests, restated in
-// tests/test_oracle_known_answers.py: test_feature_integrator.cpp:131-203, test_ray_caster.cpp,
+// PARITY STATUS: pinned (a) by the reference's own known-answer tests, restated in
+// tests/test_oracle_known_answers.py (test_feature_integrator.cpp:131-203, test_ray_caster.cpp,
 // test_interpolation_2d.cpp, test_weighting_function / test_tsdf_integrator.cpp:359-474,
-// test_mapper_masking.py:35-80,170-198, test_tsdf_decay.cpp, test_mesh.cpp (plane), numpy float16 for
-// the software half.
+// test_mapper_masking.py:35-80,170-198, test_tsdf_decay.cpp, test_mesh.cpp), and (b) BIT FOR BIT by
+// reference-compiled vectors: the reference's own device kernels (integrateBlocksKernel for TSDF / feature /
+// colour voxels, combinedBlockIndicesInImageKernel, sphereTracingKernel, the marching-cubes and mesh-appearance
+// kernels) compiled verbatim with nvblox's nvcc flags (oracle/ref_snippets/) and run on a B200 on seeded
+// inputs (tests/golden/make_ref_vectors.py -> tests/golden/ref_nvcc_*.npz; tests/test_ref_vectors.py).
+// The whole nvblox library cannot be built offline (Eigen, stdgpu, glog are fetched at CMake time), so the
+// reference's HOST code (view AABB, planes view, viewpoint cache, allocation) is pinned by (a) only, and the
+// Eigen expressions inside the kernels were compiled against a stand-in that evaluates them in Eigen 3.4's
+// order (oracle/ref_snippets/shim/Eigen/Core) -- that residual is stated in DESIGN.md section 5.
 //
-// Floating-point model: every fp32 operation is a single IEEE-754 round-to-nearest operation in the
-// order Eigen 3.4.0 evaluates the reference's expressions (3-element reductions are a0 + (a1 + a2),
-// Eigen/src/Core/Redux.h unrolled tree; Isometry * v = t + (R.row . v)); build with
-// -ffp-contract=off.  nvcc may contract mul+add into fma in the reference's device code; that is
-// unknowable without building it, so the oracle (and the CUDA product, built with -fmad=false) use
-// the uncontracted sequence.  fp16 arithmetic is one RNE rounding per operator, as
-// __hmul/__hadd/__hsub define; ORC_FUSED_HALF=1 selects the fma-contracted variant for comparison.
+// Floating-point model (orc_set_fp_model):
+//   1 = "nvcc" (DEFAULT): what the reference BINARY computes.  nvblox passes no -fmad flag
+//       (NB/cmake/nvblox_targets.cmake:128-152), so nvcc -O2 contracts mul+add pairs in DEVICE code into
+//       single-rounding fma (NVVM contracts a*b+c; ptxas fuses the mul.f32 / add.f32 and mul.f16 / add.f16 it
+//       is left with).  Every contracted expression below is written as an explicit fmaf / hfma in the
+//       operand order read from the PTX / SASS of oracle/ref_snippets (profiles/r02_ref_contraction.md).
+//       HOST code of the reference is gcc x86-64 -O2 without -mfma: never contracted.
+//   0 = "ieee": every operation individually rounded (round 1's model), kept for comparison.
+// fp16 arithmetic is one RNE rounding per operator (__hmul/__hadd/__hsub) or per fused hfma.
+// Build with -ffp-contract=off so the compiler adds no contraction of its own.
 //
 // Every function cites the reference file:line (relative to /root/reference) it follows.
 //   NB/ = submodules/nvblox/nvblox/      NT/ = submodules/nvblox/nvblox_torch/
@@ -109,6 +116,26 @@ inline Pose pose_from_row_major(const float* m) {  // NT/cpp/src/convert_tensors
 }
 
 // ------------------------------------------------------------------------------------------------
+// Floating-point model switch and the DEVICE-code variants of the geometry (see the header).
+// Operand orders are the ones nvcc 12.9 -O2 emits for the reference's expressions
+// (oracle/ref_snippets, profiles/r02_ref_contraction.md).
+// ------------------------------------------------------------------------------------------------
+int g_fp_model = 1;
+inline bool nvcc_model() { return g_fp_model != 0; }
+
+// R.row(i) . v on the device: Eigen's a0 + (a1 + a2) becomes fma(v.x, R0, fma(v.y, R1, v.z * R2))
+inline float dev_dot3(const float* r, const V3& v) {
+  if (!nvcc_model()) return sum3(r[0] * v.x, r[1] * v.y, r[2] * v.z);
+  return std::fmaf(v.x, r[0], std::fmaf(v.y, r[1], v.z * r[2]));
+}
+inline V3 dev_rotate(const Pose& T, const V3& v) { return V3{dev_dot3(T.R[0], v), dev_dot3(T.R[1], v), dev_dot3(T.R[2], v)}; }
+// Transform * Vector3f on the device: the translation is added last, unfused (add.f32 of the fma chain)
+inline V3 dev_xform(const Pose& T, const V3& v) {
+  return V3{T.t[0] + dev_dot3(T.R[0], v), T.t[1] + dev_dot3(T.R[1], v), T.t[2] + dev_dot3(T.R[2], v)};
+}
+inline float dev_fma(float a, float b, float c) { return nvcc_model() ? std::fmaf(a, b, c) : a * b + c; }
+
+// ------------------------------------------------------------------------------------------------
 // Software binary16.  Conversions are round-to-nearest-even like cvt.rn.f16.f32; NaN -> 0x7fff like
 // CUDA's __float2half.  +,-,* of two halves computed in fp32 and rounded once to half are correctly
 // rounded (24 >= 2*11+2, Figueroa), which is what __hadd/__hsub/__hmul return.
@@ -185,19 +212,22 @@ inline uint16_t hfma(uint16_t a, uint16_t b, uint16_t c) {
   return f2h(f);
 }
 
-bool g_fused_half = false;
+// ORC "fused half": follows the floating-point model unless forced (orc_set_fused_half: -1 follow, 0 off, 1 on)
+int g_fused_half_override = -1;
+inline bool fused_half_on() { return g_fused_half_override < 0 ? nvcc_model() : g_fused_half_override != 0; }
 
 // NB/include/nvblox/interpolation/internal/impl/interpolation_2d_impl.h:33-48 with FloatType = __half:
 //   x = half(off.x), y = half(off.y), dx = f10 - f00
 //   out = f00 + x*dx + y*(f01 - f00) + x*y*(f11 - f01 - dx)          (C++ precedence, left to right)
 inline uint16_t interp_half(uint16_t x, uint16_t y, uint16_t f00, uint16_t f01, uint16_t f10, uint16_t f11) {
   const uint16_t dx = hsub(f10, f00);
-  if (!g_fused_half) {
+  if (!fused_half_on()) {
     const uint16_t t2 = hadd(f00, hmul(x, dx));
     const uint16_t t5 = hadd(t2, hmul(y, hsub(f01, f00)));
     const uint16_t t9 = hmul(hmul(x, y), hsub(hsub(f11, f01), dx));
     return hadd(t5, t9);
   } else {
+    // SASS of the reference: HFMA2(x, dx, f00); HFMA2(y, f01 - f00, .); HMUL2 x*y; HFMA2(xy, f11 - f01 - dx, .)
     const uint16_t t2 = hfma(x, dx, f00);
     const uint16_t t5 = hfma(y, hsub(f01, f00), t2);
     return hfma(hmul(x, y), hsub(hsub(f11, f01), dx), t5);
@@ -206,7 +236,9 @@ inline uint16_t interp_half(uint16_t x, uint16_t y, uint16_t f00, uint16_t f01, 
 // same formula in fp32 (FloatType = float), used for the synthetic depth image
 inline float interp_float(float x, float y, float f00, float f01, float f10, float f11) {
   const float dx = f10 - f00;
-  return ((f00 + x * dx) + y * (f01 - f00)) + (x * y) * ((f11 - f01) - dx);
+  if (!nvcc_model()) return ((f00 + x * dx) + y * (f01 - f00)) + (x * y) * ((f11 - f01) - dx);
+  // device code (the only caller of the fp32 form is the appearance kernel): three FFMAs
+  return std::fmaf(x * y, (f11 - f01) - dx, std::fmaf(y, f01 - f00, std::fmaf(x, dx, f00)));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -227,6 +259,21 @@ inline void block_and_voxel_from_position(float block_size, const V3& p, I3* b, 
   v->y = std::min((int)ry, 7);
   v->z = std::min((int)rz, 7);
 }
+// device form of the same (sphere tracer, query kernel): p - bs*b is one FFMA
+inline void dev_block_and_voxel_from_position(float block_size, const V3& p, I3* b, I3* v) {
+  if (!nvcc_model()) return block_and_voxel_from_position(block_size, p, b, v);
+  const float voxel_size = block_size * (1.0f / 8.0f);
+  const float inv = (float)(1.0 / (double)voxel_size);
+  *b = block_index_from_position(block_size, p);
+  const float rx = std::fmaf(-(float)b->x, block_size, p.x) * inv;
+  const float ry = std::fmaf(-(float)b->y, block_size, p.y) * inv;
+  const float rz = std::fmaf(-(float)b->z, block_size, p.z) * inv;
+  v->x = std::min((int)rx, 7);
+  v->y = std::min((int)ry, 7);
+  v->z = std::min((int)rz, 7);
+}
+// device form of the voxel centre (projectThreadVoxel): fma(bs, 1/16, fma(bs, b, (bs/8) * v))
+inline V3 dev_voxel_center(float block_size, const I3& b, const I3& v);
 inline V3 voxel_center(float block_size, const I3& b, const I3& v) {  // :51-81
   const float voxel_size = block_size * (1.0f / 8.0f);
   const float half_voxel = block_size * (0.5f / 8.0f);
@@ -234,6 +281,16 @@ inline V3 voxel_center(float block_size, const I3& b, const I3& v) {  // :51-81
   p.x = (block_size * (float)b.x + voxel_size * (float)v.x) + half_voxel;
   p.y = (block_size * (float)b.y + voxel_size * (float)v.y) + half_voxel;
   p.z = (block_size * (float)b.z + voxel_size * (float)v.z) + half_voxel;
+  return p;
+}
+
+inline V3 dev_voxel_center(float block_size, const I3& b, const I3& v) {
+  if (!nvcc_model()) return voxel_center(block_size, b, v);
+  const float voxel_size = block_size * (1.0f / 8.0f);
+  V3 p;
+  p.x = std::fmaf(block_size, 0.5f / 8.0f, std::fmaf(block_size, (float)b.x, voxel_size * (float)v.x));
+  p.y = std::fmaf(block_size, 0.5f / 8.0f, std::fmaf(block_size, (float)b.y, voxel_size * (float)v.y));
+  p.z = std::fmaf(block_size, 0.5f / 8.0f, std::fmaf(block_size, (float)b.z, voxel_size * (float)v.z));
   return p;
 }
 
@@ -249,6 +306,17 @@ inline bool project(const Cam& c, const V3& p, float* u, float* v) {  // camera_
   float vn = p.y / p.z;
   un = un * c.fu + c.cu;
   vn = vn * c.fv + c.cv;
+  if (un > (float)c.width || vn > (float)c.height || un < 0 || vn < 0) return false;
+  *u = un;
+  *v = vn;
+  return true;
+}
+// Camera::project inside a kernel: the intrinsics are applied with one FFMA each
+inline bool dev_project(const Cam& c, const V3& p, float* u, float* v) {
+  if (!nvcc_model()) return project(c, p, u, v);
+  if (!(p.z >= 1e-6f)) return false;
+  const float un = std::fmaf(p.x / p.z, c.fu, c.cu);
+  const float vn = std::fmaf(p.y / p.z, c.fv, c.cv);
   if (un > (float)c.width || vn > (float)c.height || un < 0 || vn < 0) return false;
   *u = un;
   *v = vn;
@@ -425,6 +493,47 @@ struct RayCaster {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Reference-kernel hooks (tests/golden/make_ref_vectors.py only).  When a hook is set, the oracle keeps
+// doing the reference's HOST work (view AABB, caches, allocation, candidate lists, band filter) but hands
+// the DEVICE stage to the callback, which runs the reference's own kernel (oracle/ref_snippets) on a GPU.
+// The maps such a run produces are the reference-compiled golden vectors the un-hooked oracle and the
+// CUDA product are compared against.  All pointers are host memory; poses are row-major 4x4; cam = fu,fv,cu,cv.
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+typedef int (*orc_hook_raycast_t)(const float* T_L_C, const float* cam, int W, int H, const float* depth,
+                                  float block_size, float max_dist, float behind, int subsampling,
+                                  const int* aabb_min, const int* aabb_size, uint8_t* grid);
+typedef int (*orc_hook_tsdf_t)(const float* T_C_L, const float* cam, int W, int H, const float* depth,
+                               const uint8_t* mask, float block_size, float max_dist, float trunc, float max_weight,
+                               float invalid_decay, int mode, const int* block_idx, int n, float* voxels);
+typedef int (*orc_hook_trace_t)(const float* T_L_C, const float* cam, int W, int H, const int* all_idx, int n_all,
+                                const float* voxels, float trunc, float block_size, int max_steps, float max_len,
+                                float eps, int subsample, float* out);
+typedef int (*orc_hook_feat_t)(const float* T_C_L, const float* cam, int W, int H, const uint16_t* img,
+                               const uint8_t* mask, const float* synth, int sub, float block_size, float max_dist,
+                               float trunc, float max_weight, float alpha, const int* block_idx, int n, uint16_t* fvox);
+typedef int (*orc_hook_color_t)(const float* T_C_L, const float* cam, int W, int H, const uint8_t* img,
+                                const uint8_t* mask, const float* synth, int sub, float block_size, float max_dist,
+                                float trunc, float max_weight, float alpha, const int* block_idx, int n, uint8_t* rgb,
+                                float* weight);
+}
+struct RefHooks {
+  orc_hook_raycast_t raycast = nullptr;
+  orc_hook_tsdf_t tsdf = nullptr;
+  orc_hook_trace_t trace = nullptr;
+  orc_hook_feat_t feat = nullptr;
+  orc_hook_color_t color = nullptr;
+} g_hooks;
+inline void pose_to_row_major(const Pose& T, float* m) {
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) m[i * 4 + j] = T.R[i][j];
+    m[i * 4 + 3] = T.t[i];
+  }
+  m[12] = m[13] = m[14] = 0.0f;
+  m[15] = 1.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Map storage
 // ------------------------------------------------------------------------------------------------
 struct TsdfBlock {
@@ -521,6 +630,14 @@ std::vector<I3> blocks_in_view_raycast(Oracle& o, const float* depth, int rows, 
   const int launched_cols = (int)std::ceil(n_cols / 16.0f) * 16;
   const V3 t_L{T_L_C.t[0], T_L_C.t[1], T_L_C.t[2]};
   const V3 origin_scaled{t_L.x / bs, t_L.y / bs, t_L.z / bs};
+  if (g_hooks.raycast) {
+    float Tm[16];
+    pose_to_row_major(T_L_C, Tm);
+    const float cm[4] = {cam.fu, cam.fv, cam.cu, cam.cv};
+    const int amn[3] = {mn.x, mn.y, mn.z}, asz[3] = {sx, sy, sz};
+    if (g_hooks.raycast(Tm, cm, cols, rows, depth, bs, max_dist, behind, s, amn, asz, grid.data()))
+      std::fprintf(stderr, "orc: raycast hook failed\n");
+  } else
   for (int rr = 0; rr < launched_rows; ++rr) {
     for (int rc = 0; rc < launched_cols; ++rc) {
       int prow = rr * s, pcol = rc * s;
@@ -533,7 +650,7 @@ std::vector<I3> blocks_in_view_raycast(Oracle& o, const float* depth, int rows, 
       const V3 ray = ray_from_image_plane(cam, (float)pcol + 0.5f, (float)prow + 0.5f);
       const float len = d + behind;
       const V3 p_C{len * ray.x, len * ray.y, len * ray.z};
-      const V3 p_L = xform(T_L_C, p_C);
+      const V3 p_L = dev_xform(T_L_C, p_C);   // device code (K1)
       const I3 b = block_index_from_position(bs, p_L);
       mark(b.x, b.y, b.z);
       RayCaster rc3(origin_scaled, V3{p_L.x / bs, p_L.y / bs, p_L.z / bs});
@@ -596,9 +713,9 @@ inline float weighting(int mode, float measured, float voxel_depth, float trunc)
 // projectThreadVoxel
 inline bool project_voxel(const Oracle& o, const I3& b, const I3& v, const Cam& cam, const Pose& T_C_L, float* u,
                           float* vv, float* depth) {
-  const V3 pl = voxel_center(o.block_size, b, v);
-  const V3 pc = xform(T_C_L, pl);
-  if (!project(cam, pc, u, vv)) return false;
+  const V3 pl = dev_voxel_center(o.block_size, b, v);
+  const V3 pc = dev_xform(T_C_L, pl);
+  if (!dev_project(cam, pc, u, vv)) return false;
   *depth = pc.z;
   const float max_depth = o.p.max_integration_distance_m;
   if (max_depth > 0.0f && *depth > max_depth) return false;
@@ -622,6 +739,31 @@ void integrate_depth(Oracle& o, const float* depth, int rows, int cols, const ui
   std::vector<TsdfBlock*> blk_ptrs(blocks.size());
   for (size_t i = 0; i < blocks.size(); ++i) blk_ptrs[i] = &o.tsdf[blocks[i]];
   int64_t n_updated = 0;
+  if (g_hooks.tsdf) {
+    float Tm[16];
+    pose_to_row_major(T_C_L, Tm);
+    const float cm[4] = {cam.fu, cam.fv, cam.cu, cam.cv};
+    std::vector<int> idx(blocks.size() * 3);
+    std::vector<float> vox(blocks.size() * 1024);
+    for (size_t i = 0; i < blocks.size(); ++i) {
+      idx[3 * i] = blocks[i].x;
+      idx[3 * i + 1] = blocks[i].y;
+      idx[3 * i + 2] = blocks[i].z;
+      for (int l = 0; l < 512; ++l) {
+        vox[i * 1024 + 2 * l] = blk_ptrs[i]->d[l];
+        vox[i * 1024 + 2 * l + 1] = blk_ptrs[i]->w[l];
+      }
+    }
+    if (g_hooks.tsdf(Tm, cm, cols, rows, depth, mask, o.block_size, o.p.max_integration_distance_m, trunc,
+                     o.p.max_weight, o.p.invalid_depth_decay_factor, o.p.weighting_mode, idx.data(), (int)blocks.size(),
+                     vox.data()))
+      std::fprintf(stderr, "orc: tsdf hook failed\n");
+    for (size_t i = 0; i < blocks.size(); ++i)
+      for (int l = 0; l < 512; ++l) {
+        blk_ptrs[i]->d[l] = vox[i * 1024 + 2 * l];
+        blk_ptrs[i]->w[l] = vox[i * 1024 + 2 * l + 1];
+      }
+  } else
   // blocks are independent: OpenMP over blocks does not change any result
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : n_updated)
   for (size_t bi = 0; bi < blocks.size(); ++bi) {
@@ -650,7 +792,8 @@ void integrate_depth(Oracle& o, const float* depth, int rows, int cols, const ui
           const float d_cur = blk.d[l];
           const float w_cur = blk.w[l];
           const float w_m = weighting(o.p.weighting_mode, meas, vd, trunc);
-          float fused = (sdf * w_m + d_cur * w_cur) / (w_m + w_cur);
+          // (sdf*w_m + d_cur*w_cur) / (w_m + w_cur); contracted: FMUL sdf*w_m, FFMA(d_cur, w_cur, .)
+          float fused = (nvcc_model() ? std::fmaf(d_cur, w_cur, sdf * w_m) : (sdf * w_m + d_cur * w_cur)) / (w_m + w_cur);
           if (fused > 0.0f)
             fused = std::fmin(trunc, fused);
           else
@@ -714,9 +857,9 @@ inline bool sphere_cast(const Oracle& o, const V3& origin, const V3& dir, float 
   float t = 0.0f;
   for (int i = 0; (i < o.p.sphere_tracing_max_steps) && (t < o.p.sphere_tracing_max_ray_length_m); ++i) {
     *steps_out = i + 1;
-    const V3 p{origin.x + t * dir.x, origin.y + t * dir.y, origin.z + t * dir.z};
+    const V3 p{dev_fma(t, dir.x, origin.x), dev_fma(t, dir.y, origin.y), dev_fma(t, dir.z, origin.z)};
     I3 b, v;
-    block_and_voxel_from_position(o.block_size, p, &b, &v);
+    dev_block_and_voxel_from_position(o.block_size, p, &b, &v);
     float step;
     auto it = o.tsdf.find(b);
     bool valid = false;
@@ -765,6 +908,29 @@ void render_synthetic_depth(Oracle& o, const Cam& cam, const Pose& T_L_C, float 
   o.synth_cols = cols;
   const V3 origin{T_L_C.t[0], T_L_C.t[1], T_L_C.t[2]};
   int64_t steps_total = 0, steps_max = 0;
+  if (g_hooks.trace) {
+    float Tm[16];
+    pose_to_row_major(T_L_C, Tm);
+    const float cm[4] = {cam.fu, cam.fv, cam.cu, cam.cv};
+    std::vector<int> idx;
+    std::vector<float> vox;
+    idx.reserve(o.tsdf.size() * 3);
+    vox.reserve(o.tsdf.size() * 1024);
+    for (const auto& kv : o.tsdf) {
+      idx.push_back(kv.first.x);
+      idx.push_back(kv.first.y);
+      idx.push_back(kv.first.z);
+      for (int l = 0; l < 512; ++l) {
+        vox.push_back(kv.second.d[l]);
+        vox.push_back(kv.second.w[l]);
+      }
+    }
+    if (g_hooks.trace(Tm, cm, cam.width, cam.height, idx.data(), (int)o.tsdf.size(), vox.data(), trunc, o.block_size,
+                      o.p.sphere_tracing_max_steps, o.p.sphere_tracing_max_ray_length_m,
+                      o.p.sphere_tracing_surface_epsilon_vox * o.voxel_size, s, o.synth.data()))
+      std::fprintf(stderr, "orc: trace hook failed\n");
+    return;
+  }
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : steps_total) reduction(max : steps_max)
   for (int r = 0; r < rows; ++r)
     for (int c = 0; c < cols; ++c) {
@@ -772,13 +938,15 @@ void render_synthetic_depth(Oracle& o, const Cam& cam, const Pose& T_L_C, float 
       const float pv = (float)(r * s) + 0.5f * (float)s * 1.0f;
       const V3 ray = ray_from_image_plane(cam, pu, pv);
       // Eigen normalized(): z = squaredNorm; if (z > 0) v / sqrt(z)
-      const float sq = sum3(ray.x * ray.x, ray.y * ray.y, ray.z * ray.z);
+      // squaredNorm: x*x + (y*y + z*z); contracted: fma(x, x, fma(y, y, z*z))
+      const float sq = nvcc_model() ? std::fmaf(ray.x, ray.x, std::fmaf(ray.y, ray.y, ray.z * ray.z))
+                                    : sum3(ray.x * ray.x, ray.y * ray.y, ray.z * ray.z);
       V3 dc = ray;
       if (sq > 0.0f) {
         const float n = std::sqrt(sq);
         dc = V3{ray.x / n, ray.y / n, ray.z / n};
       }
-      const V3 dl = rotate(T_L_C, dc);
+      const V3 dl = dev_rotate(T_L_C, dc);
       float t;
       int steps = 0;
       if (sphere_cast(o, origin, dl, trunc, &t, &steps))
@@ -833,7 +1001,25 @@ void integrate_features(Oracle& o, const uint16_t* img, int rows, int cols, cons
   std::vector<std::vector<uint16_t>*> fblk_ptrs(band.size());
   for (size_t i = 0; i < band.size(); ++i) fblk_ptrs[i] = &o.feat[band[i]];
   int64_t n_upd = 0;
-  const bool fused_half = g_fused_half;
+  const bool fused_half = fused_half_on();
+  if (g_hooks.feat) {
+    float Tm[16];
+    pose_to_row_major(T_C_L, Tm);
+    const float cm[4] = {cam.fu, cam.fv, cam.cu, cam.cv};
+    const size_t per = (size_t)512 * (C + 1);
+    std::vector<int> idx(band.size() * 3);
+    std::vector<uint16_t> vox(band.size() * per);
+    for (size_t i = 0; i < band.size(); ++i) {
+      idx[3 * i] = band[i].x;
+      idx[3 * i + 1] = band[i].y;
+      idx[3 * i + 2] = band[i].z;
+      std::memcpy(vox.data() + i * per, fblk_ptrs[i]->data(), per * 2);
+    }
+    if (g_hooks.feat(Tm, cm, cols, rows, img, mask, o.synth.data(), sub, o.block_size, o.p.max_integration_distance_m,
+                     trunc, o.p.max_weight, alpha, idx.data(), (int)band.size(), vox.data()))
+      std::fprintf(stderr, "orc: feature hook failed\n");
+    for (size_t i = 0; i < band.size(); ++i) std::memcpy(fblk_ptrs[i]->data(), vox.data() + i * per, per * 2);
+  } else
 #pragma omp parallel reduction(+ : n_upd)
   {
   std::vector<uint16_t> meas((size_t)C);
@@ -927,6 +1113,7 @@ inline uint8_t interp_color_channel(float x, float y, uint8_t c00, uint8_t c01, 
   return (uint8_t)std::round(v);
 }
 inline uint8_t blend_color_channel(uint8_t a, float wa, uint8_t b, float wb) {
+  if (nvcc_model()) return (uint8_t)std::round(std::fmaf(wa, (float)a, wb * (float)b));   // FMUL + FFMA
   return (uint8_t)std::round((float)a * wa + (float)b * wb);
 }
 
@@ -959,6 +1146,31 @@ void integrate_color(Oracle& o, const uint8_t* img, int rows, int cols, const ui
   const Pose T_C_L = inverse(T_L_C);
   const float alpha = o.p.appearance_measurement_weight;
   int64_t n_upd = 0;
+  if (g_hooks.color) {
+    float Tm[16];
+    pose_to_row_major(T_C_L, Tm);
+    const float cm[4] = {cam.fu, cam.fv, cam.cu, cam.cv};
+    std::vector<int> idx(band.size() * 3);
+    std::vector<uint8_t> rgb(band.size() * 1536);
+    std::vector<float> wgt(band.size() * 512);
+    for (size_t i = 0; i < band.size(); ++i) {
+      idx[3 * i] = band[i].x;
+      idx[3 * i + 1] = band[i].y;
+      idx[3 * i + 2] = band[i].z;
+      const ColorBlock& cb = o.color[band[i]];
+      std::memcpy(rgb.data() + i * 1536, cb.c, 1536);
+      std::memcpy(wgt.data() + i * 512, cb.w, 2048);
+    }
+    if (g_hooks.color(Tm, cm, cols, rows, img, mask, o.synth.data(), sub, o.block_size,
+                      o.p.max_integration_distance_m, trunc, o.p.max_weight, alpha, idx.data(), (int)band.size(),
+                      rgb.data(), wgt.data()))
+      std::fprintf(stderr, "orc: colour hook failed\n");
+    for (size_t i = 0; i < band.size(); ++i) {
+      ColorBlock& cb = o.color[band[i]];
+      std::memcpy(cb.c, rgb.data() + i * 1536, 1536);
+      std::memcpy(cb.w, wgt.data() + i * 512, 2048);
+    }
+  } else
   for (const I3& b : band) {
     ColorBlock& blk = o.color[b];
     for (int x = 0; x < 8; ++x)
@@ -1071,7 +1283,7 @@ inline V3 interp_vertex(const V3& a, const V3& b, float s1, float s2) {  // marc
   const float diff = s1 - s2;
   if (std::fabs(diff) >= 1e-4f) {
     const float t = s1 / diff;
-    return V3{a.x + t * (b.x - a.x), a.y + t * (b.y - a.y), a.z + t * (b.z - a.z)};
+    return V3{dev_fma(t, b.x - a.x, a.x), dev_fma(t, b.y - a.y, a.y), dev_fma(t, b.z - a.z, a.z)};
   }
   return V3{0.5f * (a.x + b.x), 0.5f * (a.y + b.y), 0.5f * (a.z + b.z)};
 }
@@ -1116,9 +1328,9 @@ void mesh_block(Oracle& o, const I3& bi, MeshBlock* out) {
           }
           sdf[i] = blk->d[l];
           // block_position + voxel_size * (corner + 0.5 + 8*block_offset)   (mesh_integrator.cu:421-424)
-          pos[i].x = origin.x + vs * (((float)c[0] + 0.5f) + (float)(8 * off[0]));
-          pos[i].y = origin.y + vs * (((float)c[1] + 0.5f) + (float)(8 * off[1]));
-          pos[i].z = origin.z + vs * (((float)c[2] + 0.5f) + (float)(8 * off[2]));
+          pos[i].x = dev_fma(vs, ((float)c[0] + 0.5f) + (float)(8 * off[0]), origin.x);
+          pos[i].y = dev_fma(vs, ((float)c[1] + 0.5f) + (float)(8 * off[1]), origin.y);
+          pos[i].z = dev_fma(vs, ((float)c[2] + 0.5f) + (float)(8 * off[2]), origin.z);
         }
         if (skip) continue;
         int cfg = 0;
@@ -1170,7 +1382,11 @@ void paint_block(Oracle& o, const I3& bi, MeshBlock* mb) {
   const float vs = o.block_size / 8;
   for (size_t i = 0; i < mb->verts.size(); ++i) {
     const V3& v = mb->verts[i];
-    int ix = (int)((v.x - origin.x) / vs), iy = (int)((v.y - origin.y) / vs), iz = (int)((v.z - origin.z) / vs);
+    // p_L_V - block_size * float(idx): mul.f32 + sub.f32 in the PTX, one FFMA in the SASS
+    const float bs = o.block_size;
+    int ix = (int)((nvcc_model() ? std::fmaf(-bs, (float)bi.x, v.x) : v.x - origin.x) / vs);
+    int iy = (int)((nvcc_model() ? std::fmaf(-bs, (float)bi.y, v.y) : v.y - origin.y) / vs);
+    int iz = (int)((nvcc_model() ? std::fmaf(-bs, (float)bi.z, v.z) : v.z - origin.z) / vs);
     ix = std::max(std::min(ix, 7), 0);
     iy = std::max(std::min(iy, 7), 0);
     iz = std::max(std::min(iz, 7), 0);
@@ -1189,7 +1405,11 @@ void paint_block_color(Oracle& o, const I3& bi, MeshBlock* mb) {
   const float vs = o.block_size / 8;
   for (size_t i = 0; i < mb->verts.size(); ++i) {
     const V3& v = mb->verts[i];
-    int ix = (int)((v.x - origin.x) / vs), iy = (int)((v.y - origin.y) / vs), iz = (int)((v.z - origin.z) / vs);
+    // p_L_V - block_size * float(idx): mul.f32 + sub.f32 in the PTX, one FFMA in the SASS
+    const float bs = o.block_size;
+    int ix = (int)((nvcc_model() ? std::fmaf(-bs, (float)bi.x, v.x) : v.x - origin.x) / vs);
+    int iy = (int)((nvcc_model() ? std::fmaf(-bs, (float)bi.y, v.y) : v.y - origin.y) / vs);
+    int iz = (int)((nvcc_model() ? std::fmaf(-bs, (float)bi.z, v.z) : v.z - origin.z) / vs);
     ix = std::max(std::min(ix, 7), 0);
     iy = std::max(std::min(iy, 7), 0);
     iz = std::max(std::min(iz, 7), 0);
@@ -1317,7 +1537,17 @@ void* orc_create(float voxel_size, int C, const nvbx_params* p) {
   return o;
 }
 void orc_destroy(void* h) { delete (Oracle*)h; }
-void orc_set_fused_half(int v) { g_fused_half = v != 0; }
+void orc_set_fused_half(int v) { g_fused_half_override = v < 0 ? -1 : (v != 0); }
+void orc_set_fp_model(int m) { g_fp_model = m; }
+void orc_set_ref_hooks(orc_hook_raycast_t raycast, orc_hook_tsdf_t tsdf, orc_hook_trace_t trace, orc_hook_feat_t feat,
+                       orc_hook_color_t color) {
+  g_hooks.raycast = raycast;
+  g_hooks.tsdf = tsdf;
+  g_hooks.trace = trace;
+  g_hooks.feat = feat;
+  g_hooks.color = color;
+}
+int orc_get_fp_model(void) { return g_fp_model; }
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
@@ -1504,6 +1734,12 @@ void orc_set_tsdf_block(void* h, int x, int y, int z, const float* in) {
     b.w[l] = in[2 * l + 1];
   }
 }
+// feature block in the oracle's layout ([8][8][8][C+1] halves); allocates the block when absent (test helper)
+void orc_set_feature_block(void* h, int x, int y, int z, const uint16_t* in) {
+  Oracle& o = *(Oracle*)h;
+  std::vector<uint16_t>& blk = o.feat[I3{x, y, z}];
+  blk.assign(in, in + (size_t)512 * (o.C + 1));
+}
 void orc_mark_all_dirty(void* h) {
   Oracle& o = *(Oracle*)h;
   for (auto& kv : o.tsdf) {
@@ -1516,7 +1752,7 @@ void orc_query_tsdf(void* h, const float* xyz, int64_t n, float* out) {
   Oracle& o = *(Oracle*)h;
   for (int64_t i = 0; i < n; ++i) {
     I3 b, v;
-    block_and_voxel_from_position(o.block_size, V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, &b, &v);
+    dev_block_and_voxel_from_position(o.block_size, V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, &b, &v);
     auto it = o.tsdf.find(b);
     if (it == o.tsdf.end()) continue;
     const int l = vlin(v.x, v.y, v.z);
@@ -1528,7 +1764,7 @@ void orc_query_features(void* h, const float* xyz, int64_t n, uint16_t* out) {
   Oracle& o = *(Oracle*)h;
   for (int64_t i = 0; i < n; ++i) {
     I3 b, v;
-    block_and_voxel_from_position(o.block_size, V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, &b, &v);
+    dev_block_and_voxel_from_position(o.block_size, V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, &b, &v);
     auto it = o.feat.find(b);
     if (it == o.feat.end()) continue;
     const uint16_t* vox = it->second.data() + (size_t)vlin(v.x, v.y, v.z) * (o.C + 1);
@@ -1674,4 +1910,106 @@ int orc_project(float fx, float fy, float cx, float cy, int H, int W, const floa
 }
 uint64_t orc_weld_key(const float* v) { return weld_key(V3{v[0], v[1], v[2]}); }
 
+
+// ---- function-level entry points in the DEVICE model, mirrored one for one by the probes of
+// oracle/ref_snippets/ref_kernels.cu (ref_fn_*): tests/test_ref_vectors.py compares them bit for bit. ----
+void orc_fn_interp_half(int n, const float* xy, const uint16_t* f, uint16_t* out) {
+  for (int i = 0; i < n; ++i)
+    out[i] = interp_half(f2h(xy[2 * i]), f2h(xy[2 * i + 1]), f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+}
+void orc_fn_interp_float(int n, const float* xy, const float* f, float* out) {
+  for (int i = 0; i < n; ++i)
+    out[i] = interp_float(xy[2 * i], xy[2 * i + 1], f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+}
+// blendTwoArrays<FeatureArray> (projective_appearance_integrator.cu:286-305) on n arrays of C halves
+void orc_fn_blend(int n, int C, const uint16_t* a, const uint16_t* b, const float* w, uint16_t* out) {
+  for (int i = 0; i < n; ++i) {
+    float w1 = w[2 * i], w2 = w[2 * i + 1];
+    const float tot = w1 + w2;
+    w1 /= tot;
+    w2 /= tot;
+    const uint16_t h1 = f2h(w1), h2 = f2h(w2);
+    for (int c = 0; c < C; ++c) {
+      const size_t k = (size_t)i * C + c;
+      out[k] = fused_half_on() ? hfma(a[k], h1, hmul(b[k], h2)) : hadd(hmul(a[k], h1), hmul(b[k], h2));
+    }
+  }
+}
+void orc_fn_interp_vertex(int n, const float* v1, const float* v2, const float* sdf, float* out) {
+  for (int i = 0; i < n; ++i) {
+    const V3 r = interp_vertex(V3{v1[3 * i], v1[3 * i + 1], v1[3 * i + 2]}, V3{v2[3 * i], v2[3 * i + 1], v2[3 * i + 2]},
+                               sdf[2 * i], sdf[2 * i + 1]);
+    out[3 * i] = r.x;
+    out[3 * i + 1] = r.y;
+    out[3 * i + 2] = r.z;
+  }
+}
+void orc_fn_block_voxel(int n, float block_size, const float* p, int32_t* out) {
+  for (int i = 0; i < n; ++i) {
+    I3 b, v;
+    dev_block_and_voxel_from_position(block_size, V3{p[3 * i], p[3 * i + 1], p[3 * i + 2]}, &b, &v);
+    out[6 * i] = b.x;
+    out[6 * i + 1] = b.y;
+    out[6 * i + 2] = b.z;
+    out[6 * i + 3] = v.x;
+    out[6 * i + 4] = v.y;
+    out[6 * i + 5] = v.z;
+  }
+}
+// projectThreadVoxel: out = (u, v, depth, p_C.xyz), ok = its return value
+void orc_fn_project(int n, const float* T_C_L_rm, float fx, float fy, float cx, float cy, int W, int H, float block_size,
+                    float max_depth, const int32_t* bv, float* out, int32_t* ok) {
+  const Pose T = pose_from_row_major(T_C_L_rm);
+  Cam cam{fx, fy, cx, cy, W, H};
+  for (int i = 0; i < n; ++i) {
+    const V3 pl = dev_voxel_center(block_size, I3{bv[6 * i], bv[6 * i + 1], bv[6 * i + 2]},
+                                   I3{bv[6 * i + 3], bv[6 * i + 4], bv[6 * i + 5]});
+    const V3 pc = dev_xform(T, pl);
+    float u = 0.0f, v = 0.0f;
+    bool good = dev_project(cam, pc, &u, &v);
+    if (!good && pc.z >= 1e-6f) {  // the reference leaves the out-of-image coordinates in u_px
+      u = nvcc_model() ? std::fmaf(pc.x / pc.z, cam.fu, cam.cu) : (pc.x / pc.z) * cam.fu + cam.cu;
+      v = nvcc_model() ? std::fmaf(pc.y / pc.z, cam.fv, cam.cv) : (pc.y / pc.z) * cam.fv + cam.cv;
+    }
+    float depth = 0.0f;
+    if (good) {
+      depth = pc.z;
+      if (max_depth > 0.0f && depth > max_depth) good = false;
+    }
+    out[6 * i] = u;
+    out[6 * i + 1] = v;
+    out[6 * i + 2] = depth;
+    out[6 * i + 3] = pc.x;
+    out[6 * i + 4] = pc.y;
+    out[6 * i + 5] = pc.z;
+    ok[i] = good ? 1 : 0;
+  }
+}
+// UpdateTsdfVoxelFunctor (projective_tsdf_integrator.cu:25-99) on explicit tuples
+void orc_fn_tsdf_functor(int n, float trunc, float max_weight, float invalid_decay, int mode, const float* in,
+                         const uint8_t* active, float* voxels, uint8_t* updated) {
+  for (int i = 0; i < n; ++i) {
+    const float meas = in[2 * i], vd = in[2 * i + 1];
+    float& d = voxels[2 * i];
+    float& w = voxels[2 * i + 1];
+    updated[i] = 0;
+    if (meas <= 0.0f) {
+      if (invalid_decay >= 0.0f) w *= invalid_decay;
+      continue;
+    }
+    const float sdf = meas - vd;
+    if (sdf < -trunc) continue;
+    if (!active[i] && sdf < trunc) continue;
+    const float w_m = weighting(mode, meas, vd, trunc);
+    float fused = (nvcc_model() ? std::fmaf(d, w, sdf * w_m) : (sdf * w_m + d * w)) / (w_m + w);
+    if (fused > 0.0f)
+      fused = std::fmin(trunc, fused);
+    else
+      fused = std::fmax(-trunc, fused);
+    const float w_new = std::fmin(w_m + w, max_weight);
+    d = fused;
+    w = w_new;
+    updated[i] = 1;
+  }
+}
 }  // extern "C"

@@ -336,25 +336,28 @@ def test_static_camera_stops_allocating():
 
 
 def test_fused_half_variant_spread_is_bounded():
-    """nvcc MAY contract the reference's `mul.f16`/`add.f16` pairs into fma (no .rn in cuda_fp16.hpp), which
-    cannot be known without building it.  This measures how far the contracted sequence is from the
-    uncontracted one the oracle / product implement, on N(0,1) features: a few half-epsilons (2^-10) in
-    absolute terms; ulp distance is unbounded where cancellation leaves a near-zero result, so the
-    north_star's "1 fp16 ulp" bar is only meaningful between implementations of the SAME sequence
-    (product vs oracle: bit-exact, tests/test_gpu_parity.py)."""
+    """nvcc contracts the reference's `mul.f16` / `add.f16` pairs into HFMA2 (cuda_fp16.hpp emits them without
+    .rn; SASS in profiles/r02_ref_contraction.md), so the fused sequence is the reference's and the oracle's /
+    product's default.  This measures how far the UNCONTRACTED sequence (round 1's model) is from it on N(0,1)
+    features: a few half-epsilons (2^-10) in absolute terms, but only ~60 % of the halves within 1 ulp -- ulp
+    distance is unbounded where cancellation leaves a near-zero result.  So "within 1 fp16 ulp of nvblox" can
+    only be met by implementing the reference's own contraction, which tests/test_ref_vectors.py pins bit for
+    bit against reference-compiled vectors."""
     from tests.parity_utils import ordered_half
     res = []
-    for fused in (0, 1):
-        L.orc_set_fused_half(fused)
-        mp, p = make_params(workspace=S.WS_CUBE_STACKING, alpha=0.3)
-        m = O.OracleMapper(0.02, 32, p)
-        K = S.intrinsics(64, 64)
-        for i in range(2):
-            T = S.orbit_pose(i)
-            m.add_depth_frame(S.render_depth(K, 64, 64, T, **S.S_TABLE), T, K)
-            m.add_feature_frame(S.feature_frame(64, 64, 32, 10 + i), T, K)
-        res.append(m.all_blocks(1)[1])
-    L.orc_set_fused_half(0)
+    try:
+        for fused in (0, 1):
+            L.orc_set_fused_half(fused)
+            mp, p = make_params(workspace=S.WS_CUBE_STACKING, alpha=0.3)
+            m = O.OracleMapper(0.02, 32, p)
+            K = S.intrinsics(64, 64)
+            for i in range(2):
+                T = S.orbit_pose(i)
+                m.add_depth_frame(S.render_depth(K, 64, 64, T, **S.S_TABLE), T, K)
+                m.add_feature_frame(S.feature_frame(64, 64, 32, 10 + i), T, K)
+            res.append(m.all_blocks(1)[1])
+    finally:
+        L.orc_set_fused_half(-1)    # back to "follow the floating-point model"
     a, b = res[0].astype(np.float32), res[1].astype(np.float32)
     assert np.array_equal(res[0][..., -1].view(np.uint16), res[1][..., -1].view(np.uint16))    # weights identical
     assert np.isfinite(a).all() and np.isfinite(b).all()
@@ -362,6 +365,7 @@ def test_fused_half_variant_spread_is_bounded():
     d = np.abs(ordered_half(res[0].view(np.uint16)).astype(np.int64) -
                ordered_half(res[1].view(np.uint16)).astype(np.int64))
     assert (d <= 1).mean() > 0.6
+    assert (d > 1).any()
 
 
 # ---- colour path: test_color_integrator.cpp, test_mapper_masking.py:100-160 --------------------
