@@ -324,6 +324,12 @@ float nvbx_voxel_size(const nvbx_mapper* m, int map_id);
 /* get_all_block_indices: writes up to `capacity` int32 triples to HOST memory `out_xyz`, returns the count. */
 int64_t nvbx_get_block_indices(nvbx_mapper* m, int map_id, int layer, int32_t* out_xyz, int64_t capacity,
                                void* stream);
+/* get_all_blocks (PyVoxelBlockLayer::getAllBlocks, py_layer.cpp:177-198): index triples AND device payload pointers
+ * of every block of `layer` in ONE kernel launch and one stream synchronisation; HOST outputs (either may be
+ * null), up to `capacity` entries; returns the block count.  Pointer layout and *voxel_stride_elems as for
+ * nvbx_get_block_ptr below.  Pointers stay valid until the map is next mutated. */
+int64_t nvbx_get_all_blocks(nvbx_mapper* m, int map_id, int layer, int32_t* out_xyz, void** out_ptrs, int64_t capacity,
+                            int64_t* voxel_stride_elems, void* stream);
 /* get_block_at_index: device pointer of the block's voxel array and its voxel stride in ELEMENTS.
  * TSDF: float [8][8][8][2], stride 2.  Feature: fp16 [8][8][8][stride], stride = C + 8 (the first C are
  * the feature, element C is the weight, the rest is padding that keeps rows 16-byte aligned), to be

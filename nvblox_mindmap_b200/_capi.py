@@ -21,7 +21,7 @@ API_SYMBOLS = [
     'nvbx_upsample_features', 'nvbx_integrate_frame_host_lowres', 'nvbx_decay', 'nvbx_clear', 'nvbx_mark_all_dirty',
     'nvbx_update_feature_mesh', 'nvbx_get_feature_mesh', 'nvbx_update_color_mesh', 'nvbx_get_color_mesh',
     'nvbx_export_points', 'nvbx_gather_points', 'nvbx_num_blocks', 'nvbx_num_allocated_blocks',
-    'nvbx_num_allocated_bytes', 'nvbx_voxel_size', 'nvbx_get_block_indices', 'nvbx_get_block_ptr',
+    'nvbx_num_allocated_bytes', 'nvbx_voxel_size', 'nvbx_get_block_indices', 'nvbx_get_all_blocks', 'nvbx_get_block_ptr',
     'nvbx_allocate_block', 'nvbx_query_tsdf', 'nvbx_query_features', 'nvbx_get_counters',
     'nvbx_reset_counters', 'nvbx_integrate_frames_batch', 'nvbx_set_gather_tuning', 'nvbx_set_kernel_timing', 'nvbx_get_kernel_timing', 'nvbx_kernel_timing_report', 'nvbx_kernel_launch_count', 'nvbx_debug_last_block_list', 'nvbx_debug_profile_stamps',
     'nvbx_debug_last_synthetic_depth', 'nvbx_version',
@@ -88,6 +88,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         L.nvbx_voxel_size.restype = C.c_float
         L.nvbx_get_block_indices.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64, vp]
         L.nvbx_get_block_indices.restype = C.c_int64
+        L.nvbx_get_all_blocks.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int64, i64p, vp]
+        L.nvbx_get_all_blocks.restype = C.c_int64
         L.nvbx_get_block_ptr.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp), i64p, vp]
         L.nvbx_allocate_block.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.nvbx_query_tsdf.argtypes = [vp, C.c_int, vp, C.c_int64, vp, vp]

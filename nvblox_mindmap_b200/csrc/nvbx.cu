@@ -252,6 +252,7 @@ struct Map {
   int* d_tmp_int = nullptr;
   unsigned long long* d_tmp_ptr = nullptr;
   DevBuf<int3> idx_out;
+  DevBuf<unsigned long long> ptr_out;
 };
 
 }  // namespace
@@ -669,6 +670,7 @@ void destroy_map(Map& mp) {
   mp.st_low.release();
   mp.st_low_in.release();
   mp.idx_out.release();
+  mp.ptr_out.release();
 }
 
 Cam make_cam(float fx, float fy, float cx, float cy, int H, int W) {
@@ -1848,6 +1850,33 @@ int64_t nvbx_get_block_indices(nvbx_mapper* m, int map_id, int layer, int32_t* o
   if (out_xyz && capacity > 0) {
     const int64_t c = std::min(n, capacity);
     CUDA_TRY(cudaMemcpyAsync(out_xyz, mp.idx_out.p, (size_t)c * sizeof(int3), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+  }
+  return n;
+}
+
+int64_t nvbx_get_all_blocks(nvbx_mapper* m, int map_id, int layer, int32_t* out_xyz, void** out_ptrs, int64_t capacity,
+                            int64_t* voxel_stride_elems, void* stream_v) {
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  Map& mp = *m->maps[map_id];
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  if (voxel_stride_elems)
+    *voxel_stride_elems = layer == NVBX_LAYER_TSDF ? 2 : (layer == NVBX_LAYER_COLOR ? 8 : mp.dev.row);
+  if (layer == NVBX_LAYER_COLOR && !mp.color_enabled) return 0;
+  if (layer == NVBX_LAYER_TSDF && out_ptrs) ++mp.tsdf_version;  // the caller may write through the returned views
+  if ((rc = mp.idx_out.ensure((size_t)mp.slot_capacity, stream))) return rc;
+  if ((rc = mp.ptr_out.ensure((size_t)mp.slot_capacity, stream))) return rc;
+  CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->list_count, 0, sizeof(int), stream));
+  LAUNCH(k_collect_blocks, persistent_grid(m, 4), 256, 0, stream, mp.dev, layer, mp.idx_out.p, mp.ptr_out.p,
+         mp.slot_capacity);
+  if ((rc = read_ctrl(mp, stream))) return rc;
+  const int64_t n = mp.h_ctrl->list_count;
+  if (capacity > 0 && (out_xyz || out_ptrs)) {
+    const int64_t c = std::min(n, capacity);
+    if (out_xyz) CUDA_TRY(cudaMemcpyAsync(out_xyz, mp.idx_out.p, (size_t)c * sizeof(int3), cudaMemcpyDeviceToHost, stream));
+    if (out_ptrs)
+      CUDA_TRY(cudaMemcpyAsync(out_ptrs, mp.ptr_out.p, (size_t)c * sizeof(void*), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
   }
   return n;

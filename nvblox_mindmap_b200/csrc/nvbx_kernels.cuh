@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) k_raycast_mark(RaycastFrame f, unsigned* 
     p_C.x = len * ray.x;
     p_C.y = len * ray.y;
     p_C.z = len * ray.z;
-    const V3 p_L = xform(f.T_L_C, p_C);
+    const V3 p_L = dev_xform(f.T_L_C, p_C);
     // ray end in block units; its floor is also the block index of the end point (view_calculator.cu:231-236)
     const float e[3] = {(p_L.x / f.block_size) / 1.0f, (p_L.y / f.block_size) / 1.0f, (p_L.z / f.block_size) / 1.0f};
     const int end[3] = {(int)floorf(e[0]), (int)floorf(e[1]), (int)floorf(e[2])};
@@ -311,9 +311,9 @@ __device__ __forceinline__ bool project_voxel(const Cam& cam, const Pose& T_C_L,
   bi.x = b.x;
   bi.y = b.y;
   bi.z = b.z;
-  const V3 pl = voxel_center(block_size, bi, vx, vy, vz);
-  const V3 pc = xform(T_C_L, pl);
-  if (!project(cam, pc, u, v)) return false;
+  const V3 pl = dev_voxel_center(block_size, bi, vx, vy, vz);
+  const V3 pc = dev_xform(T_C_L, pl);
+  if (!dev_project(cam, pc, u, v)) return false;
   *vd = pc.z;
   if (max_depth > 0.0f && *vd > max_depth) return false;
   return true;
@@ -349,7 +349,7 @@ __device__ __forceinline__ unsigned tsdf_update_voxel(const MapDev& m, const Dep
     if (!active && sdf < f.trunc) break;
     const float2 cur = is_new ? make_float2(0.0f, 0.0f) : *vox;
     const float w_m = weighting(f.weighting_mode, meas, vd, f.trunc);
-    float fused = (sdf * w_m + cur.x * cur.y) / (w_m + cur.y);
+    float fused = fmaf(cur.x, cur.y, sdf * w_m) / (w_m + cur.y);   // FMUL + FFMA in the reference
     if (fused > 0.0f)
       fused = fminf(f.trunc, fused);
     else
@@ -674,7 +674,7 @@ __device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TracePara
   const float pu = (float)(c * tp.sub) + 0.5f * (float)tp.sub * 1.0f;
   const float pv = (float)(r * tp.sub) + 0.5f * (float)tp.sub * 1.0f;
   const V3 ray = ray_from_image_plane(tp.cam, pu, pv);
-  const float sq = sum3(ray.x * ray.x, ray.y * ray.y, ray.z * ray.z);
+  const float sq = fmaf(ray.x, ray.x, fmaf(ray.y, ray.y, ray.z * ray.z));
   V3 dc = ray;
   if (sq > 0.0f) {
     const float nrm = sqrtf(sq);
@@ -682,7 +682,7 @@ __device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TracePara
     dc.y = ray.y / nrm;
     dc.z = ray.z / nrm;
   }
-  const V3 dl = rotate(tp.T_L_C, dc);
+  const V3 dl = dev_rotate(tp.T_L_C, dc);
   const float ox = tp.T_L_C.t[0], oy = tp.T_L_C.t[1], oz = tp.T_L_C.t[2];
   // every block lives inside the workspace grid: leaving it for good ends the march
   const bool closed_world = (m.ws_sx > 0) && (m.ctrl->n_hash == 0);
@@ -698,16 +698,16 @@ __device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TracePara
   };
   auto locate = [&](float tt) -> Loc {
     V3 p;
-    p.x = ox + tt * dl.x;
-    p.y = oy + tt * dl.y;
-    p.z = oz + tt * dl.z;
+    p.x = fmaf(tt, dl.x, ox);
+    p.y = fmaf(tt, dl.y, oy);
+    p.z = fmaf(tt, dl.z, oz);
     I3 b, v;
     b.x = floor_div_exact(p.x, bs, bs_inv);
     b.y = floor_div_exact(p.y, bs, bs_inv);
     b.z = floor_div_exact(p.z, bs, bs_inv);
-    v.x = min((int)((p.x - bs * (float)b.x) * m.voxel_size_inv), 7);
-    v.y = min((int)((p.y - bs * (float)b.y) * m.voxel_size_inv), 7);
-    v.z = min((int)((p.z - bs * (float)b.z) * m.voxel_size_inv), 7);
+    v.x = min((int)(fmaf(-(float)b.x, bs, p.x) * m.voxel_size_inv), 7);
+    v.y = min((int)(fmaf(-(float)b.y, bs, p.y) * m.voxel_size_inv), 7);
+    v.z = min((int)(fmaf(-(float)b.z, bs, p.z) * m.voxel_size_inv), 7);
     // Block lookup on every sample (no per-thread block cache: with the table in shared memory the lookup is
     // cheaper than the divergence a cache introduces).  A slot without a TSDF layer has an all-zero TSDF
     // payload (k_allocate_one), i.e. reads as unobserved, so the layer bits need not be consulted here.
@@ -929,11 +929,11 @@ struct FeatFrame {
 
 __device__ __forceinline__ __half2 interp_h2(__half2 x, __half2 y, __half2 xy, __half2 f00, __half2 f01, __half2 f10,
                                              __half2 f11) {
+  // the reference's SASS: HFMA2(x, dx, f00); HFMA2(y, f01 - f00, .); HFMA2(x*y, f11 - f01 - dx, .)
   const __half2 dx = __hsub2(f10, f00);
-  const __half2 t2 = __hadd2_rn(f00, __hmul2_rn(x, dx));
-  const __half2 t5 = __hadd2_rn(t2, __hmul2_rn(y, __hsub2(f01, f00)));
-  const __half2 t9 = __hmul2_rn(xy, __hsub2(__hsub2(f11, f01), dx));
-  return __hadd2_rn(t5, t9);
+  const __half2 t2 = __hfma2(x, dx, f00);
+  const __half2 t5 = __hfma2(y, __hsub2(f01, f00), t2);
+  return __hfma2(xy, __hsub2(__hsub2(f11, f01), dx), t5);
 }
 __device__ __forceinline__ uint4 interp_vec(__half2 x, __half2 y, __half2 xy, uint4 a00, uint4 a01, uint4 a10,
                                             uint4 a11) {
@@ -953,7 +953,7 @@ __device__ __forceinline__ uint4 blend_vec(uint4 oldv, uint4 meas, __half2 w1, _
   const __half2* pm = reinterpret_cast<const __half2*>(&meas);
   __half2* pr = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pr[i] = __hadd2_rn(__hmul2_rn(po[i], w1), __hmul2_rn(pm[i], w2));
+  for (int i = 0; i < 4; ++i) pr[i] = __hfma2(po[i], w1, __hmul2_rn(pm[i], w2));   // HMUL2 + HFMA2
   return o;
 }
 __device__ __forceinline__ uint4 ldg_nc(const uint4* p) { return __ldg(p); }
@@ -1020,7 +1020,7 @@ __global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* _
       const int lx = (int)floorf(uc), ly = (int)floorf(vc);
       if (lx < 0 || ly < 0 || (lx + 1) > (f.scols - 1) || (ly + 1) > (f.srows - 1)) break;
       const float* sp = f.synth + (size_t)ly * f.scols + lx;
-      const float surface = interp_float(uc - (float)lx, vc - (float)ly, sp[0], sp[f.scols], sp[1], sp[f.scols + 1]);
+      const float surface = dev_interp_float(uc - (float)lx, vc - (float)ly, sp[0], sp[f.scols], sp[1], sp[f.scols + 1]);
       if (fabsf(surface - vd) > f.trunc) break;
       const float fu = u - 0.5f, fv = v - 0.5f;
       const int px = (int)floorf(fu), py = (int)floorf(fv);
@@ -1495,7 +1495,7 @@ __global__ void __launch_bounds__(512) k_color_update(MapDev m, const int* __res
       const int lx = (int)floorf(uc), ly = (int)floorf(vc);
       if (lx < 0 || ly < 0 || (lx + 1) > (f.scols - 1) || (ly + 1) > (f.srows - 1)) break;
       const float* sp = f.synth + (size_t)ly * f.scols + lx;
-      const float surface = interp_float(uc - (float)lx, vc - (float)ly, sp[0], sp[f.scols], sp[1], sp[f.scols + 1]);
+      const float surface = dev_interp_float(uc - (float)lx, vc - (float)ly, sp[0], sp[f.scols], sp[1], sp[f.scols + 1]);
       if (fabsf(surface - vd) > f.trunc) break;
       const float fu = u - 0.5f, fv = v - 0.5f;
       const int px = (int)floorf(fu), py = (int)floorf(fv);
@@ -1512,10 +1512,10 @@ __global__ void __launch_bounds__(512) k_color_update(MapDev m, const int* __res
       for (int c = 0; c < 3; ++c) {
         const float m00 = (float)__ldg(p00 + c), m10 = (float)__ldg(p00 + 3 + c);
         const float m01 = (float)__ldg(p01 + c), m11 = (float)__ldg(p01 + 3 + c);
-        unsigned ch = (unsigned)(uint8_t)roundf(interp_float(ox, oy, m00, m01, m10, m11));
+        unsigned ch = (unsigned)(uint8_t)roundf(dev_interp_float(ox, oy, m00, m01, m10, m11));
         if (!first) {
           const float old = (float)((cur.x >> (8 * c)) & 0xffu);
-          ch = (unsigned)(uint8_t)roundf(old * f.w1 + (float)ch * f.w2);
+          ch = (unsigned)(uint8_t)roundf(fmaf(f.w1, old, f.w2 * (float)ch));   // FMUL + FFMA in the reference
         }
         rgb |= ch << (8 * c);
       }
@@ -1670,6 +1670,30 @@ __global__ void __launch_bounds__(256) k_collect_block_indices(MapDev m, uint8_t
   }
 }
 
+// getAllBlocks (py_layer.cpp:177-198) in one pass: block index AND payload pointer of every block of a layer.
+__global__ void __launch_bounds__(256) k_collect_blocks(MapDev m, int layer, int3* out_idx, unsigned long long* out_ptr,
+                                                        int capacity) {
+  pdl_prologue();
+  const int n = m.ctrl->slot_high;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    unsigned long long p = 0ull;
+    if (layer == 0) {
+      if (m.blk_layers[s] & kLayerTsdfBit) p = (unsigned long long)tsdf_block(m, s);
+    } else if (layer == 2) {
+      if (m.blk_layers[s] & kLayerColorBit) p = (unsigned long long)color_block(m, s);
+    } else {
+      if ((m.blk_layers[s] & kLayerFeatBit) && m.blk_feat[s] >= 0) p = (unsigned long long)feat_block(m, m.blk_feat[s]);
+    }
+    if (p) {
+      const int pos = atomicAdd(&m.ctrl->list_count, 1);
+      if (pos < capacity) {
+        out_idx[pos] = m.blk_index[s];
+        out_ptr[pos] = p;
+      }
+    }
+  }
+}
+
 // single-thread helpers for allocate_block_at_index / get_block_at_index
 __global__ void k_allocate_one(MapDev m, int x, int y, int z, int layer, int* newfeat_slot_out) {
   pdl_prologue();
@@ -1735,7 +1759,7 @@ __global__ void __launch_bounds__(128) k_query_tsdf(MapDev m, const float* __res
   p.y = xyz[3 * i + 1];
   p.z = xyz[3 * i + 2];
   I3 b, v;
-  block_and_voxel_from_position(m.block_size, m.voxel_size_inv, p, &b, &v);
+  dev_block_and_voxel_from_position(m.block_size, m.voxel_size_inv, p, &b, &v);
   const int slot = find_slot(m, b.x, b.y, b.z);
   if (slot < 0 || !(m.blk_layers[slot] & kLayerTsdfBit)) return;
   out[i] = tsdf_block(m, slot)[(v.x * 8 + v.y) * 8 + v.z];
@@ -1752,7 +1776,7 @@ __global__ void __launch_bounds__(128) k_query_features(MapDev m, const float* _
   p.y = xyz[3 * q + 1];
   p.z = xyz[3 * q + 2];
   I3 b, v;
-  block_and_voxel_from_position(m.block_size, m.voxel_size_inv, p, &b, &v);
+  dev_block_and_voxel_from_position(m.block_size, m.voxel_size_inv, p, &b, &v);
   const int slot = find_slot(m, b.x, b.y, b.z);
   if (slot < 0 || m.blk_feat[slot] < 0) return;
   const __half* row = feat_block(m, m.blk_feat[slot]) + (size_t)((v.x * 8 + v.y) * 8 + v.z) * m.row;

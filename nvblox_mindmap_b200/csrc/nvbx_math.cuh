@@ -155,6 +155,56 @@ NVBX_HD float weighting(int mode, float measured, float voxel_depth, float trunc
   return 0.0f;
 }
 
+// ---- DEVICE-code forms (nvcc-contracted, see the header) ---------------------------------------------------
+// R.row(i) . v: Eigen's a0 + (a1 + a2) becomes fma(v.x, R0, fma(v.y, R1, v.z * R2))
+NVBX_HD float dev_dot3(const float* r, const V3& v) { return fmaf(v.x, r[0], fmaf(v.y, r[1], v.z * r[2])); }
+NVBX_HD V3 dev_rotate(const Pose& T, const V3& v) {
+  V3 o;
+  o.x = dev_dot3(T.R[0], v);
+  o.y = dev_dot3(T.R[1], v);
+  o.z = dev_dot3(T.R[2], v);
+  return o;
+}
+// Transform * Vector3f: the translation is added last, unfused
+NVBX_HD V3 dev_xform(const Pose& T, const V3& v) {
+  V3 o;
+  o.x = T.t[0] + dev_dot3(T.R[0], v);
+  o.y = T.t[1] + dev_dot3(T.R[1], v);
+  o.z = T.t[2] + dev_dot3(T.R[2], v);
+  return o;
+}
+// getCenterPositionFromBlockIndexAndVoxelIndex inside projectThreadVoxel: fma(bs, 1/16, fma(bs, b, (bs/8) * v))
+NVBX_HD V3 dev_voxel_center(float block_size, const I3& b, int vx, int vy, int vz) {
+  const float voxel_size = block_size * (1.0f / 8.0f);
+  V3 p;
+  p.x = fmaf(block_size, 0.5f / 8.0f, fmaf(block_size, (float)b.x, voxel_size * (float)vx));
+  p.y = fmaf(block_size, 0.5f / 8.0f, fmaf(block_size, (float)b.y, voxel_size * (float)vy));
+  p.z = fmaf(block_size, 0.5f / 8.0f, fmaf(block_size, (float)b.z, voxel_size * (float)vz));
+  return p;
+}
+// Camera::project inside a kernel: one FFMA per axis for the intrinsics
+NVBX_HD bool dev_project(const Cam& c, const V3& p, float* u, float* v) {
+  if (!(p.z >= 1e-6f)) return false;
+  const float un = fmaf(p.x / p.z, c.fu, c.cu);
+  const float vn = fmaf(p.y / p.z, c.fv, c.cv);
+  if (un > (float)c.width || vn > (float)c.height || un < 0 || vn < 0) return false;
+  *u = un;
+  *v = vn;
+  return true;
+}
+// interpolatePixels<float> inside the appearance kernel: three FFMAs
+NVBX_HD float dev_interp_float(float x, float y, float f00, float f01, float f10, float f11) {
+  const float dx = f10 - f00;
+  return fmaf(x * y, (f11 - f01) - dx, fmaf(y, f01 - f00, fmaf(x, dx, f00)));
+}
+// getBlockAndVoxelIndexFromPositionInLayer inside a kernel: p - bs*b is one FFMA
+NVBX_HD void dev_block_and_voxel_from_position(float block_size, float voxel_size_inv, const V3& p, I3* b, I3* v) {
+  *b = block_index_from_position(block_size, p);
+  v->x = min((int)(fmaf(-(float)b->x, block_size, p.x) * voxel_size_inv), 7);
+  v->y = min((int)(fmaf(-(float)b->y, block_size, p.y) * voxel_size_inv), 7);
+  v->z = min((int)(fmaf(-(float)b->z, block_size, p.z) * voxel_size_inv), 7);
+}
+
 // ---- AABB helpers (host): camera.cpp:51-103,153-166, workspace_bounds.cpp:20-61 ----------------------
 struct Aabb {
   float mn[3], mx[3];

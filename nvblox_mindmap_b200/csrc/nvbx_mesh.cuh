@@ -99,9 +99,9 @@ __device__ __forceinline__ void interp_vertex(const float* a, const float* b, fl
   const float diff = s1 - s2;
   if (fabsf(diff) >= 1e-4f) {
     const float t = s1 / diff;
-    o[0] = a[0] + t * (b[0] - a[0]);
-    o[1] = a[1] + t * (b[1] - a[1]);
-    o[2] = a[2] + t * (b[2] - a[2]);
+    o[0] = fmaf(t, b[0] - a[0], a[0]);   // vertex1 + t * (vertex2 - vertex1): one FFMA per axis in the reference
+    o[1] = fmaf(t, b[1] - a[1], a[1]);
+    o[2] = fmaf(t, b[2] - a[2], a[2]);
   } else {
     o[0] = 0.5f * (a[0] + b[0]);
     o[1] = 0.5f * (a[1] + b[1]);
@@ -112,7 +112,7 @@ __device__ __forceinline__ void interp_vertex(const float* a, const float* b, fl
 // Closest-voxel feature of a vertex (updateAppearanceBlockByClosestVoxel, mesh_integrator_appearance.cu:
 // 97-146): one warp copies the C-half row with 128-bit accesses; zeros when the block has no features
 // (updateAppearanceBlocksConstant :148-159).
-__device__ __forceinline__ void warp_paint_vertex(const MapDev& m, const __half* fblk, const float* origin, float vs,
+__device__ __forceinline__ void warp_paint_vertex(const MapDev& m, const __half* fblk, const int3 b, float vs,
                                                   float x, float y, float z, __half* dst) {
   const int nvec = m.C >> 3;
   uint4* d = reinterpret_cast<uint4*>(dst);
@@ -121,7 +121,10 @@ __device__ __forceinline__ void warp_paint_vertex(const MapDev& m, const __half*
     for (int c = lane; c < nvec; c += 32) d[c] = make_uint4(0, 0, 0, 0);
     return;
   }
-  int ix = (int)((x - origin[0]) / vs), iy = (int)((y - origin[1]) / vs), iz = (int)((z - origin[2]) / vs);
+  // p_L_V - block_size * float(block index): mul.f32 + sub.f32 in the reference's PTX, one FFMA in its SASS
+  const float bs = m.block_size;
+  int ix = (int)(fmaf(-bs, (float)b.x, x) / vs), iy = (int)(fmaf(-bs, (float)b.y, y) / vs),
+      iz = (int)(fmaf(-bs, (float)b.z, z) / vs);
   ix = max(min(ix, 7), 0);
   iy = max(min(iy, 7), 0);
   iz = max(min(iz, 7), 0);
@@ -213,12 +216,12 @@ __device__ void mesh_one_block(const MapDev& m, const MeshParams& mp, MeshSmem& 
         const int bx = vx + kMcCornerOffsets[cb][0], by = vy + kMcCornerOffsets[cb][1],
                   bz = vz + kMcCornerOffsets[cb][2];
         // block_position + voxel_size * ((corner&7) + 0.5 + 8*block_offset)   mesh_integrator.cu:421-424
-        pa[0] = origin[0] + vs * (((float)(ax & 7) + 0.5f) + (float)(8 * (ax >> 3)));
-        pa[1] = origin[1] + vs * (((float)(ay & 7) + 0.5f) + (float)(8 * (ay >> 3)));
-        pa[2] = origin[2] + vs * (((float)(az & 7) + 0.5f) + (float)(8 * (az >> 3)));
-        pb[0] = origin[0] + vs * (((float)(bx & 7) + 0.5f) + (float)(8 * (bx >> 3)));
-        pb[1] = origin[1] + vs * (((float)(by & 7) + 0.5f) + (float)(8 * (by >> 3)));
-        pb[2] = origin[2] + vs * (((float)(bz & 7) + 0.5f) + (float)(8 * (bz >> 3)));
+        pa[0] = fmaf(vs, ((float)(ax & 7) + 0.5f) + (float)(8 * (ax >> 3)), origin[0]);
+        pa[1] = fmaf(vs, ((float)(ay & 7) + 0.5f) + (float)(8 * (ay >> 3)), origin[1]);
+        pa[2] = fmaf(vs, ((float)(az & 7) + 0.5f) + (float)(8 * (az >> 3)), origin[2]);
+        pb[0] = fmaf(vs, ((float)(bx & 7) + 0.5f) + (float)(8 * (bx >> 3)), origin[0]);
+        pb[1] = fmaf(vs, ((float)(by & 7) + 0.5f) + (float)(8 * (by >> 3)), origin[1]);
+        pb[2] = fmaf(vs, ((float)(bz & 7) + 0.5f) + (float)(8 * (bz >> 3)), origin[2]);
       }
       // corner distances come back from the staged lattice (dynamic register indexing would spill)
       const float sa = s.tsdf[(vx + kMcCornerOffsets[ca][0]) * 81 + (vy + kMcCornerOffsets[ca][1]) * 9 +
@@ -327,8 +330,9 @@ __device__ void mesh_one_block(const MapDev& m, const MeshParams& mp, MeshSmem& 
       }
       unsigned rgb = kGrayVoxel;
       if (cblk) {
-        int ix = (int)((x - origin[0]) / vs_paint), iy = (int)((y - origin[1]) / vs_paint),
-            iz = (int)((z - origin[2]) / vs_paint);
+        const float bs = m.block_size;
+        int ix = (int)(fmaf(-bs, (float)b.x, x) / vs_paint), iy = (int)(fmaf(-bs, (float)b.y, y) / vs_paint),
+            iz = (int)(fmaf(-bs, (float)b.z, z) / vs_paint);
         ix = max(min(ix, 7), 0);
         iy = max(min(iy, 7), 0);
         iz = max(min(iz, 7), 0);
@@ -360,7 +364,7 @@ __device__ void mesh_one_block(const MapDev& m, const MeshParams& mp, MeshSmem& 
         y = o[1];
         z = o[2];
       }
-      warp_paint_vertex(m, fblk, origin, vs_paint, x, y, z, out.feats + (size_t)(voff + i) * m.C);
+      warp_paint_vertex(m, fblk, b, vs_paint, x, y, z, out.feats + (size_t)(voff + i) * m.C);
     }
   }
   *n_verts_out = n_unique;

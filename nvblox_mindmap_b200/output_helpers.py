@@ -62,11 +62,18 @@ def _sample_exported(mapper, mapper_id: int, vertices: torch.Tensor, features: t
     return out_v, out_f, valid
 
 
+def _owned(tensors, zero_copy: bool):
+    """The reference returns tensors that own their memory; ours come out of arenas the next export / mesh update
+    recycles.  Unless the caller opts into the zero-copy views, hand out copies."""
+    return tensors if zero_copy else tuple(t.clone() for t in tensors)
+
+
 def sample_to_n_vertices(vertices: torch.Tensor, features: torch.Tensor, desired_num_vertices: int, method,
-                         seed: Optional[int] = None, mapper=None, mapper_id: int = 0
+                         seed: Optional[int] = None, mapper=None, mapper_id: int = 0, zero_copy: bool = False
                          ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """vertex_sampling.py:29-81.  `vertices` / `features` are CUDA tensors; they are staged through the mapper's
-    export arena (identity filter) unless they already are its last export."""
+    export arena (identity filter).  Returns tensors that own their memory unless `zero_copy=True` (then they are
+    views of the mapper's arenas, valid until its next export / gather / mesh update)."""
     assert vertices.dim() == 2
     assert features.dim() == 2
     assert vertices.shape[0] == features.shape[0]
@@ -75,19 +82,21 @@ def sample_to_n_vertices(vertices: torch.Tensor, features: torch.Tensor, desired
     big = 3.0e38
     ev, ef = mapper.export_points(mapper_id, (-big,) * 3, (big,) * 3, 0, False, vertices=vertices,
                                   features=features.to(torch.float16))
-    return _sample_exported(mapper, mapper_id, ev, ef, desired_num_vertices, method, seed, None)
+    return _owned(_sample_exported(mapper, mapper_id, ev, ef, desired_num_vertices, method, seed, None), zero_copy)
 
 
 def get_vertices_and_features(mapper, mapper_id: int, nvblox_mapping_config, remove_zero_features: bool,
                               num_excess_features: int, sample_vertices: bool,
                               number_of_vertices_to_sample: Optional[int] = None, vertex_sampling_method=None,
-                              seed: Optional[int] = None, features_dtype: Optional[torch.dtype] = None
-                              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                              seed: Optional[int] = None, features_dtype: Optional[torch.dtype] = None,
+                              zero_copy: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """nvblox_output_helpers.py:22-89.  Returns (vertices, features, valid_mask) with the reference's shapes: a
     leading batch dimension of 1 on all three when sampling, on the mask only otherwise.
 
     `features_dtype=torch.float32` (ours) additionally folds the cast of isaaclab_nvblox_mapper.py:243-246 into
-    the gather pass."""
+    the gather pass.  The returned tensors OWN their memory, as the reference's do (the caller keeps them across
+    later steps); `zero_copy=True` (ours) returns views of the mapper's export arenas instead, valid until the
+    mapper's next export / gather / mesh update."""
     mapper.update_feature_mesh(mapper_id)
     mesh = mapper.get_feature_mesh(mapper_id)
     assert mesh.vertices().shape[0] == mesh.vertex_features().shape[0]
@@ -100,7 +109,7 @@ def get_vertices_and_features(mapper, mapper_id: int, nvblox_mapping_config, rem
             vertices, features = mapper.gather_points(mapper_id, None, vertices.shape[0], features.shape[1],
                                                       features_dtype, n_rows=vertices.shape[0])
         valid_mask = torch.ones(vertices.shape[0], dtype=torch.bool, device=vertices.device).unsqueeze(0)
-        return vertices, features, valid_mask
+        return _owned((vertices, features, valid_mask), zero_copy)
     vertices, features, valid_mask = _sample_exported(mapper, mapper_id, vertices, features,
                                                       number_of_vertices_to_sample, vertex_sampling_method, seed,
                                                       features_dtype)
@@ -108,4 +117,4 @@ def get_vertices_and_features(mapper, mapper_id: int, nvblox_mapping_config, rem
         vertices = vertices.unsqueeze(0)
         features = features.unsqueeze(0)
         valid_mask = valid_mask.unsqueeze(0)
-    return vertices, features, valid_mask
+    return _owned((vertices, features, valid_mask), zero_copy)

@@ -98,28 +98,34 @@ class MapBatch:
             d, f = depth_frames[k], feature_frames[k]
             K = intrinsics if isinstance(intrinsics, t.Tensor) else intrinsics[k]
             assert d.is_cuda and d.dtype == t.float32 and d.dim() == 2, 'Depth frame should be a 2-d float32 CUDA tensor.'
-            d = d if d.is_contiguous() else d.contiguous()
+            # The kernels read the frames on the per-map streams: a `.contiguous()` copy made here would be written on
+            # torch's current stream with nothing ordering the two, so non-contiguous inputs are rejected.
+            assert d.is_contiguous(), 'MapBatch: depth frames must be contiguous.'
             j.height, j.width = int(d.shape[0]), int(d.shape[1])
             j.depth = d.data_ptr()
             dm = None if depth_masks is None else depth_masks[k]
+            assert dm is None or dm.is_contiguous(), 'MapBatch: mask frames must be contiguous.'
             j.depth_mask = None if dm is None else self.mappers[k]._mask_ptr(dm, d)
             if f is not None:
                 assert f.is_cuda and f.dtype == t.float16 and f.dim() == 3 and f.shape[:2] == d.shape, \
                     'Feature frame should be a [H, W, C] float16 CUDA tensor of the depth frame\'s size.'
-                f = f if f.is_contiguous() else f.contiguous()
+                assert f.is_contiguous(), 'MapBatch: feature frames must be contiguous.'
                 j.channels = int(f.shape[2])
                 j.features = f.data_ptr()
                 fm = None if feature_masks is None else feature_masks[k]
+                assert fm is None or fm.is_contiguous(), 'MapBatch: mask frames must be contiguous.'
                 j.feature_mask = None if fm is None else self.mappers[k]._mask_ptr(fm, f)
             else:
                 j.channels, j.features, j.feature_mask = 0, None, None
             p = poses[k]
             assert (not p.is_cuda) and p.dtype == t.float32 and tuple(p.shape) == (4, 4), 'T_W_C should be a 4x4 CPU tensor.'
-            self._C.memmove(j.T_L_C, (p if p.is_contiguous() else p.contiguous()).data_ptr(), 64)
+            pc = p if p.is_contiguous() else p.contiguous()      # bound to a name: alive while its bytes are read
+            self._C.memmove(j.T_L_C, pc.data_ptr(), 64)
             assert (not K.is_cuda) and K.dtype == t.float32 and tuple(K.shape) == (3, 3), 'K should be a 3x3 CPU tensor.'
-            k9 = _F9.from_address((K if K.is_contiguous() else K.contiguous()).data_ptr())
-            j.fx, j.fy, j.cx, j.cy = k9[0], k9[4], k9[2], k9[5]
-            keep.append((d, f))
+            Kc = K if K.is_contiguous() else K.contiguous()
+            k9 = _F9.from_address(Kc.data_ptr())
+            j.fx, j.fy, j.cx, j.cy = float(k9[0]), float(k9[4]), float(k9[2]), float(k9[5])
+            keep.append((d, f, dm, None if f is None else fm))
         self._keep = keep          # alive until the next call (the launches read them asynchronously)
         self._capi.check(self._lib.nvbx_integrate_frames_batch(self._jobs, n, self._host_threads))
 

@@ -103,15 +103,28 @@ class Layer(abc.ABC):
         return torch.from_numpy(out[:min(n, n2)].copy())
 
     def get_all_blocks(self) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
-        """(block tensors, block indices): zero-copy device views + int32[3] CPU index tensors."""
-        idx = self.get_all_block_indices()
-        blocks, indices = [], []
-        for row in idx:
-            b = self._block_view(int(row[0]), int(row[1]), int(row[2]))
-            if b is not None:
-                blocks.append(b)
-                indices.append(row.clone())
-        return blocks, indices
+        """(block tensors, block indices): zero-copy device views + int32[3] CPU index tensors.
+
+        One kernel launch and one stream synchronisation for the whole layer (reference: one pass over the
+        layer, py_layer.cpp:177-198), not one per block."""
+        L = _capi.load()
+        stride = C.c_int64()
+        n = int(_capi.check(L.nvbx_get_all_blocks(self._h(), self._map_id, self._layer_id, None, None, 0,
+                                                  C.byref(stride), self._stream())))
+        if n == 0:
+            return [], []
+        idx = np.zeros((n, 3), np.int32)
+        ptrs = np.zeros(n, np.uint64)
+        n2 = int(_capi.check(L.nvbx_get_all_blocks(self._h(), self._map_id, self._layer_id,
+                                                   idx.ctypes.data_as(C.c_void_p), ptrs.ctypes.data_as(C.c_void_p), n,
+                                                   C.byref(stride), self._stream())))
+        n = min(n, n2)
+        ne, s = self.num_elements_per_voxel(), int(stride.value)
+        dtype = {_TSDF: torch.float32, _FEATURE: torch.float16, _COLOR: torch.uint8}[self._layer_id]
+        idx_t = torch.from_numpy(idx[:n].copy())
+        blocks = [device_view(int(ptrs[k]), (8, 8, 8, ne), dtype, self._mapper._device,
+                              strides_elems=(64 * s, 8 * s, s, 1), owner=self._mapper) for k in range(n)]
+        return blocks, [idx_t[k] for k in range(n)]
 
     def get_block_limits(self) -> Tuple[torch.Tensor, torch.Tensor]:
         idx = self.get_all_block_indices()
@@ -120,9 +133,10 @@ class Layer(abc.ABC):
     def get_voxels_matching_condition(self, get_voxel_mask: Callable) -> Tuple[torch.Tensor, torch.Tensor]:
         """Values [N,E] and centres [N,3] of the voxels for which `get_voxel_mask(block)` is true."""
         blocks, indices = self.get_all_blocks()
-        centers = indexing.get_voxel_center_grids(indices, self.voxel_size())
-        pts = [torch.zeros((0, 3), device='cuda')]
-        vals = [torch.zeros((0, self.num_elements_per_voxel()), device='cuda')]
+        dev = f'cuda:{self._mapper._device}'
+        centers = indexing.get_voxel_center_grids(indices, self.voxel_size(), device=dev)
+        pts = [torch.zeros((0, 3), device=dev)]
+        vals = [torch.zeros((0, self.num_elements_per_voxel()), device=dev)]
         for blk, ctr in zip(blocks, centers):
             mask = get_voxel_mask(blk)
             assert mask.shape == torch.Size([8, 8, 8]), 'Your condition should generate a 8x8x8 mask.'
@@ -213,7 +227,8 @@ def convert_layer_to_dense_tensor(layer: Union[TsdfLayer, FeatureLayer],
     else:
         raise TypeError(f'Unsupported layer type to convert to dense tensor: {type(layer)}')
     n = layer.block_dim_in_voxels
-    out = torch.full((nblk * n).tolist() + [depth], fill_value=unobserved_value, dtype=torch.float32, device='cuda')
+    dev = f'cuda:{layer._mapper._device}'
+    out = torch.full((nblk * n).tolist() + [depth], fill_value=unobserved_value, dtype=torch.float32, device=dev)
     for row in layer.get_all_block_indices():
         rel = row - bmin
         if bool((rel < 0).any()) or bool((rel >= nblk).any()):
@@ -224,7 +239,7 @@ def convert_layer_to_dense_tensor(layer: Union[TsdfLayer, FeatureLayer],
         x, y, z = (rel * n).tolist()
         out[x:x + n, y:y + n, z:z + n] = blk[..., :depth].to(torch.float32)
     lo, hi = bmin * n, (bmax + 1) * n
-    grids = torch.meshgrid(*[torch.arange(int(lo[i]), int(hi[i]), device='cuda') for i in range(3)], indexing='ij')
+    grids = torch.meshgrid(*[torch.arange(int(lo[i]), int(hi[i]), device=dev) for i in range(3)], indexing='ij')
     centers = (torch.stack(grids, dim=-1) + 0.5) * layer.voxel_size()
     assert out.shape[:-1] == centers.shape[:-1]
     return out, centers

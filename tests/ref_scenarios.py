@@ -334,3 +334,106 @@ def mesh_rows_from(idx, verts, voxel, vb) -> dict:
     allr = np.concatenate(out) if out else np.zeros((0, 4), np.int64)
     return dict(mesh_vertex_bits=allr[:, :3].astype(np.uint32), mesh_vertex_voxel=allr[:, 3].astype(np.int16),
                 mesh_counts=np.asarray(cnt, np.int32))
+
+
+# -------------------------------------------------------------------------------------------------------------
+# the CUDA product as a backend (tests/test_gpu_ref_vectors.py)
+# -------------------------------------------------------------------------------------------------------------
+class GpuBackend:
+    def __init__(self, sc, channels, device=0):
+        import torch
+        from nvblox_torch.constants import constants
+        from nvblox_torch.mapper import Mapper
+        constants.set_feature_array_num_elements(channels)
+        mp, _ = scenario_params(sc)
+        self.t = torch
+        self.dev = f'cuda:{device}'
+        self.C = channels
+        self.m = Mapper(voxel_sizes_m=float(sc['voxel_size']), mapper_parameters=mp)
+
+    def _d(self, a):
+        return None if a is None else self.t.from_numpy(np.ascontiguousarray(a)).to(self.dev)
+
+    def depth(self, depth, T, K, mask):
+        self.m.add_depth_frame(self._d(depth), self.t.from_numpy(T), self.t.from_numpy(K), self._d(mask))
+
+    def features(self, feat, T, K, mask):
+        self.m.add_feature_frame(self._d(feat), self.t.from_numpy(T), self.t.from_numpy(K), self._d(mask))
+
+    def color(self, rgb, T, K, mask):
+        self.m.add_color_frame(self._d(rgb), self.t.from_numpy(T), self.t.from_numpy(K), self._d(mask))
+
+    def decay(self):
+        self.m.decay()
+
+    def last_block_list(self, which):
+        from nvblox_mindmap_b200 import _capi
+        L = _capi.load()
+        n = int(_capi.check(L.nvbx_debug_last_block_list(self.m._handle, 0, which, None, 0, self.m._stream())))
+        out = np.zeros((max(n, 1), 3), np.int32)
+        _capi.check(L.nvbx_debug_last_block_list(self.m._handle, 0, which, out.ctypes.data_as(C.c_void_p), n,
+                                                 self.m._stream()))
+        return out[:n]
+
+    def synthetic_depth(self):
+        from nvblox_mindmap_b200 import _capi
+        from nvblox_mindmap_b200.torch_interop import device_view
+        L = _capi.load()
+        p, r, c = C.c_void_p(), C.c_int(), C.c_int()
+        _capi.check(L.nvbx_debug_last_synthetic_depth(self.m._handle, 0, C.byref(p), C.byref(r), C.byref(c)))
+        return device_view(p.value, (r.value, c.value), self.t.float32, self.m._device, owner=self.m).cpu().numpy()
+
+    def _layer(self, view, shape, dtype):
+        from tests.parity_utils import gpu_blocks
+        idx, data = gpu_blocks(view)
+        if data is None:
+            data = np.zeros((0,) + shape, dtype)
+        return idx, data
+
+    def tsdf(self):
+        return self._layer(self.m.tsdf_layer_view(0), (8, 8, 8, 2), np.float32)
+
+    def feat(self):
+        return self._layer(self.m.feature_layer_view(0), (8, 8, 8, self.C + 1), np.float16)
+
+    def colour(self):
+        from nvblox_mindmap_b200.torch_interop import device_view
+        layer = self.m.color_layer_view(0)
+        idx, rgb = self._layer(layer, (8, 8, 8, 3), np.uint8)
+        w = np.zeros((len(idx), 8, 8, 8), np.float32)
+        for k, row in enumerate(idx):
+            blk = layer.get_block_at_index(self.t.from_numpy(row))
+            raw = device_view(blk.data_ptr(), (8, 8, 8, 8), self.t.uint8, self.m._device, owner=self.m).cpu().numpy()
+            w[k] = raw[..., 4:8].copy().view(np.float32)[..., 0]
+        return idx, rgb, w
+
+
+def gpu_mesh_rows(sc, channels, tsdf_idx, tsdf_data, device=0) -> np.ndarray:
+    """Un-welded marching-cubes vertices + painted voxel id of the given TSDF layer through the CUDA product:
+    globally sorted rows (x bits, y bits, z bits, voxel)."""
+    import torch
+    from nvblox_mindmap_b200 import _capi
+    from nvblox_torch.constants import constants
+    from nvblox_torch.mapper import Mapper
+    constants.set_feature_array_num_elements(channels)
+    mp, _ = scenario_params(sc)
+    mp._mesh_integrator_params.mesh_integrator_weld_vertices = False
+    m = Mapper(voxel_sizes_m=float(sc['voxel_size']), mapper_parameters=mp)
+    tl, fl = m.tsdf_layer_view(0), m.feature_layer_view(0)
+    fb = torch.zeros((8, 8, 8, channels + 1), dtype=torch.float16, device=f'cuda:{device}')
+    fb[..., 0] = torch.arange(512, device=f'cuda:{device}').reshape(8, 8, 8).to(torch.float16)
+    for i, b in enumerate(tsdf_idx):
+        bt = torch.from_numpy(np.ascontiguousarray(b))
+        tl.allocate_block_at_index(bt)
+        fl.allocate_block_at_index(bt)
+    for i, b in enumerate(tsdf_idx):    # views are taken after every allocation (allocation may move nothing, but
+        bt = torch.from_numpy(np.ascontiguousarray(b))    # the documented contract is "invalidated by any mutation")
+        tl.get_block_at_index(bt).copy_(torch.from_numpy(tsdf_data[i]).to(f'cuda:{device}'))
+        fl.get_block_at_index(bt).copy_(fb)
+    _capi.check(_capi.load().nvbx_mark_all_dirty(m._handle, 0, m._stream()))
+    m.update_feature_mesh(0)
+    mesh = m.get_feature_mesh(0)
+    v = mesh.vertices().cpu().numpy()
+    vox = mesh.vertex_features()[:, 0].cpu().numpy().astype(np.int64)
+    rows = np.concatenate([np.ascontiguousarray(v, np.float32).view(np.uint32).astype(np.int64), vox[:, None]], axis=1)
+    return rows[np.lexsort(rows.T[::-1])] if len(rows) else rows

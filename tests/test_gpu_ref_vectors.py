@@ -1,0 +1,52 @@
+"""The CUDA product against REFERENCE-COMPILED golden vectors (tests/golden/ref_nvcc_pipeline_*.npz): frame sequences
+whose every device stage was computed by the reference's own kernels (compiled verbatim with nvblox's nvcc flags,
+oracle/ref_snippets/, tests/golden/make_ref_vectors.py).  The product must reproduce the per-frame block lists, the
+synthetic depth images, the TSDF / feature / colour layers, the un-welded marching-cubes vertices and the voxel the
+mesh paint picks BIT FOR BIT (north_star bars: block sets exact, TSDF 1e-5 relative, features 1 fp16 ulp -- all met
+with zero slack).  Nothing here reads /root/reference or oracle/_ref."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import ref_scenarios as RS
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint8).reshape(a.shape + (a.dtype.itemsize,)) if a.dtype.kind == 'f' else a
+
+
+@pytest.mark.parametrize('name', list(RS.SCENARIOS))
+def test_product_reproduces_reference_kernels(name):
+    gold = np.load(os.path.join(GOLD, f'ref_nvcc_pipeline_{name}.npz'))
+    sc = RS.SCENARIOS[name]
+    mine = RS.run_scenario(sc, 16, RS.GpuBackend(sc, 16))
+    for k in mine:
+        assert mine[k].shape == gold[k].shape, f'{name}/{k}: shape {mine[k].shape} vs reference {gold[k].shape}'
+        bad = int((_bits(mine[k]) != _bits(gold[k])).sum())
+        assert bad == 0, f'{name}/{k}: {bad} elements differ from the reference kernels'
+    # marching cubes + closest-voxel paint on the reference's own final TSDF layer
+    rows = RS.gpu_mesh_rows(sc, 16, gold['tsdf_idx'], gold['tsdf_data'])
+    ref = np.concatenate([gold['mesh_vertex_bits'].astype(np.int64), gold['mesh_vertex_voxel'].astype(np.int64)[:, None]],
+                         axis=1)
+    ref = ref[np.lexsort(ref.T[::-1])]
+    assert rows.shape == ref.shape and np.array_equal(rows, ref), f'{name}: mesh vertices / painted voxels differ'
+    assert len(ref) > 1000
+
+
+def test_product_reproduces_reference_kernels_c768():
+    """The headline channel count through the C = 768 gather kernel: digests + sampled rows."""
+    gold = np.load(os.path.join(GOLD, 'ref_nvcc_pipeline_cube_stacking_c768.npz'))
+    dg = json.loads(str(gold['digests']))
+    sc = RS.SCENARIOS['cube_stacking']
+    mine = RS.run_scenario(sc, 768, RS.GpuBackend(sc, 768))
+    rows = np.ascontiguousarray(mine['feat_data']).reshape(-1, 769)[gold['sample_rows']].view(np.uint16)
+    assert np.array_equal(rows, gold['sample_values'])
+    for k, v in mine.items():
+        assert hashlib.sha256(np.ascontiguousarray(v).tobytes()).hexdigest() == dg[k], k
