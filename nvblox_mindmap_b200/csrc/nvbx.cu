@@ -253,6 +253,7 @@ struct Map {
   unsigned long long* d_tmp_ptr = nullptr;
   DevBuf<int3> idx_out;
   DevBuf<unsigned long long> ptr_out;
+  DevBuf<int> slot_out;
 };
 
 }  // namespace
@@ -671,6 +672,7 @@ void destroy_map(Map& mp) {
   mp.st_low_in.release();
   mp.idx_out.release();
   mp.ptr_out.release();
+  mp.slot_out.release();
 }
 
 Cam make_cam(float fx, float fy, float cx, float cy, int H, int W) {
@@ -1834,27 +1836,10 @@ int64_t nvbx_num_allocated_bytes(nvbx_mapper* m, int map_id, int layer, void* st
   return (int64_t)mp.feat_capacity * kVoxelsPerBlock * (int64_t)mp.dev.row * (int64_t)sizeof(__half);
 }
 
-int64_t nvbx_get_block_indices(nvbx_mapper* m, int map_id, int layer, int32_t* out_xyz, int64_t capacity,
-                               void* stream_v) {
-  int rc = check_map(m, map_id);
-  if (rc) return rc;
-  Map& mp = *m->maps[map_id];
-  cudaStream_t stream = (cudaStream_t)stream_v;
-  if ((rc = mp.idx_out.ensure((size_t)mp.slot_capacity, stream))) return rc;
-  CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->list_count, 0, sizeof(int), stream));
-  LAUNCH(k_collect_block_indices, persistent_grid(m, 4), 256, 0, stream, mp.dev,
-         (uint8_t)(layer == NVBX_LAYER_TSDF ? kLayerTsdfBit : (layer == NVBX_LAYER_COLOR ? kLayerColorBit : kLayerFeatBit)),
-         mp.idx_out.p, mp.slot_capacity);
-  if ((rc = read_ctrl(mp, stream))) return rc;
-  const int64_t n = mp.h_ctrl->list_count;
-  if (out_xyz && capacity > 0) {
-    const int64_t c = std::min(n, capacity);
-    CUDA_TRY(cudaMemcpyAsync(out_xyz, mp.idx_out.p, (size_t)c * sizeof(int3), cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
-  }
-  return n;
-}
-
+// Blocks of a layer in DESCENDING slot order.  Slot ids are handed out in increasing order, so this is reverse
+// allocation order -- what iterating the reference's std::unordered_map gives for a freshly built layer (each new
+// node goes to the head of the node list; NT tests/test_layer.py:101-138 rely on it) -- and it is deterministic,
+// which the arrival order of the collecting kernel's atomics is not.
 int64_t nvbx_get_all_blocks(nvbx_mapper* m, int map_id, int layer, int32_t* out_xyz, void** out_ptrs, int64_t capacity,
                             int64_t* voxel_stride_elems, void* stream_v) {
   int rc = check_map(m, map_id);
@@ -1867,19 +1852,41 @@ int64_t nvbx_get_all_blocks(nvbx_mapper* m, int map_id, int layer, int32_t* out_
   if (layer == NVBX_LAYER_TSDF && out_ptrs) ++mp.tsdf_version;  // the caller may write through the returned views
   if ((rc = mp.idx_out.ensure((size_t)mp.slot_capacity, stream))) return rc;
   if ((rc = mp.ptr_out.ensure((size_t)mp.slot_capacity, stream))) return rc;
+  if ((rc = mp.slot_out.ensure((size_t)mp.slot_capacity, stream))) return rc;
   CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->list_count, 0, sizeof(int), stream));
   LAUNCH(k_collect_blocks, persistent_grid(m, 4), 256, 0, stream, mp.dev, layer, mp.idx_out.p, mp.ptr_out.p,
-         mp.slot_capacity);
+         mp.slot_out.p, mp.slot_capacity);
   if ((rc = read_ctrl(mp, stream))) return rc;
   const int64_t n = mp.h_ctrl->list_count;
-  if (capacity > 0 && (out_xyz || out_ptrs)) {
-    const int64_t c = std::min(n, capacity);
-    if (out_xyz) CUDA_TRY(cudaMemcpyAsync(out_xyz, mp.idx_out.p, (size_t)c * sizeof(int3), cudaMemcpyDeviceToHost, stream));
-    if (out_ptrs)
-      CUDA_TRY(cudaMemcpyAsync(out_ptrs, mp.ptr_out.p, (size_t)c * sizeof(void*), cudaMemcpyDeviceToHost, stream));
+  if (capacity > 0 && n > 0 && (out_xyz || out_ptrs)) {
+    std::vector<int3> idx((size_t)n);
+    std::vector<unsigned long long> ptrs((size_t)n);
+    std::vector<int> slots((size_t)n);
+    CUDA_TRY(cudaMemcpyAsync(idx.data(), mp.idx_out.p, (size_t)n * sizeof(int3), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(ptrs.data(), mp.ptr_out.p, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             stream));
+    CUDA_TRY(cudaMemcpyAsync(slots.data(), mp.slot_out.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
+    std::vector<int> order((size_t)n);
+    for (int64_t i = 0; i < n; ++i) order[(size_t)i] = (int)i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return slots[(size_t)a] > slots[(size_t)b]; });
+    const int64_t c = std::min(n, capacity);
+    for (int64_t i = 0; i < c; ++i) {
+      const size_t k = (size_t)order[(size_t)i];
+      if (out_xyz) {
+        out_xyz[3 * i] = idx[k].x;
+        out_xyz[3 * i + 1] = idx[k].y;
+        out_xyz[3 * i + 2] = idx[k].z;
+      }
+      if (out_ptrs) out_ptrs[i] = (void*)ptrs[k];
+    }
   }
   return n;
+}
+
+int64_t nvbx_get_block_indices(nvbx_mapper* m, int map_id, int layer, int32_t* out_xyz, int64_t capacity,
+                               void* stream_v) {
+  return nvbx_get_all_blocks(m, map_id, layer, out_xyz, nullptr, capacity, nullptr, stream_v);
 }
 
 int nvbx_get_block_ptr(nvbx_mapper* m, int map_id, int layer, int x, int y, int z, void** ptr,

@@ -1659,20 +1659,10 @@ __global__ void __launch_bounds__(256) k_clear_all(MapDev m) {
 // ================================================================================================
 // a13. Layer views and point queries.
 // ================================================================================================
-__global__ void __launch_bounds__(256) k_collect_block_indices(MapDev m, uint8_t layer_bit, int3* out, int capacity) {
-  pdl_prologue();
-  const int n = m.ctrl->slot_high;
-  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-    if (m.blk_layers[s] & layer_bit) {
-      const int pos = atomicAdd(&m.ctrl->list_count, 1);
-      if (pos < capacity) out[pos] = m.blk_index[s];
-    }
-  }
-}
-
-// getAllBlocks (py_layer.cpp:177-198) in one pass: block index AND payload pointer of every block of a layer.
+// getAllBlocks / getAllBlockIndices (py_layer.cpp:177-198) in one pass: slot id, block index AND payload pointer of
+// every block of a layer (the host orders the result by slot id).
 __global__ void __launch_bounds__(256) k_collect_blocks(MapDev m, int layer, int3* out_idx, unsigned long long* out_ptr,
-                                                        int capacity) {
+                                                        int* out_slot, int capacity) {
   pdl_prologue();
   const int n = m.ctrl->slot_high;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
@@ -1689,6 +1679,7 @@ __global__ void __launch_bounds__(256) k_collect_blocks(MapDev m, int layer, int
       if (pos < capacity) {
         out_idx[pos] = m.blk_index[s];
         out_ptr[pos] = p;
+        out_slot[pos] = s;
       }
     }
   }

@@ -32,3 +32,7 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+# The reference's own test files are staged (unmodified, git-ignored) under tests/ref_tests/_ref/ and are run THROUGH
+# tests/test_gpu_reference_suite.py (which supplies the package layout and stubs they need), never collected directly.
+collect_ignore_glob = ['ref_tests/_ref/*']

