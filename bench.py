@@ -188,6 +188,9 @@ def run_ours(args, rank, world, local_rank):
     constants.set_feature_array_num_elements(C_FEAT)
     mp, _ = mapper_params()
     mapper = Mapper(voxel_sizes_m=VOXEL, mapper_parameters=mp, device=local_rank)
+    # replay: every frame of the sequence stays resident and unmodified, which is the contract of frame pipelining
+    # (the gather of frame i on the map's own stream, the depth path of frame i + 1 underneath it; same results)
+    mapper.set_pipelining(bool(args.pipelining))
 
     n_total = args.warmup + args.steps
     K, frames = poses_and_depths(max(n_total, 1))
@@ -227,6 +230,7 @@ def run_ours(args, rank, world, local_rank):
     for i in range(args.warmup, n_total):
         step(i)
     t_host = time.perf_counter() - t_host      # host time to ENQUEUE the steps (no sync inside)
+    mapper.pipeline_join()                     # the timed region ends when the last gather has finished
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -665,6 +669,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--sweep-gather', action='store_true', help='tuning aid: time every gather schedule')
     ap.add_argument('--quick', action='store_true', help='tuning aid: device-timed pass + kernel timing only')
+    ap.add_argument('--pipelining', type=int, default=1, help='frame pipelining (Mapper.set_pipelining) in the device-timed pass')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

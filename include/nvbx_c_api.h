@@ -269,6 +269,19 @@ int nvbx_clear(nvbx_mapper* m, int map_id, void* stream);
  * the block payloads were written through the layer views. */
 int nvbx_mark_all_dirty(nvbx_mapper* m, int map_id, void* stream);
 
+/* ---- frame pipelining (ours) ------------------------------------------------------------------------------
+ * nvbx_set_pipelining(m, 1): the memory-bound gather of feature frame i runs on a stream owned by the map, so that the
+ * latency-bound depth path of frame i + 1 (raycast, TSDF update, sphere tracing + band selection, geometry), which the
+ * caller enqueues next on ITS stream, runs underneath it instead of behind it.  Results are unchanged (bit for bit).
+ * Contract while it is on: the FEATURE frame passed to nvbx_integrate_features must stay valid and unmodified until
+ * the second-next nvbx_integrate_features call on that map returns, or until any call that reads or frees feature
+ * data (decay, clear, mesh update, feature block views, feature queries, nvbx_pipeline_join) -- every such call first
+ * orders its stream behind the gathers in flight.  Depth frames, masks and colour frames are consumed on the caller's
+ * stream as before.  Off by default (the reference's callers free or overwrite a frame right after the call). */
+int nvbx_set_pipelining(nvbx_mapper* m, int on);
+/* Order `stream` behind every gather in flight of map_id (-1: all maps). */
+int nvbx_pipeline_join(nvbx_mapper* m, int map_id, void* stream);
+
 /* ---- surface extraction ------------------------------------------------------------------------- */
 
 /* Mapper::updateFeatureMesh, py_mapper.cu:196-204 -> Mapper::updateMeshTemplate mapper.cpp:580-614

@@ -17,7 +17,8 @@ _lib = None
 API_SYMBOLS = [
     'nvbx_default_params', 'nvbx_create', 'nvbx_destroy', 'nvbx_num_maps', 'nvbx_feature_channels',
     'nvbx_get_params', 'nvbx_last_error', 'nvbx_integrate_depth', 'nvbx_integrate_features',
-    'nvbx_integrate_color', 'nvbx_integrate_frame_host', 'nvbx_set_host_fetch_mode', 'nvbx_integrate_features_lowres',
+    'nvbx_integrate_color', 'nvbx_integrate_frame_host', 'nvbx_set_host_fetch_mode', 'nvbx_set_pipelining',
+    'nvbx_pipeline_join', 'nvbx_integrate_features_lowres',
     'nvbx_upsample_features', 'nvbx_integrate_frame_host_lowres', 'nvbx_decay', 'nvbx_clear', 'nvbx_mark_all_dirty',
     'nvbx_update_feature_mesh', 'nvbx_get_feature_mesh', 'nvbx_update_color_mesh', 'nvbx_get_color_mesh',
     'nvbx_export_points', 'nvbx_gather_points', 'nvbx_num_blocks', 'nvbx_num_allocated_blocks',
@@ -95,6 +96,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         L.nvbx_query_tsdf.argtypes = [vp, C.c_int, vp, C.c_int64, vp, vp]
         L.nvbx_query_features.argtypes = [vp, C.c_int, vp, C.c_int64, vp, vp]
         L.nvbx_set_host_fetch_mode.argtypes = [vp, C.c_int]
+        L.nvbx_set_pipelining.argtypes = [vp, C.c_int]
+        L.nvbx_pipeline_join.argtypes = [vp, C.c_int, vp]
         L.nvbx_get_counters.argtypes = [vp, C.c_int, C.POINTER(NvbxCounters), vp]
         L.nvbx_reset_counters.argtypes = [vp, C.c_int, vp]
         L.nvbx_set_gather_tuning.argtypes = [C.c_int, C.c_int, C.c_int]

@@ -204,7 +204,12 @@ struct Map {
   DevBuf<int> view_slots, band_slots, newfeat_slots, cband_slots;
   int color_parity = 0;
   bool have_cband_list = false;
-  DevBuf<FeatItem> items;
+  DevBuf<FeatItem> items2[2];  // feature work-item lists, double-buffered by MapDev::fp
+  // Frame pipelining (nvbx_set_pipelining): the gather of feature frame i runs on `gstream`, ordered after the
+  // frame's geometry kernel by `ev_geom`; `ev_gather[p]` marks the end of the last gather that used parity p.
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t ev_geom = nullptr, ev_gather[2] = {nullptr, nullptr};
+  bool gather_pending[2] = {false, false};
   DevBuf<float> synth;
   int synth_rows = 0, synth_cols = 0;
   // The synthetic depth image is a pure function of (pose, camera, truncation, TSDF contents): the colour and
@@ -265,6 +270,7 @@ struct nvbx_mapper {
   int C = 0;
   int sm_count = 148;
   int host_fetch_mode = NVBX_HOST_FETCH_SPARSE;
+  bool pipelining = false;  // nvbx_set_pipelining
   nvbx_params params{};
   std::vector<std::unique_ptr<Map>> maps;
 };
@@ -324,7 +330,38 @@ int grow_color_slabs(Map& mp, cudaStream_t stream) {
 }
 
 // Grow the slot table (and TSDF slabs, hash) to hold `new_cap` block indices.
+// ---- frame pipelining (nvbx_set_pipelining) -------------------------------------------------------------
+// The gather of feature frame i may run on the map's own stream while the caller's stream already carries the
+// depth path of frame i + 1 (raycast, TSDF update, sphere tracing + band selection, geometry): those kernels are
+// latency-bound and touch nothing the memory-bound gather reads or writes (Ctrl counters and the item list are
+// double-buffered by MapDev::fp, voxel weights are written by the geometry kernel).
+int pipeline_init(Map& mp) {
+  if (mp.gstream) return NVBX_OK;
+  int lo = 0, hi = 0;
+  CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CUDA_TRY(cudaStreamCreateWithPriority(&mp.gstream, cudaStreamNonBlocking, lo));  // lowest: the short kernels go first
+  CUDA_TRY(cudaEventCreateWithFlags(&mp.ev_geom, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&mp.ev_gather[0], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&mp.ev_gather[1], cudaEventDisableTiming));
+  return NVBX_OK;
+}
+// Order `stream` after every gather still in flight: called by whatever reads or frees feature blocks.
+int pipeline_join(Map& mp, cudaStream_t stream) {
+  for (int p = 0; p < 2; ++p)
+    if (mp.gather_pending[p]) {
+      CUDA_TRY(cudaStreamWaitEvent(stream, mp.ev_gather[p], 0));
+      mp.gather_pending[p] = false;
+    }
+  return NVBX_OK;
+}
+// Host-side wait (before device memory the gather uses is re-allocated or freed).
+int pipeline_drain(Map& mp) {
+  if (mp.gstream && (mp.gather_pending[0] || mp.gather_pending[1])) CUDA_TRY(cudaStreamSynchronize(mp.gstream));
+  return NVBX_OK;
+}
+
 int grow_slots(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
+  if (int prc = pipeline_drain(mp)) return prc;
   CUDA_TRY(cudaStreamSynchronize(stream));
   const int old = mp.slot_capacity;
   new_cap = ((new_cap + (1 << kTsdfSlabShift) - 1) >> kTsdfSlabShift) << kTsdfSlabShift;
@@ -369,6 +406,7 @@ int grow_slots(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
 }
 
 int grow_feats(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
+  if (int prc = pipeline_drain(mp)) return prc;
   CUDA_TRY(cudaStreamSynchronize(stream));
   const int old = mp.feat_capacity;
   new_cap = ((new_cap + (1 << kFeatSlabShift) - 1) >> kFeatSlabShift) << kFeatSlabShift;
@@ -649,7 +687,16 @@ void destroy_map(Map& mp) {
   mp.band_slots.release();
   mp.newfeat_slots.release();
   mp.cband_slots.release();
-  mp.items.release();
+  mp.items2[0].release();
+  mp.items2[1].release();
+  if (mp.gstream) {
+    cudaStreamSynchronize(mp.gstream);
+    cudaStreamDestroy(mp.gstream);
+    cudaEventDestroy(mp.ev_geom);
+    cudaEventDestroy(mp.ev_gather[0]);
+    cudaEventDestroy(mp.ev_gather[1]);
+    mp.gstream = nullptr;
+  }
   mp.synth.release();
   mp.cnt_v.release();
   mp.cnt_t.release();
@@ -728,24 +775,24 @@ int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, 
   if ((rc = timing_begin(m, 0, stream))) return rc;
   switch (gather_variant()) {  // <CH, units in flight per warp, resident CTAs per SM>
     case 1:
-      LAUNCH((k_feature_gather<CH, 2, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
+      LAUNCH((k_feature_gather<CH, 2, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p, ff, last_chunk);
       break;
     case 2:
-      LAUNCH((k_feature_gather<CH, 1, 6>), persistent_grid(m, 6), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
+      LAUNCH((k_feature_gather<CH, 1, 6>), persistent_grid(m, 6), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p, ff, last_chunk);
       break;
     case 3:
-      LAUNCH((k_feature_gather<CH, 1, 8>), persistent_grid(m, 8), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
+      LAUNCH((k_feature_gather<CH, 1, 8>), persistent_grid(m, 8), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p, ff, last_chunk);
       break;
     case 5:
-      LAUNCH((k_feature_gather_dyn<CH, 512, 2>), persistent_grid(m, 2), 512, 0, stream, mp.dev, mp.items.p,
-             (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
+      LAUNCH((k_feature_gather_dyn<CH, 512, 2>), persistent_grid(m, 2), 512, 0, stream, mp.dev, mp.items2[mp.dev.fp].p,
+             (int)mp.items2[mp.dev.fp].cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
       break;
     case 6:
-      LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 5), 256, 0, stream, mp.dev, mp.items.p,
-             (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
+      LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 5), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p,
+             (int)mp.items2[mp.dev.fp].cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
       break;
     case 0:
-      LAUNCH((k_feature_gather<CH, 1, 4>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p, ff, last_chunk);
+      LAUNCH((k_feature_gather<CH, 1, 4>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p, ff, last_chunk);
       break;
     case 10:  // cp.async.bulk + mbarrier staging, one 8-warp CTA per SM (C = 256 * CH only)
       if constexpr (CH > 0) {
@@ -756,27 +803,27 @@ int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, 
         }();
         (void)once;
         LAUNCH((k_feature_gather_tma<CH>), persistent_grid(m, 1), kTmaWarps * 32, TmaGather<CH>::kSmemBytes, stream,
-               mp.dev, mp.items.p, ff, last_chunk);
+               mp.dev, mp.items2[mp.dev.fp].p, ff, last_chunk);
       } else {
-        LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p,
-               (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
+        LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p,
+               (int)mp.items2[mp.dev.fp].cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
       }
       break;
     case 7:  // the 48-register build on 4 CTAs / SM: leaves registers for two CTAs of the next frame's raycast
-      LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p,
-             (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
+      LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p,
+             (int)mp.items2[mp.dev.fp].cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
       break;
     case 8:
-      LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items.p,
-             (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
+      LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p,
+             (int)mp.items2[mp.dev.fp].cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
       break;
     case 9:
-      LAUNCH((k_feature_gather_dyn<CH, 256, 6>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p,
-             (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
+      LAUNCH((k_feature_gather_dyn<CH, 256, 6>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p,
+             (int)mp.items2[mp.dev.fp].cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
       break;
     default:
-      LAUNCH((k_feature_gather_dyn<CH, 256, 4>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items.p,
-             (int)mp.items.cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
+      LAUNCH((k_feature_gather_dyn<CH, 256, 4>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p,
+             (int)mp.items2[mp.dev.fp].cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
   }
   return timing_end(m, 0, stream);
 }
@@ -788,15 +835,15 @@ int launch_gather_up(nvbx_mapper* m, Map& mp, const FeatFrame& ff, const UpFrame
   if ((rc = timing_begin(m, 0, stream))) return rc;
   switch (mode) {  // <CH, torch kernel flavour, resident CTAs per SM>
     case 1:
-      LAUNCH((k_feature_gather_up<CH, 1, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items.p, ff, uf,
+      LAUNCH((k_feature_gather_up<CH, 1, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p, ff, uf,
              last_chunk);
       break;
     case 2:
-      LAUNCH((k_feature_gather_up<CH, 2, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items.p, ff, uf,
+      LAUNCH((k_feature_gather_up<CH, 2, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p, ff, uf,
              last_chunk);
       break;
     default:
-      LAUNCH((k_feature_gather_up<CH, 0, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items.p, ff, uf,
+      LAUNCH((k_feature_gather_up<CH, 0, 3>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p, ff, uf,
              last_chunk);
   }
   return timing_end(m, 0, stream);
@@ -906,6 +953,7 @@ int nvbx_create(int n_maps, const float* voxel_sizes_m, const nvbx_params* param
 void nvbx_destroy(nvbx_mapper* m) {
   if (!m) return;
   cudaSetDevice(m->device);
+  for (auto& mp : m->maps) pipeline_drain(*mp);
   for (auto& mp : m->maps) destroy_map(*mp);
   delete m;
 }
@@ -1153,7 +1201,7 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
     if ((rc = mp.band_slots.ensure((size_t)cand_bound, stream))) return rc;
     if ((rc = mp.newfeat_slots.ensure((size_t)cand_bound, stream))) return rc;
     const long long chunk_blocks = std::min<long long>(cand_bound, kFeatureChunkBlocks);
-    if ((rc = mp.items.ensure((size_t)chunk_blocks * kVoxelsPerBlock, stream))) return rc;
+    if ((rc = mp.items2[mp.dev.fp].ensure((size_t)chunk_blocks * kVoxelsPerBlock, stream))) return rc;
     band_list = mp.band_slots.p;
   } else {
     if ((rc = enable_color(mp, stream))) return rc;
@@ -1273,6 +1321,16 @@ int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, co
   cudaStream_t stream = (cudaStream_t)stream_v;
   Map& mp = *m->maps[map_id];
   mp.have_band_list = false;
+  // This frame re-uses the item list and the counters of parity fp: the gather that read them last (frame i - 2,
+  // if it ran on the gather stream) must be done before the frame's first kernel.  A frame that cannot be pipelined
+  // (host-resident / low-res feature sources) runs its gather on the caller's stream, behind every gather in flight.
+  bool pipe = m->pipelining && !hf && !uf && features != nullptr;
+  if (!pipe) {
+    if ((rc = pipeline_join(mp, stream))) return rc;
+  } else if (mp.gather_pending[mp.dev.fp]) {
+    CUDA_TRY(cudaStreamWaitEvent(stream, mp.ev_gather[mp.dev.fp], 0));
+    mp.gather_pending[mp.dev.fp] = false;
+  }
   AppearancePrep prep;
   if ((rc = appearance_prepare(m, mp, mp.planes_cache, height, width, T_L_C_rm, fx, fy, cx, cy, -1, stream, &prep)))
     return rc;
@@ -1309,18 +1367,24 @@ int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, co
     std::memcpy(&ff.h_w2, &h2, 2);
   }
   ff.read_old = (p.strict_blend || ff.alpha != 1.0f) ? 1 : 0;
+  if (pipe && cand_bound > chunk_blocks) {  // several geometry / gather passes share one item list: not pipelined
+    pipe = false;
+    if ((rc = pipeline_join(mp, stream))) return rc;
+  }
+  if (pipe && (rc = pipeline_init(mp))) return rc;
+  cudaStream_t gs = pipe ? mp.gstream : stream;
   for (long long begin = 0; begin < cand_bound; begin += chunk_blocks) {
     const long long end = std::min(cand_bound, begin + chunk_blocks);
     const int last = end >= cand_bound ? 1 : 0;
-    if (begin > 0) CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->item_count, 0, sizeof(int), stream));
+    if (begin > 0) CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->item_count[mp.dev.fp], 0, sizeof(int), stream));
     const int ggrid = persistent_grid(m, 2);  // full grid: new feature blocks are zero-filled by all CTAs
-    LAUNCH(k_feature_geometry, ggrid, 512, 0, stream, mp.dev, mp.band_slots.p, mp.newfeat_slots.p, ff, mp.items.p,
+    LAUNCH(k_feature_geometry, ggrid, 512, 0, stream, mp.dev, mp.band_slots.p, mp.newfeat_slots.p, ff, mp.items2[mp.dev.fp].p,
            (int)begin, (int)end);
     const int ch = (m->C % 256 == 0 && m->C / 256 >= 1 && m->C / 256 <= 4) ? m->C / 256 : 0;
     if (hf) {
       const int nvec = m->C / 8;
       uint4* dev_img = (uint4*)const_cast<void*>(features);
-      LAUNCH(k_pixel_mark, persistent_grid(m, 2), 256, 0, stream, mp.dev, mp.items.p, hf->bitmap, width);
+      LAUNCH(k_pixel_mark, persistent_grid(m, 2), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p, hf->bitmap, width);
       const int fgrid = std::min(persistent_grid(m, 8), (hf->n_words + 7) / 8);
       if (ch == 3)
         LAUNCH(k_pixel_fetch<3>, fgrid, 256, 0, stream, mp.dev, hf->bitmap, hf->n_words, hf->host_img, dev_img, nvec);
@@ -1336,19 +1400,30 @@ int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, co
         rc = launch_gather_up<4>(m, mp, ff, *uf, up_mode, last, stream);
       else
         rc = launch_gather_up<0>(m, mp, ff, *uf, up_mode, last, stream);
-    } else if (ch == 3)
-      rc = launch_gather<3>(m, mp, ff, last, stream);
-    else if (ch == 4)
-      rc = launch_gather<4>(m, mp, ff, last, stream);
-    else if (ch == 2)
-      rc = launch_gather<2>(m, mp, ff, last, stream);
-    else if (ch == 1)
-      rc = launch_gather<1>(m, mp, ff, last, stream);
-    else
-      rc = launch_gather<0>(m, mp, ff, last, stream);
+    } else {
+      if (pipe) {
+        CUDA_TRY(cudaEventRecord(mp.ev_geom, stream));
+        CUDA_TRY(cudaStreamWaitEvent(gs, mp.ev_geom, 0));
+      }
+      if (ch == 3)
+        rc = launch_gather<3>(m, mp, ff, last, gs);
+      else if (ch == 4)
+        rc = launch_gather<4>(m, mp, ff, last, gs);
+      else if (ch == 2)
+        rc = launch_gather<2>(m, mp, ff, last, gs);
+      else if (ch == 1)
+        rc = launch_gather<1>(m, mp, ff, last, gs);
+      else
+        rc = launch_gather<0>(m, mp, ff, last, gs);
+      if (pipe && !rc) {
+        CUDA_TRY(cudaEventRecord(mp.ev_gather[mp.dev.fp], gs));
+        mp.gather_pending[mp.dev.fp] = true;
+      }
+    }
     if (rc) return rc;
   }
   mp.have_band_list = true;
+  mp.dev.fp ^= 1;  // the next feature frame uses the other half of the double-buffered lists
   return NVBX_OK;
 }
 
@@ -1506,6 +1581,31 @@ int nvbx_integrate_frame_host(nvbx_mapper* m, int map_id, const float* depth_hos
                                  stream_v, hf.host_img ? &hf : nullptr);
 }
 
+int nvbx_set_pipelining(nvbx_mapper* m, int on) {
+  if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper");
+  if (!on)
+    for (auto& mp : m->maps) {
+      int rc = pipeline_drain(*mp);
+      if (rc) return rc;
+      mp->gather_pending[0] = mp->gather_pending[1] = false;
+    }
+  m->pipelining = on != 0;
+  return NVBX_OK;
+}
+int nvbx_pipeline_join(nvbx_mapper* m, int map_id, void* stream_v) {
+  if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper");
+  if (map_id < 0) {
+    for (int i = 0; i < (int)m->maps.size(); ++i) {
+      int rc = pipeline_join(*m->maps[i], (cudaStream_t)stream_v);
+      if (rc) return rc;
+    }
+    return NVBX_OK;
+  }
+  int rc = check_map(m, map_id);
+  if (rc) return rc;
+  return pipeline_join(*m->maps[map_id], (cudaStream_t)stream_v);
+}
+
 int nvbx_set_host_fetch_mode(nvbx_mapper* m, int mode) {
   if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper");
   if (mode != NVBX_HOST_FETCH_SPARSE && mode != NVBX_HOST_FETCH_DENSE)
@@ -1578,6 +1678,7 @@ int nvbx_decay(nvbx_mapper* m, int map_id, void* stream_v) {
   }
   int rc = check_map(m, map_id);
   if (rc) return rc;
+  if ((rc = pipeline_join(*m->maps[map_id], (cudaStream_t)stream_v))) return rc;
   return decay_one(m, *m->maps[map_id], (cudaStream_t)stream_v);
 }
 
@@ -1594,6 +1695,7 @@ int nvbx_clear(nvbx_mapper* m, int map_id, void* stream_v) {
   if (rc) return rc;
   Map& mp = *m->maps[map_id];
   cudaStream_t stream = (cudaStream_t)stream_v;
+  if ((rc = pipeline_join(mp, stream))) return rc;
   ++mp.tsdf_version;
   LAUNCH(k_clear_all, persistent_grid(m, 4), 256, 0, stream, mp.dev);
   mp.slot_used_ub = 0;
@@ -1678,6 +1780,7 @@ static int update_mesh(nvbx_mapper* m, int map_id, int kind, void* stream_v) {
   }
   int rc = check_map(m, map_id);
   if (rc) return rc;
+  if ((rc = pipeline_join(*m->maps[map_id], (cudaStream_t)stream_v))) return rc;
   return update_mesh_one(m, *m->maps[map_id], kind, (cudaStream_t)stream_v);
 }
 
@@ -1850,6 +1953,7 @@ int64_t nvbx_get_all_blocks(nvbx_mapper* m, int map_id, int layer, int32_t* out_
     *voxel_stride_elems = layer == NVBX_LAYER_TSDF ? 2 : (layer == NVBX_LAYER_COLOR ? 8 : mp.dev.row);
   if (layer == NVBX_LAYER_COLOR && !mp.color_enabled) return 0;
   if (layer == NVBX_LAYER_TSDF && out_ptrs) ++mp.tsdf_version;  // the caller may write through the returned views
+  if (layer == NVBX_LAYER_FEATURE && out_ptrs && (rc = pipeline_join(mp, stream))) return rc;
   if ((rc = mp.idx_out.ensure((size_t)mp.slot_capacity, stream))) return rc;
   if ((rc = mp.ptr_out.ensure((size_t)mp.slot_capacity, stream))) return rc;
   if ((rc = mp.slot_out.ensure((size_t)mp.slot_capacity, stream))) return rc;
@@ -1898,6 +2002,7 @@ int nvbx_get_block_ptr(nvbx_mapper* m, int map_id, int layer, int x, int y, int 
   cudaStream_t stream = (cudaStream_t)stream_v;
   if (layer == NVBX_LAYER_COLOR && !mp.color_enabled) return fail(NVBX_ERR_NOT_FOUND, "block (%d, %d, %d) is not allocated", x, y, z);
   if (layer == NVBX_LAYER_TSDF) ++mp.tsdf_version;  // the caller may write through the returned view
+  if (layer == NVBX_LAYER_FEATURE && (rc = pipeline_join(mp, stream))) return rc;
   LAUNCH(k_find_one, 1, 1, 0, stream, mp.dev, x, y, z, layer, mp.d_tmp_ptr);
   unsigned long long h = 0;
   CUDA_TRY(cudaMemcpyAsync(&h, mp.d_tmp_ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
@@ -1915,6 +2020,7 @@ int nvbx_allocate_block(nvbx_mapper* m, int map_id, int layer, int x, int y, int
   if (!key_in_range(x, y, z)) return fail(NVBX_ERR_INVALID_ARGUMENT, "block index out of range");
   Map& mp = *m->maps[map_id];
   cudaStream_t stream = (cudaStream_t)stream_v;
+  if ((rc = pipeline_join(mp, stream))) return rc;
   if ((rc = ensure_slots(m, mp, 1, stream))) return rc;
   ++mp.tsdf_version;
   if (layer == NVBX_LAYER_COLOR) {
@@ -1947,6 +2053,7 @@ int nvbx_query_features(nvbx_mapper* m, int map_id, const void* xyz, int64_t n, 
   if (n < 0 || (n > 0 && (!xyz || !out))) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad query buffers");
   if (n == 0) return NVBX_OK;
   Map& mp = *m->maps[map_id];
+  if ((rc = pipeline_join(mp, (cudaStream_t)stream_v))) return rc;
   LAUNCH(k_query_features, (unsigned)((n * 32 + 127) / 128), 128, 0, (cudaStream_t)stream_v, mp.dev,
          (const float*)xyz, (long long)n, (__half*)out);
   return NVBX_OK;

@@ -615,7 +615,7 @@ __device__ __forceinline__ void band_select_tile(const MapDev& m, const PlanesVi
             m.blk_layers[s] |= kLayerFeatBit;
             atomicAdd(&m.ctrl->n_feat, 1);
             count_add(m, kCntFeatBlocksAllocated, 1);
-            newfeat_slots[atomicAdd(&m.ctrl->newfeat_count, 1)] = fs;
+            newfeat_slots[atomicAdd(&m.ctrl->newfeat_count[m.fp], 1)] = fs;
             flag = kNewFlag;  // zero-filled (cooperatively, by all CTAs) in k_feature_geometry
           }
         }
@@ -625,7 +625,7 @@ __device__ __forceinline__ void band_select_tile(const MapDev& m, const PlanesVi
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, has);
     if (ballot) {
-      int* counter = color_parity >= 0 ? &m.ctrl->cband_count[color_parity] : &m.ctrl->band_count;
+      int* counter = color_parity >= 0 ? &m.ctrl->cband_count[color_parity] : &m.ctrl->band_count[m.fp];
       int base = 0;
       if (lane == 0) base = atomicAdd(counter, __popc(ballot));
       base = __shfl_sync(0xffffffffu, base, 0);
@@ -834,7 +834,13 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
   const long long t0 = clock64();
 #endif
   PROF_BEGIN(prof_seq_early(m.ctrl), kProfTrace);
-  if (blockIdx.x == 0 && threadIdx.x == 0) m.ctrl->item_count = 0;  // consumed by k_feature_geometry
+  if (blockIdx.x == 0 && threadIdx.x == 0 && color_parity == -1) {
+    // This frame's item list (last read by the gather of frame i - 2, which the host ordered before this launch)
+    // and the OTHER half of the band counters (last read by the geometry of frame i - 1, written next by frame i + 1).
+    m.ctrl->item_count[m.fp] = 0;
+    m.ctrl->band_count[m.fp ^ 1] = 0;
+    m.ctrl->newfeat_count[m.fp ^ 1] = 0;
+  }
   // n_trace_ctas == 0: the synthetic depth image of this pose / camera / TSDF state is already in `image`
   if ((int)blockIdx.x < n_trace_ctas) {
     const int c = (blockIdx.x % trace_tiles_x) * 16 + (threadIdx.x & 7) + ((threadIdx.x >> 7) << 3);
@@ -974,26 +980,30 @@ __global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* _
   pdl_prologue();
   __shared__ int s_warp_base[17];
   __shared__ int s_base;
-  const int n = min(m.ctrl->band_count, block_end);
+  const int n = min(m.ctrl->band_count[m.fp], block_end);
   const int t = threadIdx.x;
   const int lane = t & 31, warp = t >> 5;
   const int vx = t >> 6, vy = (t >> 3) & 7, vz = t & 7;
   const int C = m.C;
   unsigned long long n_updated = 0;
-  if (blockIdx.x == 0 && t == 0) m.ctrl->gather_ticket = 0;  // consumed by k_feature_gather_dyn (next launch)
+  if (blockIdx.x == 0 && t == 0) m.ctrl->gather_ticket[m.fp] = 0;  // consumed by this frame's k_feature_gather_dyn
   PROF_BEGIN(prof_seq_late(m.ctrl), kProfGeometry);
 
   // Zero-fill the feature blocks allocated by this frame (blox_impl.h:92-97), every CTA taking an equal
   // slice of each, so that a 794 KB block costs each SM a few KB; the gather kernel runs after us.
   if (block_begin == 0) {
-    const int n_new = m.ctrl->newfeat_count;
-    const int vec_per_block = (kVoxelsPerBlock * m.row) / 8;
+    // The weight vector of each row (the uint4 behind the C feature halves) is NOT touched here: the CTA that
+    // owns the block writes all 512 of them below, possibly before another CTA's slice of the fill gets there.
+    const int n_new = m.ctrl->newfeat_count[m.fp];
+    const int row_vecs_z = m.row >> 3, wvec = C >> 3;
+    const int vec_per_block = kVoxelsPerBlock * row_vecs_z;
     const int per_cta = (vec_per_block + gridDim.x - 1) / gridDim.x;
     const int k0 = blockIdx.x * per_cta, k1 = min(vec_per_block, k0 + per_cta);
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (int j = 0; j < n_new; ++j) {
       uint4* p = reinterpret_cast<uint4*>(feat_block(m, newfeat_slots[j]));
-      for (int k = k0 + t; k < k1; k += 512) p[k] = z;
+      for (int k = k0 + t; k < k1; k += 512)
+        if (k % row_vecs_z != wvec) p[k] = z;
     }
   }
 
@@ -1035,6 +1045,10 @@ __global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* _
       active = true;
     } while (false);
 
+    // The voxel's new weight (+ the zero padding of its row) is written HERE, not by the gather: the next frame's
+    // geometry reads it, and must not depend on a gather that may still be running on another stream.
+    if (active || is_new)
+      *(reinterpret_cast<uint4*>(blk + (size_t)t * m.row) + (C >> 3)) = make_uint4((unsigned)it.wnew, 0u, 0u, 0u);
     // block-level compaction: ballot + 16-entry scan, one atomicAdd per block on the global list
     const unsigned ballot = __ballot_sync(0xffffffffu, active);
     if (lane == 0) s_warp_base[warp + 1] = __popc(ballot);
@@ -1047,7 +1061,7 @@ __global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* _
         acc += s_warp_base[w];
         s_warp_base[w] = acc;
       }
-      s_base = acc ? atomicAdd(&m.ctrl->item_count, acc) : 0;
+      s_base = acc ? atomicAdd(&m.ctrl->item_count[m.fp], acc) : 0;
       n_updated += (unsigned long long)acc;
     }
     __syncthreads();
@@ -1059,8 +1073,9 @@ __global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* _
   if (t == 0) {
     if (n_updated) count_add(m, kCntFeatVoxelsUpdated, n_updated);
     if (blockIdx.x == 0 && block_begin == 0) {
-      count_add(m, kCntFeatBandBlocks, (unsigned long long)m.ctrl->band_count);
+      count_add(m, kCntFeatBandBlocks, (unsigned long long)m.ctrl->band_count[m.fp]);
       count_add(m, kCntFeatureFrames, 1);
+      m.ctrl->last_band_count = m.ctrl->band_count[m.fp];  // debug / parity hook (nvbx_debug_last_block_list)
     }
   }
   PROF_END(kProfGeometry);
@@ -1072,7 +1087,7 @@ __global__ void __launch_bounds__(256, CTAS) k_feature_gather(MapDev m, const Fe
                                                               FeatFrame f, int last_chunk) {
   pdl_prologue();
   PROF_BEGIN(prof_seq_late(m.ctrl), kProfGather);
-  const int n_items = m.ctrl->item_count;
+  const int n_items = m.ctrl->item_count[m.fp];
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1121,15 +1136,10 @@ __global__ void __launch_bounds__(256, CTAS) k_feature_gather(MapDev m, const Fe
                              a10[k], a11[k]);
         if (blend) o = blend_vec(old[k], o, w1, w2);
         dst[cvec[k]] = o;
-        if (cvec[k] == 0) dst[nvec] = make_uint4((unsigned)it[k].wnew, 0u, 0u, 0u);  // weight + zero padding
       }
     }
   }
-  if (last_chunk && blockIdx.x == 0 && threadIdx.x == 0) {
-    m.ctrl->last_band_count = m.ctrl->band_count;
-    m.ctrl->band_count = 0;  // ready for the next frame's band_select_tile
-    m.ctrl->newfeat_count = 0;
-  }
+  (void)last_chunk;
   PROF_END(kProfGather);
 }
 
@@ -1155,7 +1165,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_feature_gather_dyn(MapDev m, 
   FeatItem cur;  // speculative: issued together with the item_count load
   *reinterpret_cast<uint4*>(&cur) =
       __ldg(reinterpret_cast<const uint4*>(items + min(warp / ch_per_item, items_cap - 1)));
-  const int n_items = m.ctrl->item_count;
+  const int n_items = m.ctrl->item_count[m.fp];
   const long long n_units = (long long)n_items * ch_per_item;
   // dyn_permille < 0: CTA-blocked deal -- CTA c owns the contiguous units [c * n / G, (c + 1) * n / G), i.e. work
   // items of neighbouring voxels (the list is in block / voxel order), whose bilinear footprints overlap: the
@@ -1166,7 +1176,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_feature_gather_dyn(MapDev m, 
   const __half2 w1 = __half2half2(__ushort_as_half(f.h_w1));
   const __half2 w2 = __half2half2(__ushort_as_half(f.h_w2));
   const size_t row_vecs = (size_t)(m.row >> 3);
-  int* ticket = &m.ctrl->gather_ticket;
+  int* ticket = &m.ctrl->gather_ticket[m.fp];
 
   long long q = warp;
   long long stride = warps_total, end = n_static;
@@ -1229,16 +1239,11 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_feature_gather_dyn(MapDev m, 
       uint4 o = interp_vec(__half2half2(hx), __half2half2(hy), __half2half2(__hmul_rn(hx, hy)), a00, a01, a10, a11);
       if (blend) o = blend_vec(old, o, w1, w2);
       dst[cvec] = o;
-      if (cvec == 0) dst[nvec] = make_uint4((unsigned)cur.wnew, 0u, 0u, 0u);  // weight + zero padding
     }
     cur = nxt;
     q = qn;
   }
-  if (last_chunk && blockIdx.x == 0 && threadIdx.x == 0) {
-    m.ctrl->last_band_count = m.ctrl->band_count;
-    m.ctrl->band_count = 0;  // ready for the next frame's band_select_tile
-    m.ctrl->newfeat_count = 0;
-  }
+  (void)last_chunk;
   PROF_END(kProfGather);
 }
 
@@ -1296,7 +1301,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 1) k_feature_gather_tma(MapDev
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long warps_total = (long long)gridDim.x * kTmaWarps;
   const long long warp = (long long)blockIdx.x * kTmaWarps + wid;
-  const int n_items = m.ctrl->item_count;
+  const int n_items = m.ctrl->item_count[m.fp];
   const int nvec = m.C >> 3;
   const size_t row_vecs = (size_t)(m.row >> 3);
   const __half2 w1 = __half2half2(__ushort_as_half(f.h_w1));
@@ -1350,7 +1355,6 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 1) k_feature_gather_tma(MapDev
           if (blend) o = blend_vec(dst[v], o, w1, w2);
           dst[v] = o;
         }
-        if (lane == 0) dst[nvec] = make_uint4((unsigned)cur.wnew, 0u, 0u, 0u);  // weight + zero padding
         __syncwarp();  // every lane has read stage s: it may be overwritten
         issue(s, it[s]);
       }
@@ -1358,11 +1362,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 1) k_feature_gather_tma(MapDev
     }
     parity ^= 1u;
   }
-  if (last_chunk && blockIdx.x == 0 && threadIdx.x == 0) {
-    m.ctrl->last_band_count = m.ctrl->band_count;
-    m.ctrl->band_count = 0;  // ready for the next frame's band_select_tile
-    m.ctrl->newfeat_count = 0;
-  }
+  (void)last_chunk;
   PROF_END(kProfGather);
 }
 
@@ -1378,7 +1378,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 1) k_feature_gather_tma(MapDev
 __global__ void __launch_bounds__(256) k_pixel_mark(MapDev m, const FeatItem* __restrict__ items,
                                                     unsigned* __restrict__ bitmap, int cols) {
   pdl_prologue();
-  const int n = m.ctrl->item_count;
+  const int n = m.ctrl->item_count[m.fp];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int pix = __ldg(&items[i].pix);
 #pragma unroll
@@ -1638,9 +1638,9 @@ __global__ void __launch_bounds__(256) k_clear_all(MapDev m) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     Ctrl* c = m.ctrl;
     c->n_hash = 0;
-    c->band_count = 0;
-    c->newfeat_count = 0;
-    c->item_count = 0;
+    c->band_count[0] = c->band_count[1] = 0;
+    c->newfeat_count[0] = c->newfeat_count[1] = 0;
+    c->item_count[0] = c->item_count[1] = 0;
     c->slot_free_top = 0;
     c->slot_high = 0;
     c->feat_free_top = 0;

@@ -78,20 +78,24 @@ struct Ctrl {
   int rebuild;         // hash must be rebuilt (blocks were released)
   int view_count;      // length of the current TSDF view list
   int cand_count;      // length of the feature candidate list
-  int band_count;      // length of the feature band list
-  int newfeat_count;   // feature blocks allocated this frame (to be zero-filled)
+  // Per-feature-frame lists are counted in the half selected by MapDev::fp (the frame's parity): the producer of
+  // frame i appends to [fp], the half [fp ^ 1] is cleared by a kernel of frame i that runs after its last reader of
+  // frame i - 1 and before its next writer of frame i + 1 -- no kernel both reads and resets one counter, and the
+  // gather of frame i (which may run on its own stream, nvbx_set_pipelining) shares nothing with the kernels of
+  // frame i + 1.
+  int band_count[2];     // length of the feature band list (k_trace_and_band -> k_feature_geometry)
+  int newfeat_count[2];  // feature blocks allocated this frame (to be zero-filled by k_feature_geometry)
   int list_count;      // generic compaction counter (block index export)
   int mesh_total_v;    // totals of the mesh being built
   int mesh_total_t;
-  int item_count;      // length of the feature work-item list of the current chunk
+  int item_count[2];   // length of the feature work-item list of the current chunk (geometry -> gather)
   int last_band_count; // band_count of the last completed feature frame (debug / parity hook)
   int n_hash;          // blocks resident in the overflow hash (0: every block is in the workspace grid)
   int n_color;         // live colour blocks
   int cband_count[2];  // colour band list length, double-buffered by frame parity (the consumer of one frame
                        // clears the other half, so no kernel both reads and resets the same counter)
   int last_cband_count;
-  int gather_ticket;  // k_feature_gather_dyn's work ticket; zeroed by k_feature_geometry
-  int pad;
+  int gather_ticket[2];  // k_feature_gather_dyn's work ticket; zeroed by k_feature_geometry
   unsigned long long counters[kCntNum];
 };
 
@@ -129,6 +133,7 @@ struct MapDev {
   float voxel_size_inv;
   int C;    // feature channels
   int row;  // halves per feature voxel row (C + 8)
+  int fp;   // parity of the current feature frame: which half of the double-buffered Ctrl counters / item lists it uses
 };
 
 __device__ __forceinline__ float2* tsdf_block(const MapDev& m, int slot) {

@@ -164,7 +164,7 @@ template <int CH, int MODE, int CTAS>
 __global__ void __launch_bounds__(256, CTAS) k_feature_gather_up(MapDev m, const FeatItem* __restrict__ items,
                                                                  FeatFrame f, UpFrame uf, int last_chunk) {
   pdl_prologue();
-  const int n_items = m.ctrl->item_count;
+  const int n_items = m.ctrl->item_count[m.fp];
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -197,13 +197,8 @@ __global__ void __launch_bounds__(256, CTAS) k_feature_gather_up(MapDev m, const
     uint4 o = interp_vec(__half2half2(hx), __half2half2(hy), __half2half2(__hmul_rn(hx, hy)), a00, a01, a10, a11);
     if (blend) o = blend_vec(old, o, w1, w2);
     dst[cvec] = o;
-    if (cvec == 0) dst[nvec] = make_uint4((unsigned)it.wnew, 0u, 0u, 0u);  // weight + zero padding
   }
-  if (last_chunk && blockIdx.x == 0 && threadIdx.x == 0) {
-    m.ctrl->last_band_count = m.ctrl->band_count;
-    m.ctrl->band_count = 0;
-    m.ctrl->newfeat_count = 0;
-  }
+  (void)last_chunk;
 }
 
 // The whole [H, W, C] fp16 frame the chained path would have produced (parity checks, visualisation; not on

@@ -120,6 +120,8 @@ class Mapper:
         _capi.check(self._lib.nvbx_create(len(voxel_sizes), sizes, C.byref(nv), self._feature_channels, self._device,
                                           C.byref(handle)))
         self._handle = handle
+        self._pipelining = False
+        self._held_frames = {}    # mapper_id -> the last two feature frames (kept alive while pipelining)
 
     def __del__(self):
         h = getattr(self, '_handle', None)
@@ -199,6 +201,28 @@ class Mapper:
         _capi.check(self._lib.nvbx_integrate_features(
             self._handle, mapper_id, feature_frame.data_ptr(), feature_frame.shape[0], feature_frame.shape[1],
             feature_frame.shape[2], mask_ptr, _pose16(t_w_c), fx, fy, cx, cy, self._stream()))
+        if self._pipelining:
+            # the gather of this frame runs on the map's own stream and reads the frame until the second-next feature
+            # call has returned: keep the tensor alive so that the caching allocator cannot hand its memory out
+            held = self._held_frames.setdefault(mapper_id, [])
+            held.append(feature_frame)
+            del held[:-2]
+
+    def set_pipelining(self, on: bool = True) -> None:
+        """(ours) Overlap the memory-bound gather of feature frame i with the latency-bound depth path of frame i + 1
+        (include/nvbx_c_api.h: nvbx_set_pipelining).  Results are bit-identical.  While it is on, a feature frame must
+        not be overwritten IN PLACE until two more feature frames have been added to that map, or until a call that
+        reads the feature layer (decay / clear / mesh / block views / queries / `pipeline_join`); the frames
+        themselves are kept alive here.  Meant for replay / datagen loops that hold their frames."""
+        _capi.check(self._lib.nvbx_set_pipelining(self._handle, 1 if on else 0))
+        self._pipelining = bool(on)
+        if not on:
+            self._held_frames = {}
+
+    def pipeline_join(self, mapper_id: int = -1) -> None:
+        """(ours) Order torch's current stream behind every feature gather still in flight."""
+        _capi.check(self._lib.nvbx_pipeline_join(self._handle, mapper_id, self._stream()))
+        self._held_frames = {}
 
     def integrate_frame_from_host(self, depth, features, t_w_c, intrinsics, depth_mask=None, feature_mask=None,
                                   mapper_id: int = 0) -> None:

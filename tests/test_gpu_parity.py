@@ -409,3 +409,40 @@ def test_empty_and_degenerate_inputs():
     assert pair.check_tsdf() > 0 and pair.check_features(max_ulp=1) > 0 and pair.check_mesh() > 0
     pair.clear()
     assert pair.check_tsdf() == 0 and pair.check_mesh() == 0
+
+
+@pytest.mark.parametrize('alpha', [1.0, 0.8])
+def test_pipelined_frames_are_bit_identical(alpha):
+    """Frame pipelining (Mapper.set_pipelining: the gather of frame i on the map's own stream, the depth path of
+    frame i + 1 underneath it) changes nothing in the map: TSDF, features (alpha < 1 blends with what the previous
+    frames' gathers wrote), per-frame band lists, mesh, with decay / queries / block views joining in between."""
+    import torch
+    from nvblox_torch.mapper import QueryType
+    mp, op = make_params(workspace=S.WS_CUBE_STACKING, alpha=alpha, strict=True)
+    pair = Pair(0.02, 768, mp, op)
+    pair.gpu.set_pipelining(True)
+    H = W = 128
+    K = S.intrinsics(W, H)
+    frames = [S.feature_frame(H, W, 768, 900 + i) for i in range(3)]
+    for i in range(9):
+        T = S.orbit_pose(3 * i)
+        pair.depth(S.render_depth(K, H, W, T, **S.S_TABLE), T, K)
+        pair.features(frames[i % 3], T, K)
+        g, c = pair.last_block_list(1)
+        assert np.array_equal(g, c)
+        if i % 4 == 3:
+            pair.decay()                      # joins the gathers in flight before freeing blocks
+        if i == 5:                            # a feature query in the middle of the stream of frames
+            idx, _ = pair.cpu.all_blocks(1)
+            q = ((idx[:64].astype(np.float32) + 0.5) * np.float32(0.16)).astype(np.float32)
+            got = pair.gpu.query_layer(QueryType.FEATURE, torch.from_numpy(q).cuda(), mapper_id=0).cpu().numpy()
+            assert np.array_equal(got.view(np.uint16), pair.cpu.query_features(q).view(np.uint16))
+    assert pair.check_tsdf() > 0
+    assert pair.check_features(max_ulp=0) > 0
+    assert pair.check_mesh() > 0
+    # switching it off drains the gather stream; further frames keep matching
+    pair.gpu.set_pipelining(False)
+    T = S.orbit_pose(40)
+    pair.depth(S.render_depth(K, H, W, T, **S.S_TABLE), T, K)
+    pair.features(frames[0], T, K)
+    assert pair.check_features(max_ulp=0) > 0
