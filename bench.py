@@ -248,8 +248,38 @@ def run_ours(args, rank, world, local_rank):
             sweep_gather(args, lib, mapper, depths, poses, feats, K_t, step)
         return
 
+    def sequence_pass(seq):
+        """The same frames through Mapper.integrate_frames (one Python -> C crossing per `seq` frames)."""
+        idx = list(range(args.warmup, n_total))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        t0 = time.perf_counter()
+        for k in range(0, len(idx), seq):
+            ii = idx[k:k + seq]
+            mapper.integrate_frames([depths[i] for i in ii], [feats[i % N_FEATURE_BUFFERS] for i in ii],
+                                    [poses[i] for i in ii], K_t)
+        th = time.perf_counter() - t0
+        mapper.pipeline_join()
+        b.record()
+        torch.cuda.synchronize()
+        return {'frames_per_call': seq, 'frames_per_s': len(idx) / (a.elapsed_time(b) / 1000.0),
+                'ms_per_step': a.elapsed_time(b) / len(idx), 'host_enqueue_ms_per_step': 1000.0 * th / len(idx)}
+
     if args.quick:
         if rank == 0:
+            print(json.dumps({'sequence_api': [sequence_pass(q) for q in (1, 8, 32)]}), flush=True)
+            th = [0.0, 0.0]
+            for i in range(args.warmup, n_total):
+                t0 = time.perf_counter()
+                mapper.add_depth_frame(depths[i], poses[i], K_t)
+                t1 = time.perf_counter()
+                mapper.add_feature_frame(feats[i % N_FEATURE_BUFFERS], poses[i], K_t)
+                th[0] += t1 - t0
+                th[1] += time.perf_counter() - t1
+            torch.cuda.synchronize()
+            print(json.dumps({'host_us_depth_call': 1e6 * th[0] / args.steps, 'host_us_feature_call': 1e6 * th[1] / args.steps}),
+                  flush=True)
             kms = kernel_time_ms(args, mapper, depths, poses, feats, K_t)
             print(json.dumps({'per_kernel_us': per_kernel_us(args, mapper, depths, poses, feats, K_t)}), flush=True)
             print(json.dumps({'quick': True, 'value': value, 'ms_per_step': ms / args.steps, 'kernel_ms': kms,

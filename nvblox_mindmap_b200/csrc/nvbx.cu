@@ -201,16 +201,19 @@ struct Map {
   unsigned* small_grid[2] = {nullptr, nullptr};  // double-buffered bitmap of small views (2 x kFusedBitmapWords)
   int small_cur = 0;
   bool small_dirty = false;
-  DevBuf<int> view_slots, band_slots, newfeat_slots, cband_slots;
+  DevBuf<int> view_slots, cband_slots;
+  DevBuf<int> band_slots2[kFrameRing], newfeat_slots2[kFrameRing];  // per feature frame, ring slot MapDev::fp
   int color_parity = 0;
   bool have_cband_list = false;
-  DevBuf<FeatItem> items2[2];  // feature work-item lists, double-buffered by MapDev::fp
+  DevBuf<FeatItem> items2[kFrameRing];  // feature work-item lists, ring slot MapDev::fp
   // Frame pipelining (nvbx_set_pipelining): the gather of feature frame i runs on `gstream`, ordered after the
-  // frame's geometry kernel by `ev_geom`; `ev_gather[p]` marks the end of the last gather that used parity p.
+  // frame's geometry kernel by `ev_trace`; `ev_gather[r]` marks the end of the last gather that used ring slot r (and
+  // with it the last use of every buffer of that slot on `gstream`).
   cudaStream_t gstream = nullptr;
-  cudaEvent_t ev_geom = nullptr, ev_gather[2] = {nullptr, nullptr};
-  bool gather_pending[2] = {false, false};
-  DevBuf<float> synth;
+  cudaEvent_t ev_trace = nullptr, ev_gather[kFrameRing] = {};
+  bool gather_pending[kFrameRing] = {};
+  DevBuf<float> synth2[kFrameRing];  // synthetic depth images, ring slot MapDev::fp
+  int synth_last = 0;       // which of them the last appearance frame used (debug hook)
   int synth_rows = 0, synth_cols = 0;
   // The synthetic depth image is a pure function of (pose, camera, truncation, TSDF contents): the colour and
   // feature frames of one mindmap step share all four, so the second one skips the sphere tracing.
@@ -220,6 +223,7 @@ struct Map {
     float trunc = 0;
     int sub = 0;
     unsigned long long tsdf_version = 0;
+    int buf = 0;  // which synth2[] holds the image
     bool valid = false;
   } synth_key;
   unsigned long long tsdf_version = 1;  // bumped by everything that may change TSDF voxels or the block set
@@ -335,19 +339,20 @@ int grow_color_slabs(Map& mp, cudaStream_t stream) {
 // depth path of frame i + 1 (raycast, TSDF update, sphere tracing + band selection, geometry): those kernels are
 // latency-bound and touch nothing the memory-bound gather reads or writes (Ctrl counters and the item list are
 // double-buffered by MapDev::fp, voxel weights are written by the geometry kernel).
+int env_int(const char* name, int dflt);
 int pipeline_init(Map& mp) {
   if (mp.gstream) return NVBX_OK;
   int lo = 0, hi = 0;
   CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-  CUDA_TRY(cudaStreamCreateWithPriority(&mp.gstream, cudaStreamNonBlocking, lo));  // lowest: the short kernels go first
-  CUDA_TRY(cudaEventCreateWithFlags(&mp.ev_geom, cudaEventDisableTiming));
-  CUDA_TRY(cudaEventCreateWithFlags(&mp.ev_gather[0], cudaEventDisableTiming));
-  CUDA_TRY(cudaEventCreateWithFlags(&mp.ev_gather[1], cudaEventDisableTiming));
+  static const int prio = env_int("NVBX_PIPE_PRIO", 0);  // tuning knob: 0 lowest (the short kernels go first), 1 highest
+  CUDA_TRY(cudaStreamCreateWithPriority(&mp.gstream, cudaStreamNonBlocking, prio ? hi : lo));
+  CUDA_TRY(cudaEventCreateWithFlags(&mp.ev_trace, cudaEventDisableTiming));
+  for (int r = 0; r < kFrameRing; ++r) CUDA_TRY(cudaEventCreateWithFlags(&mp.ev_gather[r], cudaEventDisableTiming));
   return NVBX_OK;
 }
 // Order `stream` after every gather still in flight: called by whatever reads or frees feature blocks.
 int pipeline_join(Map& mp, cudaStream_t stream) {
-  for (int p = 0; p < 2; ++p)
+  for (int p = 0; p < kFrameRing; ++p)
     if (mp.gather_pending[p]) {
       CUDA_TRY(cudaStreamWaitEvent(stream, mp.ev_gather[p], 0));
       mp.gather_pending[p] = false;
@@ -356,8 +361,25 @@ int pipeline_join(Map& mp, cudaStream_t stream) {
 }
 // Host-side wait (before device memory the gather uses is re-allocated or freed).
 int pipeline_drain(Map& mp) {
-  if (mp.gstream && (mp.gather_pending[0] || mp.gather_pending[1])) CUDA_TRY(cudaStreamSynchronize(mp.gstream));
+  bool any = false;
+  for (int r = 0; r < kFrameRing; ++r) any |= mp.gather_pending[r];
+  if (mp.gstream && any) CUDA_TRY(cudaStreamSynchronize(mp.gstream));
   return NVBX_OK;
+}
+// The frame about to be enqueued re-uses ring slot mp.dev.fp (item list, band lists, synthetic depth image, their
+// counters): the gather that read them last -- kFrameRing feature frames ago -- must be COMPLETE, because nothing on
+// the caller's stream orders the new kernels behind it.  It practically always is (the ring is four frames deep);
+// when the gather stream really lags that far, the host waits here rather than the device.
+int pipeline_slot_ready(Map& mp) {
+  const int r = mp.dev.fp;
+  if (!mp.gather_pending[r]) return NVBX_OK;
+  const cudaError_t q = cudaEventQuery(mp.ev_gather[r]);
+  if (q == cudaErrorNotReady) {
+    CUDA_TRY(cudaEventSynchronize(mp.ev_gather[r]));
+  } else if (q != cudaSuccess) {
+    CUDA_TRY(q);
+  }
+  return NVBX_OK;  // gather_pending[r] stays set: a later join still has to order the CALLER'S stream behind it
 }
 
 int grow_slots(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
@@ -684,20 +706,20 @@ void destroy_map(Map& mp) {
   mp.small_grid[1] = nullptr;
   mp.grid.release();
   mp.view_slots.release();
-  mp.band_slots.release();
-  mp.newfeat_slots.release();
+  for (int b = 0; b < kFrameRing; ++b) {
+    mp.band_slots2[b].release();
+    mp.newfeat_slots2[b].release();
+    mp.synth2[b].release();
+  }
   mp.cband_slots.release();
-  mp.items2[0].release();
-  mp.items2[1].release();
+  for (int r = 0; r < kFrameRing; ++r) mp.items2[r].release();
   if (mp.gstream) {
     cudaStreamSynchronize(mp.gstream);
     cudaStreamDestroy(mp.gstream);
-    cudaEventDestroy(mp.ev_geom);
-    cudaEventDestroy(mp.ev_gather[0]);
-    cudaEventDestroy(mp.ev_gather[1]);
+    cudaEventDestroy(mp.ev_trace);
+    for (int r = 0; r < kFrameRing; ++r) cudaEventDestroy(mp.ev_gather[r]);
     mp.gstream = nullptr;
   }
-  mp.synth.release();
   mp.cnt_v.release();
   mp.cnt_t.release();
   mp.off_v.release();
@@ -770,7 +792,7 @@ int gather_ticket_units() {
 }
 
 template <int CH>
-int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, cudaStream_t stream) {
+int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, cudaStream_t stream, bool pipelined) {
   int rc;
   if ((rc = timing_begin(m, 0, stream))) return rc;
   switch (gather_variant()) {  // <CH, units in flight per warp, resident CTAs per SM>
@@ -809,10 +831,21 @@ int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, 
                (int)mp.items2[mp.dev.fp].cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
       }
       break;
-    case 7:  // the 48-register build on 4 CTAs / SM: leaves registers for two CTAs of the next frame's raycast
-      LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 4), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p,
+    case 7: {  // the 48-register build on 4 CTAs / SM: leaves registers for two CTAs of the next frame's raycast
+      static const int waves = std::max(1, env_int("NVBX_GATHER_WAVES", 1));  // tuning knob: grid = waves x resident CTAs
+      static const int pad = [] {  // tuning knob: dynamic shared memory per CTA (caps the resident CTAs per SM)
+        const int v = std::max(0, env_int("NVBX_GATHER_SMEM_PAD", 0));
+        if (v > 48 * 1024)
+          cudaFuncSetAttribute(k_feature_gather_dyn<CH, 256, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, v);
+        return v;
+      }();
+      // On its own stream (frame pipelining) the gather runs on THREE CTAs per SM: the 28 k registers it leaves free
+      // hold one CTA of any kernel of the next frame's depth path (k_tsdf_update and k_trace_and_band need 20 k),
+      // which is what lets those kernels run underneath it (25.7 k vs 24.2 k frames/s with four; r02 sweep).
+      LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, pipelined ? 3 : 4) * waves, 256, pad, stream, mp.dev, mp.items2[mp.dev.fp].p,
              (int)mp.items2[mp.dev.fp].cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
       break;
+    }
     case 8:
       LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, 3), 256, 0, stream, mp.dev, mp.items2[mp.dev.fp].p,
              (int)mp.items2[mp.dev.fp].cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
@@ -1132,6 +1165,7 @@ struct AppearancePrep {
   Cam cam;
   int srows = 0, scols = 0, sub = 0;
   long long cand_bound = 0;
+  const float* synth = nullptr;  // the frame's synthetic depth image (freshly traced or re-used)
 };
 
 // color_parity < 0: feature frame (band list -> mp.band_slots / ctrl->band_count, feature slots allocated);
@@ -1198,18 +1232,18 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
       return NVBX_OK;
     };
     if ((rc = ensure_feats(m, mp, cand_bound, stream, count_new))) return rc;
-    if ((rc = mp.band_slots.ensure((size_t)cand_bound, stream))) return rc;
-    if ((rc = mp.newfeat_slots.ensure((size_t)cand_bound, stream))) return rc;
+    if ((rc = mp.band_slots2[mp.dev.fp].ensure((size_t)cand_bound, stream))) return rc;
+    if ((rc = mp.newfeat_slots2[mp.dev.fp].ensure((size_t)cand_bound, stream))) return rc;
     const long long chunk_blocks = std::min<long long>(cand_bound, kFeatureChunkBlocks);
     if ((rc = mp.items2[mp.dev.fp].ensure((size_t)chunk_blocks * kVoxelsPerBlock, stream))) return rc;
-    band_list = mp.band_slots.p;
+    band_list = mp.band_slots2[mp.dev.fp].p;
   } else {
     if ((rc = enable_color(mp, stream))) return rc;
     if ((rc = mp.cband_slots.ensure((size_t)cand_bound, stream))) return rc;
     band_list = mp.cband_slots.p;
   }
   const int srows = height / sub, scols = width / sub;
-  if ((rc = mp.synth.ensure((size_t)srows * scols, stream))) return rc;
+  if ((rc = mp.synth2[mp.dev.fp].ensure((size_t)srows * scols, stream))) return rc;
   out->srows = srows;
   out->scols = scols;
   out->sub = height / srows;  // projective_integrator_impl.cuh:424-425
@@ -1224,11 +1258,15 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
   tp.sub = sub;
   tp.rows = srows;
   tp.cols = scols;
+  tp.free_dist = p.truncation_distance_vox * mp.voxel_size;  // == DepthFrame::trunc of nvbx_integrate_depth
+  static const int use_free = env_int("NVBX_TRACE_FREE", 1);
+  tp.use_free = use_free;
   // synthetic depth already rendered for exactly this pose / camera / TSDF state (the other appearance frame of
   // the same step): skip the sphere tracing, keep the band selection
   Map::SynthKey& key = mp.synth_key;
+  // (a traced image goes to synth2[fp]; the callers made sure that ring slot is free -- pipeline_slot_ready)
   const bool reuse = key.valid && key.tsdf_version == mp.tsdf_version && key.trunc == trunc && key.sub == sub &&
-                     mp.synth_rows == srows && mp.synth_cols == scols &&
+                     mp.synth_rows == srows && mp.synth_cols == scols && mp.synth2[key.buf].p != nullptr &&
                      std::memcmp(&key.T, &T_L_C, sizeof(Pose)) == 0 && std::memcmp(&key.cam, &cam, sizeof(Cam)) == 0;
   mp.synth_rows = srows;
   mp.synth_cols = scols;
@@ -1243,8 +1281,8 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
     key.valid = false;  // a failed launch leaves no valid image behind
     static const int spec = env_int("NVBX_TRACE_SPEC", 1), ilp = env_int("NVBX_BAND_ILP", 2);
 #define NVBX_TB(S, I)                                                                                                \
-  LAUNCH((k_trace_and_band<S, I>), n_trace + n_band, 256, 0, stream, mp.dev, tp, mp.synth.p, trace_tiles_x, n_trace, \
-         pv, trunc, band_list, mp.newfeat_slots.p, tile_cells, n_tiles, color_parity)
+  LAUNCH((k_trace_and_band<S, I>), n_trace + n_band, 256, 0, stream, mp.dev, tp, mp.synth2[mp.dev.fp].p, trace_tiles_x, \
+         n_trace, pv, trunc, band_list, mp.newfeat_slots2[mp.dev.fp].p, tile_cells, n_tiles, color_parity)
     if (spec == 1 && ilp == 1) {
       NVBX_TB(1, 1);
     } else if (spec == 1) {
@@ -1264,8 +1302,11 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
     key.trunc = trunc;
     key.sub = sub;
     key.tsdf_version = mp.tsdf_version;
+    if (!reuse) key.buf = mp.dev.fp;
     key.valid = true;
   }
+  mp.synth_last = key.buf;
+  out->synth = mp.synth2[key.buf].p;
   return NVBX_OK;
 }
 
@@ -1321,15 +1362,13 @@ int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, co
   cudaStream_t stream = (cudaStream_t)stream_v;
   Map& mp = *m->maps[map_id];
   mp.have_band_list = false;
-  // This frame re-uses the item list and the counters of parity fp: the gather that read them last (frame i - 2,
-  // if it ran on the gather stream) must be done before the frame's first kernel.  A frame that cannot be pipelined
-  // (host-resident / low-res feature sources) runs its gather on the caller's stream, behind every gather in flight.
+  // A frame that cannot be pipelined (host-resident / low-res feature sources) runs its gather on the caller's
+  // stream, behind every gather in flight; a pipelined one only needs its ring slot to be free (pipeline_slot_ready).
   bool pipe = m->pipelining && !hf && !uf && features != nullptr;
   if (!pipe) {
     if ((rc = pipeline_join(mp, stream))) return rc;
-  } else if (mp.gather_pending[mp.dev.fp]) {
-    CUDA_TRY(cudaStreamWaitEvent(stream, mp.ev_gather[mp.dev.fp], 0));
-    mp.gather_pending[mp.dev.fp] = false;
+  } else if ((rc = pipeline_slot_ready(mp))) {
+    return rc;
   }
   AppearancePrep prep;
   if ((rc = appearance_prepare(m, mp, mp.planes_cache, height, width, T_L_C_rm, fx, fy, cx, cy, -1, stream, &prep)))
@@ -1345,7 +1384,7 @@ int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, co
   FeatFrame ff;
   ff.img = (const __half*)features;
   ff.mask = (const uint8_t*)mask;
-  ff.synth = mp.synth.p;
+  ff.synth = prep.synth;
   ff.rows = height;
   ff.cols = width;
   ff.srows = srows;
@@ -1378,8 +1417,13 @@ int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, co
     const int last = end >= cand_bound ? 1 : 0;
     if (begin > 0) CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->item_count[mp.dev.fp], 0, sizeof(int), stream));
     const int ggrid = persistent_grid(m, 2);  // full grid: new feature blocks are zero-filled by all CTAs
-    LAUNCH(k_feature_geometry, ggrid, 512, 0, stream, mp.dev, mp.band_slots.p, mp.newfeat_slots.p, ff, mp.items2[mp.dev.fp].p,
-           (int)begin, (int)end);
+    static const bool geom_on_gs = env_int("NVBX_PIPE_GEOM", 0) != 0;  // tuning knob: geometry on the gather stream (measured slower)
+    if (pipe && geom_on_gs) {  // geometry + gather of this frame on the map's own stream, behind its trace / band select
+      CUDA_TRY(cudaEventRecord(mp.ev_trace, stream));
+      CUDA_TRY(cudaStreamWaitEvent(gs, mp.ev_trace, 0));
+    }
+    LAUNCH(k_feature_geometry, ggrid, 512, 0, (pipe && !geom_on_gs) ? stream : gs, mp.dev, mp.band_slots2[mp.dev.fp].p, mp.newfeat_slots2[mp.dev.fp].p, ff,
+           mp.items2[mp.dev.fp].p, (int)begin, (int)end);
     const int ch = (m->C % 256 == 0 && m->C / 256 >= 1 && m->C / 256 <= 4) ? m->C / 256 : 0;
     if (hf) {
       const int nvec = m->C / 8;
@@ -1401,20 +1445,20 @@ int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, co
       else
         rc = launch_gather_up<0>(m, mp, ff, *uf, up_mode, last, stream);
     } else {
-      if (pipe) {
-        CUDA_TRY(cudaEventRecord(mp.ev_geom, stream));
-        CUDA_TRY(cudaStreamWaitEvent(gs, mp.ev_geom, 0));
+      if (pipe && !geom_on_gs) {
+        CUDA_TRY(cudaEventRecord(mp.ev_trace, stream));
+        CUDA_TRY(cudaStreamWaitEvent(gs, mp.ev_trace, 0));
       }
       if (ch == 3)
-        rc = launch_gather<3>(m, mp, ff, last, gs);
+        rc = launch_gather<3>(m, mp, ff, last, gs, pipe);
       else if (ch == 4)
-        rc = launch_gather<4>(m, mp, ff, last, gs);
+        rc = launch_gather<4>(m, mp, ff, last, gs, pipe);
       else if (ch == 2)
-        rc = launch_gather<2>(m, mp, ff, last, gs);
+        rc = launch_gather<2>(m, mp, ff, last, gs, pipe);
       else if (ch == 1)
-        rc = launch_gather<1>(m, mp, ff, last, gs);
+        rc = launch_gather<1>(m, mp, ff, last, gs, pipe);
       else
-        rc = launch_gather<0>(m, mp, ff, last, gs);
+        rc = launch_gather<0>(m, mp, ff, last, gs, pipe);
       if (pipe && !rc) {
         CUDA_TRY(cudaEventRecord(mp.ev_gather[mp.dev.fp], gs));
         mp.gather_pending[mp.dev.fp] = true;
@@ -1423,7 +1467,7 @@ int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, co
     if (rc) return rc;
   }
   mp.have_band_list = true;
-  mp.dev.fp ^= 1;  // the next feature frame uses the other half of the double-buffered lists
+  mp.dev.fp = (mp.dev.fp + 1) % kFrameRing;  // the next feature frame uses the next ring slot
   return NVBX_OK;
 }
 
@@ -1492,6 +1536,7 @@ int nvbx_integrate_color(nvbx_mapper* m, int map_id, const void* rgb, int height
   Map& mp = *m->maps[map_id];
   mp.have_cband_list = false;
   const int parity = mp.color_parity;
+  if ((rc = pipeline_slot_ready(mp))) return rc;  // a traced synthetic depth image goes to synth2[fp]
   AppearancePrep prep;
   if ((rc = appearance_prepare(m, mp, mp.planes_cache, height, width, T_L_C_rm, fx, fy, cx, cy, parity, stream,
                                &prep)))
@@ -1500,7 +1545,7 @@ int nvbx_integrate_color(nvbx_mapper* m, int map_id, const void* rgb, int height
   ColorFrame cf;
   cf.img = (const uint8_t*)rgb;
   cf.mask = (const uint8_t*)mask;
-  cf.synth = mp.synth.p;
+  cf.synth = prep.synth;
   cf.rows = height;
   cf.cols = width;
   cf.srows = prep.srows;
@@ -1952,7 +1997,10 @@ int64_t nvbx_get_all_blocks(nvbx_mapper* m, int map_id, int layer, int32_t* out_
   if (voxel_stride_elems)
     *voxel_stride_elems = layer == NVBX_LAYER_TSDF ? 2 : (layer == NVBX_LAYER_COLOR ? 8 : mp.dev.row);
   if (layer == NVBX_LAYER_COLOR && !mp.color_enabled) return 0;
-  if (layer == NVBX_LAYER_TSDF && out_ptrs) ++mp.tsdf_version;  // the caller may write through the returned views
+  if (layer == NVBX_LAYER_TSDF && out_ptrs) {  // the caller may write through the returned views
+    ++mp.tsdf_version;
+    LAUNCH(k_clear_free_bits, persistent_grid(m, 2), 256, 0, stream, mp.dev);
+  }
   if (layer == NVBX_LAYER_FEATURE && out_ptrs && (rc = pipeline_join(mp, stream))) return rc;
   if ((rc = mp.idx_out.ensure((size_t)mp.slot_capacity, stream))) return rc;
   if ((rc = mp.ptr_out.ensure((size_t)mp.slot_capacity, stream))) return rc;
@@ -2001,7 +2049,10 @@ int nvbx_get_block_ptr(nvbx_mapper* m, int map_id, int layer, int x, int y, int 
   Map& mp = *m->maps[map_id];
   cudaStream_t stream = (cudaStream_t)stream_v;
   if (layer == NVBX_LAYER_COLOR && !mp.color_enabled) return fail(NVBX_ERR_NOT_FOUND, "block (%d, %d, %d) is not allocated", x, y, z);
-  if (layer == NVBX_LAYER_TSDF) ++mp.tsdf_version;  // the caller may write through the returned view
+  if (layer == NVBX_LAYER_TSDF) {  // the caller may write through the returned view
+    ++mp.tsdf_version;
+    LAUNCH(k_clear_free_bits, persistent_grid(m, 2), 256, 0, stream, mp.dev);
+  }
   if (layer == NVBX_LAYER_FEATURE && (rc = pipeline_join(mp, stream))) return rc;
   LAUNCH(k_find_one, 1, 1, 0, stream, mp.dev, x, y, z, layer, mp.d_tmp_ptr);
   unsigned long long h = 0;
@@ -2065,6 +2116,7 @@ int nvbx_get_counters(nvbx_mapper* m, int map_id, nvbx_counters* out, void* stre
   if (rc) return rc;
   if (!out) return fail(NVBX_ERR_INVALID_ARGUMENT, "out is null");
   Map& mp = *m->maps[map_id];
+  if ((rc = pipeline_join(mp, (cudaStream_t)stream_v))) return rc;  // the geometry kernel counts on the gather stream
   if ((rc = read_ctrl(mp, (cudaStream_t)stream_v))) return rc;
   const unsigned long long* c = mp.h_ctrl->counters;
   std::memset(out, 0, sizeof(*out));
@@ -2092,6 +2144,7 @@ int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream_v) {
   int rc = check_map(m, map_id);
   if (rc) return rc;
   Map& mp = *m->maps[map_id];
+  if ((rc = pipeline_join(mp, (cudaStream_t)stream_v))) return rc;
   CUDA_TRY(cudaMemsetAsync(mp.d_ctrl->counters, 0, sizeof(unsigned long long) * kCntNum, (cudaStream_t)stream_v));
   return NVBX_OK;
 }
@@ -2289,11 +2342,12 @@ int64_t nvbx_debug_last_block_list(nvbx_mapper* m, int map_id, int which, int32_
     return n;
   }
   if (which == 2 ? !mp.have_cband_list : !mp.have_band_list) return 0;
+  if ((rc = pipeline_join(mp, stream))) return rc;  // the geometry kernel (gather stream) records last_band_count
   if ((rc = read_ctrl(mp, stream))) return rc;
   const int n = which == 2 ? mp.h_ctrl->last_cband_count : mp.h_ctrl->last_band_count;
   if (out_xyz && capacity > 0 && n > 0) {
     std::vector<int> slots((size_t)n);
-    CUDA_TRY(cudaMemcpyAsync(slots.data(), which == 2 ? mp.cband_slots.p : mp.band_slots.p, (size_t)n * sizeof(int),
+    CUDA_TRY(cudaMemcpyAsync(slots.data(), which == 2 ? mp.cband_slots.p : mp.band_slots2[(mp.dev.fp + kFrameRing - 1) % kFrameRing].p, (size_t)n * sizeof(int),
                              cudaMemcpyDeviceToHost, stream));
     std::vector<int3> all((size_t)mp.slot_capacity);
     CUDA_TRY(cudaMemcpyAsync(all.data(), mp.dev.blk_index, all.size() * sizeof(int3), cudaMemcpyDeviceToHost, stream));
@@ -2332,7 +2386,7 @@ int nvbx_debug_last_synthetic_depth(nvbx_mapper* m, int map_id, const void** ptr
   int rc = check_map(m, map_id);
   if (rc) return rc;
   Map& mp = *m->maps[map_id];
-  if (ptr) *ptr = mp.synth.p;
+  if (ptr) *ptr = mp.synth2[mp.synth_last].p;
   if (rows) *rows = mp.synth_rows;
   if (cols) *cols = mp.synth_cols;
   return NVBX_OK;

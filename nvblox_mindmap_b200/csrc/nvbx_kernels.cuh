@@ -319,9 +319,10 @@ __device__ __forceinline__ bool project_voxel(const Cam& cam, const Pose& T_C_L,
   return true;
 }
 
-// One voxel of one block (thread t of the CTA); returns 1 if the voxel was fused with a measurement.
+// One voxel of one block (thread t of the CTA); returns 1 if the voxel was fused with a measurement.  *is_free: the
+// voxel was written by this frame and now holds (+truncation distance, weight > 1e-4) -- observed free space.
 __device__ __forceinline__ unsigned tsdf_update_voxel(const MapDev& m, const DepthFrame& f, int slot, bool is_new,
-                                                      int t) {
+                                                      int t, bool* is_free) {
   const int vx = t >> 6, vy = (t >> 3) & 7, vz = t & 7;
   const int3 b = m.blk_index[slot];
   float2* vox = tsdf_block(m, slot) + t;
@@ -359,7 +360,16 @@ __device__ __forceinline__ unsigned tsdf_update_voxel(const MapDev& m, const Dep
     updated = 1;
   } while (false);
   if (write) *vox = out;
+  *is_free = write && out.x == f.trunc && out.y > 1e-4f;
   return updated;
+}
+// All 512 voxels free -> kBlockFreeBit of the slot (one barrier; every thread of the CTA calls this).
+__device__ __forceinline__ void publish_block_free(const MapDev& m, int slot, bool voxel_free) {
+  const int all = __syncthreads_and(voxel_free);
+  if (threadIdx.x == 0) {
+    const uint8_t l = m.blk_layers[slot];
+    m.blk_layers[slot] = all ? (l | kBlockFreeBit) : (l & (uint8_t)~kBlockFreeBit);
+  }
 }
 
 // Where the list of blocks to update comes from.
@@ -400,7 +410,9 @@ __global__ void __launch_bounds__(512, 3) k_tsdf_update(MapDev m, ViewSource src
       if (raw < 0) continue;
       const int slot = raw & kSlotMask;
       if (t == 0) m.blk_dirty[slot] = kDirtyAll;  // blocks_to_update_tracker_.addBlocksToUpdate (mapper.cpp:406)
-      updated += tsdf_update_voxel(m, f, slot, (raw & kNewFlag) != 0, t);
+      bool vfree;
+      updated += tsdf_update_voxel(m, f, slot, (raw & kNewFlag) != 0, t, &vfree);
+      publish_block_free(m, slot, vfree);
     }
   } else {
     unsigned w0 = 0u, w1 = 0u;
@@ -473,7 +485,11 @@ __global__ void __launch_bounds__(512, 3) k_tsdf_update(MapDev m, ViewSource src
       }
       __syncthreads();
       const int raw = s_slot;
-      if (raw >= 0) updated += tsdf_update_voxel(m, f, raw & kSlotMask, (raw & kNewFlag) != 0, t);
+      if (raw >= 0) {  // uniform per CTA
+        bool vfree;
+        updated += tsdf_update_voxel(m, f, raw & kSlotMask, (raw & kNewFlag) != 0, t, &vfree);
+        publish_block_free(m, raw & kSlotMask, vfree);
+      }
       __syncthreads();  // s_slot is rewritten by the next rank
     }
   }
@@ -653,6 +669,8 @@ struct TraceParams {
   float eps;
   int sub;
   int rows, cols;  // synthetic image size
+  float free_dist;  // the TSDF truncation distance: what every voxel of a kBlockFreeBit block holds
+  int use_free;     // tuning knob (NVBX_TRACE_FREE): consult kBlockFreeBit
 };
 
 // floor(p / block_size) exactly as block_index_from_position computes it, without the IEEE division on
@@ -695,6 +713,7 @@ __device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TracePara
   struct Loc {
     const float2* addr;
     bool gone;
+    bool free;  // the sample lies in a block of observed free space: its value is (free_dist, valid), no load needed
   };
   auto locate = [&](float tt) -> Loc {
     V3 p;
@@ -715,8 +734,13 @@ __device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TracePara
     int slot = -1;
     Loc l;
     l.gone = false;
+    l.free = false;
     if (cell >= 0) {
       slot = s_ws ? s_ws[cell] : m.ws_slot[cell];
+      if (s_ws && slot >= 0) {  // staged table: bit 30 = the block is observed free space (kBlockFreeBit)
+        l.free = (slot & kNewFlag) != 0;
+        slot &= kSlotMask;
+      }
     } else if (!closed_world) {
       slot = hash_find(m, b.x, b.y, b.z);
     } else {
@@ -755,7 +779,8 @@ __device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TracePara
 #pragma unroll
     for (int j = 0; j < kSpec; ++j) loc[j] = locate(tk[j]);
 #pragma unroll
-    for (int j = 0; j < kSpec; ++j) val[j] = loc[j].addr ? *loc[j].addr : make_float2(0.0f, 0.0f);
+    for (int j = 0; j < kSpec; ++j)
+      val[j] = loc[j].free ? make_float2(tp.free_dist, 1.0f) : (loc[j].addr ? *loc[j].addr : make_float2(0.0f, 0.0f));
 #pragma unroll
     for (int k = 0; k < kSpec; ++k) {
       Loc cur = loc[k];
@@ -834,20 +859,19 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
   const long long t0 = clock64();
 #endif
   PROF_BEGIN(prof_seq_early(m.ctrl), kProfTrace);
-  if (blockIdx.x == 0 && threadIdx.x == 0 && color_parity == -1) {
-    // This frame's item list (last read by the gather of frame i - 2, which the host ordered before this launch)
-    // and the OTHER half of the band counters (last read by the geometry of frame i - 1, written next by frame i + 1).
-    m.ctrl->item_count[m.fp] = 0;
-    m.ctrl->band_count[m.fp ^ 1] = 0;
-    m.ctrl->newfeat_count[m.fp ^ 1] = 0;
-  }
+  // this ring slot's item list: last read by the gather of frame i - kFrameRing, complete before we were enqueued
+  if (blockIdx.x == 0 && threadIdx.x == 0 && color_parity == -1) m.ctrl->item_count[m.fp] = 0;
   // n_trace_ctas == 0: the synthetic depth image of this pose / camera / TSDF state is already in `image`
   if ((int)blockIdx.x < n_trace_ctas) {
     const int c = (blockIdx.x % trace_tiles_x) * 16 + (threadIdx.x & 7) + ((threadIdx.x >> 7) << 3);
     const int r = (blockIdx.x / trace_tiles_x) * 16 + ((threadIdx.x >> 3) & 15);
     const bool stage_ws = m.ws_cells > 0 && m.ws_cells <= kTraceSmemCells;
     if (stage_ws) {
-      for (int i = threadIdx.x; i < m.ws_cells; i += 256) s_ws[i] = m.ws_slot[i];
+      for (int i = threadIdx.x; i < m.ws_cells; i += 256) {
+        int s = m.ws_slot[i];
+        if (tp.use_free && s >= 0 && (m.blk_layers[s] & kBlockFreeBit)) s |= kNewFlag;  // bit 30: observed free space
+        s_ws[i] = s;
+      }
       __syncthreads();
     }
     [[maybe_unused]] int n_steps = 0;
@@ -1139,7 +1163,12 @@ __global__ void __launch_bounds__(256, CTAS) k_feature_gather(MapDev m, const Fe
       }
     }
   }
-  (void)last_chunk;
+  if (last_chunk && blockIdx.x == 0 && threadIdx.x == 0) {
+    // The band list of this frame was consumed by its geometry kernel (complete: we run behind it); the next writer
+    // of this ring slot's counters is the band selection of frame i + kFrameRing, enqueued only after this gather.
+    m.ctrl->band_count[m.fp] = 0;
+    m.ctrl->newfeat_count[m.fp] = 0;
+  }
   PROF_END(kProfGather);
 }
 
@@ -1243,7 +1272,12 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_feature_gather_dyn(MapDev m, 
     cur = nxt;
     q = qn;
   }
-  (void)last_chunk;
+  if (last_chunk && blockIdx.x == 0 && threadIdx.x == 0) {
+    // The band list of this frame was consumed by its geometry kernel (complete: we run behind it); the next writer
+    // of this ring slot's counters is the band selection of frame i + kFrameRing, enqueued only after this gather.
+    m.ctrl->band_count[m.fp] = 0;
+    m.ctrl->newfeat_count[m.fp] = 0;
+  }
   PROF_END(kProfGather);
 }
 
@@ -1362,7 +1396,12 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 1) k_feature_gather_tma(MapDev
     }
     parity ^= 1u;
   }
-  (void)last_chunk;
+  if (last_chunk && blockIdx.x == 0 && threadIdx.x == 0) {
+    // The band list of this frame was consumed by its geometry kernel (complete: we run behind it); the next writer
+    // of this ring slot's counters is the band selection of frame i + kFrameRing, enqueued only after this gather.
+    m.ctrl->band_count[m.fp] = 0;
+    m.ctrl->newfeat_count[m.fp] = 0;
+  }
   PROF_END(kProfGather);
 }
 
@@ -1573,6 +1612,9 @@ __global__ void __launch_bounds__(256) k_decay(MapDev m, DecayParams dp) {
     if (touched) *p = q;
     const bool decayed = (q.y < hi) && (q.w < hi);
     const int all = __syncthreads_and(decayed);
+    // a decay that may change distances, or push weights to the sphere tracer's validity threshold (1e-4), voids
+    // what kBlockFreeBit asserts; the default decay (floor 1e-3, distances untouched) does not
+    if (threadIdx.x == 0 && (dp.set_free || dp.threshold <= 1e-4f)) m.blk_layers[slot] = layers & (uint8_t)~kBlockFreeBit;
     if (threadIdx.x == 0) {
       if (all && dp.deallocate) {
         // release everything hanging off this block index
@@ -1638,9 +1680,7 @@ __global__ void __launch_bounds__(256) k_clear_all(MapDev m) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     Ctrl* c = m.ctrl;
     c->n_hash = 0;
-    c->band_count[0] = c->band_count[1] = 0;
-    c->newfeat_count[0] = c->newfeat_count[1] = 0;
-    c->item_count[0] = c->item_count[1] = 0;
+    for (int r = 0; r < kFrameRing; ++r) c->band_count[r] = c->newfeat_count[r] = c->item_count[r] = 0;
     c->slot_free_top = 0;
     c->slot_high = 0;
     c->feat_free_top = 0;
@@ -1659,6 +1699,17 @@ __global__ void __launch_bounds__(256) k_clear_all(MapDev m) {
 // ================================================================================================
 // a13. Layer views and point queries.
 // ================================================================================================
+// A TSDF block view is about to be handed to the caller, who may write through it: no block is known to be free
+// space any more (kBlockFreeBit).
+__global__ void __launch_bounds__(256) k_clear_free_bits(MapDev m) {
+  pdl_prologue();
+  const int n = m.ctrl->slot_high;
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    const uint8_t l = m.blk_layers[s];
+    if (l & kBlockFreeBit) m.blk_layers[s] = l & (uint8_t)~kBlockFreeBit;
+  }
+}
+
 // getAllBlocks / getAllBlockIndices (py_layer.cpp:177-198) in one pass: slot id, block index AND payload pointer of
 // every block of a layer (the host orders the result by slot id).
 __global__ void __launch_bounds__(256) k_collect_blocks(MapDev m, int layer, int3* out_idx, unsigned long long* out_ptr,

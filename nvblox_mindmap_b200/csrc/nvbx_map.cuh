@@ -26,6 +26,7 @@
 namespace nvbx {
 
 constexpr int kVoxelsPerBlock = 512;
+constexpr int kFrameRing = 4;  // feature frames whose per-frame lists may be alive at once (frame pipelining)
 constexpr int kTsdfSlabShift = 10;  // 1024 blocks  (4 MiB) per TSDF slab
 constexpr int kFeatSlabShift = 4;   // 16 blocks (12.1 MiB at C=768) per feature slab
 constexpr int kMaxSlabs = 1 << 15;
@@ -34,6 +35,11 @@ constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr uint8_t kLayerTsdfBit = 1;
 constexpr uint8_t kLayerFeatBit = 2;
 constexpr uint8_t kLayerColorBit = 4;
+// Not a layer: "every one of this block's 512 TSDF voxels holds distance == +truncation distance with a weight above
+// the sphere tracer's validity threshold", i.e. the block is observed free space.  Set / cleared by k_tsdf_update for
+// the blocks it updates, cleared by whatever else may change TSDF voxels; lets the sphere tracer step through such a
+// block without reading it (the value it would read is known exactly).
+constexpr uint8_t kBlockFreeBit = 8;
 // blk_dirty bits: one "to update" set per mesh layer (BlocksToUpdateTracker, blocks_to_update_tracker.cpp:32-60:
 // every addBlocksToUpdate feeds all consumer sets, every consumer clears only its own)
 constexpr uint8_t kDirtyFeatMesh = 1;
@@ -78,24 +84,26 @@ struct Ctrl {
   int rebuild;         // hash must be rebuilt (blocks were released)
   int view_count;      // length of the current TSDF view list
   int cand_count;      // length of the feature candidate list
-  // Per-feature-frame lists are counted in the half selected by MapDev::fp (the frame's parity): the producer of
-  // frame i appends to [fp], the half [fp ^ 1] is cleared by a kernel of frame i that runs after its last reader of
-  // frame i - 1 and before its next writer of frame i + 1 -- no kernel both reads and resets one counter, and the
-  // gather of frame i (which may run on its own stream, nvbx_set_pipelining) shares nothing with the kernels of
-  // frame i + 1.
-  int band_count[2];     // length of the feature band list (k_trace_and_band -> k_feature_geometry)
-  int newfeat_count[2];  // feature blocks allocated this frame (to be zero-filled by k_feature_geometry)
+  // Per-feature-frame lists live in the ring slot MapDev::fp = (feature frame number) mod kFrameRing.  Frame i
+  // appends its band list to band_count[fp] (band selection), its geometry kernel reads it and fills item_count[fp]
+  // items, its gather consumes them and clears the band counters; item_count[fp] is cleared by the band-selection
+  // kernel of the NEXT frame that uses the slot (frame i + kFrameRing).  Before the host enqueues that frame it makes
+  // sure -- with an event query, in practice always already satisfied -- that the gather of frame i is complete, so
+  // the kernels of frame i that run on the map's gather stream (nvbx_set_pipelining) share no list with the kernels of
+  // the following frames, and no wait is ever inserted between two kernels of the caller's stream.
+  int band_count[kFrameRing];     // length of the feature band list (k_trace_and_band -> k_feature_geometry)
+  int newfeat_count[kFrameRing];  // feature blocks allocated this frame (to be zero-filled by k_feature_geometry)
   int list_count;      // generic compaction counter (block index export)
   int mesh_total_v;    // totals of the mesh being built
   int mesh_total_t;
-  int item_count[2];   // length of the feature work-item list of the current chunk (geometry -> gather)
+  int item_count[kFrameRing];   // length of the feature work-item list of the current chunk (geometry -> gather)
   int last_band_count; // band_count of the last completed feature frame (debug / parity hook)
   int n_hash;          // blocks resident in the overflow hash (0: every block is in the workspace grid)
   int n_color;         // live colour blocks
   int cband_count[2];  // colour band list length, double-buffered by frame parity (the consumer of one frame
                        // clears the other half, so no kernel both reads and resets the same counter)
   int last_cband_count;
-  int gather_ticket[2];  // k_feature_gather_dyn's work ticket; zeroed by k_feature_geometry
+  int gather_ticket[kFrameRing];  // k_feature_gather_dyn's work ticket; zeroed by k_feature_geometry
   unsigned long long counters[kCntNum];
 };
 
@@ -133,7 +141,8 @@ struct MapDev {
   float voxel_size_inv;
   int C;    // feature channels
   int row;  // halves per feature voxel row (C + 8)
-  int fp;   // parity of the current feature frame: which half of the double-buffered Ctrl counters / item lists it uses
+  int fp;   // ring slot of the current feature frame (frame number mod kFrameRing): which copy of the per-frame Ctrl
+            // counters / lists it uses
 };
 
 __device__ __forceinline__ float2* tsdf_block(const MapDev& m, int slot) {

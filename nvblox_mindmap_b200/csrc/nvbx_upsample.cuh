@@ -198,7 +198,10 @@ __global__ void __launch_bounds__(256, CTAS) k_feature_gather_up(MapDev m, const
     if (blend) o = blend_vec(old, o, w1, w2);
     dst[cvec] = o;
   }
-  (void)last_chunk;
+  if (last_chunk && blockIdx.x == 0 && threadIdx.x == 0) {
+    m.ctrl->band_count[m.fp] = 0;
+    m.ctrl->newfeat_count[m.fp] = 0;
+  }
 }
 
 // The whole [H, W, C] fp16 frame the chained path would have produced (parity checks, visualisation; not on

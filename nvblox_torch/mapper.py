@@ -208,6 +208,49 @@ class Mapper:
             held.append(feature_frame)
             del held[:-2]
 
+    def integrate_frames(self, depth_frames, feature_frames, poses, intrinsics, mapper_id: int = 0,
+                         depth_masks=None, feature_masks=None) -> None:
+        """(ours) A SEQUENCE of frames of one map in one call: frame k = add_depth_frame(depth_frames[k], ...) followed
+        by add_feature_frame(feature_frames[k], ...) (feature_frames[k] may be None), in order, with one crossing of
+        the Python / C boundary for the whole sequence (nvbx_integrate_frames_batch).  For replay / datagen loops
+        whose frames are already resident; the map is identical to the one the per-frame calls build.
+        `poses`: list of CPU [4,4] tensors; `intrinsics`: one CPU [3,3] tensor or a list."""
+        from nvblox_mindmap_b200.params import NvbxFrameJob
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        n = len(depth_frames)
+        assert len(feature_frames) == n and len(poses) == n
+        jobs = (NvbxFrameJob * n)()
+        stream = self._stream()
+        keep = []
+        for k in range(n):
+            d, f, T = depth_frames[k], feature_frames[k], poses[k]
+            K = intrinsics if isinstance(intrinsics, torch.Tensor) else intrinsics[k]
+            check_integrator_inputs(d, T, K, 'Depth', 2, torch.float32)
+            d = d if d.is_contiguous() else d.contiguous()
+            j = jobs[k]
+            j.mapper, j.map_id, j.stream = self._handle.value, mapper_id, stream
+            j.height, j.width = int(d.shape[0]), int(d.shape[1])
+            j.depth = d.data_ptr()
+            dm = None if depth_masks is None else depth_masks[k]
+            j.depth_mask = self._mask_ptr(dm, d)
+            if f is not None:
+                check_integrator_inputs(f, T, K, 'Feature', 3, torch.float16, self._feature_channels)
+                assert f.shape[0] == d.shape[0] and f.shape[1] == d.shape[1], 'Feature frame size should match the depth frame.'
+                f = f if f.is_contiguous() else f.contiguous()
+                j.channels = int(f.shape[2])
+                j.features = f.data_ptr()
+                fm = None if feature_masks is None else feature_masks[k]
+                j.feature_mask = self._mask_ptr(fm, f)
+            Tc = T if T.is_contiguous() else T.contiguous()
+            C.memmove(j.T_L_C, Tc.data_ptr(), 64)
+            j.fx, j.fy, j.cx, j.cy = _fxfycxcy(K)
+            keep.append((d, f, dm, Tc))
+        _capi.check(self._lib.nvbx_integrate_frames_batch(jobs, n, 1))
+        if self._pipelining:
+            held = self._held_frames.setdefault(mapper_id, [])
+            held.extend(t[1] for t in keep if t[1] is not None)
+            del held[:-2]
+
     def set_pipelining(self, on: bool = True) -> None:
         """(ours) Overlap the memory-bound gather of feature frame i with the latency-bound depth path of frame i + 1
         (include/nvbx_c_api.h: nvbx_set_pipelining).  Results are bit-identical.  While it is on, a feature frame must

@@ -119,7 +119,8 @@ def test_get_all_blocks_single_pass():
         before = int(L.nvbx_kernel_launch_count())
         blocks, indices = view.get_all_blocks()
         launches = int(L.nvbx_kernel_launch_count()) - before
-        assert launches <= 2, f'get_all_blocks launched {launches} kernels for {len(blocks)} blocks'
+        # count pass + (TSDF views only: clear of the free-space flags) + collect pass, independent of the block count
+        assert launches <= 3, f'get_all_blocks launched {launches} kernels for {len(blocks)} blocks'
         ci, cd = pair.cpu.all_blocks(layer_id)
         got = np.stack([i.numpy() for i in indices])
         order = np.lexsort((got[:, 2], got[:, 1], got[:, 0]))

@@ -29,6 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--frames', type=int, default=48)
     ap.add_argument('--out', default=None)
+    ap.add_argument('--pipelining', type=int, default=1)
     args = ap.parse_args()
     import torch
     import bench
@@ -39,6 +40,7 @@ def main():
     constants.set_feature_array_num_elements(bench.C_FEAT)
     mp, _ = bench.mapper_params()
     mapper = Mapper(voxel_sizes_m=bench.VOXEL, mapper_parameters=mp, device=0)
+    mapper.set_pipelining(bool(args.pipelining))
     n_warm = 16
     n = n_warm + args.frames
     assert args.frames <= 56
@@ -65,6 +67,7 @@ def main():
     for i in range(n_warm, n):
         step(i)
     host_us = 1e6 * (time.perf_counter() - t0) / args.frames
+    mapper.pipeline_join()
     _capi.check(lib.nvbx_debug_profile_stamps(mapper._handle, buf, 0))
     st = np.frombuffer(buf, dtype=np.uint64).reshape(64, 8, 2).astype(np.float64)
 
