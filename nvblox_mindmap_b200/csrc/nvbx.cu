@@ -1261,6 +1261,11 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
   tp.free_dist = p.truncation_distance_vox * mp.voxel_size;  // == DepthFrame::trunc of nvbx_integrate_depth
   static const int use_free = env_int("NVBX_TRACE_FREE", 1);
   tp.use_free = use_free;
+  // Team march (eight lanes per ray, sphere_trace_team): bit-identical, measured 14.9 vs 16.1 us alone but SLOWER under
+  // the gather of the previous frame (42.1 vs 39.3 us per frame): the long rays spend their steps next to the surface,
+  // where every step depends on the value just read, so the extra lanes only add work.  Kept selectable.
+  static const int team = env_int("NVBX_TRACE_TEAM", 0);
+  tp.team = team;
   // synthetic depth already rendered for exactly this pose / camera / TSDF state (the other appearance frame of
   // the same step): skip the sphere tracing, keep the band selection
   Map::SynthKey& key = mp.synth_key;
@@ -1275,8 +1280,9 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
     int tile_cells = 32;
     while (tile_cells < 256 && (entry->bound + tile_cells - 1) / tile_cells > 2 * m->sm_count) tile_cells <<= 1;
     const int n_tiles = (entry->bound + tile_cells - 1) / tile_cells;
-    const int trace_tiles_x = (scols + 15) / 16;
-    const int n_trace = reuse ? 0 : trace_tiles_x * ((srows + 15) / 16);
+    // trace CTAs: 8 x 4 rays with eight lanes per ray (team march), or 16 x 16 rays with one thread per ray
+    const int trace_tiles_x = tp.team ? (scols + 7) / 8 : (scols + 15) / 16;
+    const int n_trace = reuse ? 0 : trace_tiles_x * (tp.team ? (srows + 3) / 4 : (srows + 15) / 16);
     const int n_band = std::max(1, std::min(n_tiles, persistent_grid(m, 4)));
     key.valid = false;  // a failed launch leaves no valid image behind
     static const int spec = env_int("NVBX_TRACE_SPEC", 1), ilp = env_int("NVBX_BAND_ILP", 2);

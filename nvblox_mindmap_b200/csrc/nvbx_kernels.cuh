@@ -671,6 +671,7 @@ struct TraceParams {
   int rows, cols;  // synthetic image size
   float free_dist;  // the TSDF truncation distance: what every voxel of a kBlockFreeBit block holds
   int use_free;     // tuning knob (NVBX_TRACE_FREE): consult kBlockFreeBit
+  int team;         // 1: eight lanes per ray (sphere_trace_team), trace CTAs cover 8 x 4 rays; 0: one thread per ray
 };
 
 // floor(p / block_size) exactly as block_index_from_position computes it, without the IEEE division on
@@ -843,6 +844,149 @@ __device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TracePara
   return n_steps;
 }
 
+// ---- team march: G lanes share one ray ---------------------------------------------------------------------
+// The scalar march above is a chain of <= ~24 dependent (address arithmetic + L2 round trip) steps per ray, and the
+// slowest rays set the kernel's duration.  Here a team of G lanes works on ONE ray: in every round lane j samples
+// the position the march WOULD reach after j more steps of the last step length (t_j = t + guess + ... + guess,
+// the same sequence of float additions the scalar march performs when its steps stay equal), all G loads fly at
+// once, and the samples are then consumed in order for as long as the true position equals the sampled one BIT FOR
+// BIT -- i.e. for as long as every consumed step really had the predicted length.  Through unobserved space (step =
+// truncation distance) and observed free space (step = the clamped TSDF value) that is G steps per round trip; next
+// to the surface, where the steps shrink, it degenerates to the scalar march.  The sequence of (t, value) pairs, the
+// termination rule and the result are exactly the scalar march's (and the reference's, sphere_tracer.cu:31-131).
+template <int G>
+__device__ __forceinline__ void sphere_trace_team(const MapDev& m, const TraceParams& tp, int r, int c, bool in_image,
+                                                  float* __restrict__ image, const int* s_ws) {
+  const int tl = threadIdx.x & (G - 1);  // lane within the team
+  const float pu = (float)(c * tp.sub) + 0.5f * (float)tp.sub * 1.0f;
+  const float pv = (float)(r * tp.sub) + 0.5f * (float)tp.sub * 1.0f;
+  const V3 ray = ray_from_image_plane(tp.cam, pu, pv);
+  const float sq = fmaf(ray.x, ray.x, fmaf(ray.y, ray.y, ray.z * ray.z));
+  V3 dc = ray;
+  if (sq > 0.0f) {
+    const float nrm = sqrtf(sq);
+    dc.x = ray.x / nrm;
+    dc.y = ray.y / nrm;
+    dc.z = ray.z / nrm;
+  }
+  const V3 dl = dev_rotate(tp.T_L_C, dc);
+  const float ox = tp.T_L_C.t[0], oy = tp.T_L_C.t[1], oz = tp.T_L_C.t[2];
+  const bool closed_world = (m.ws_sx > 0) && (m.ctrl->n_hash == 0);
+  const I3 ws_mx = {m.ws_mn.x + m.ws_sx - 1, m.ws_mn.y + m.ws_sy - 1, m.ws_mn.z + m.ws_sz - 1};
+  const float bs = m.block_size, bs_inv = 1.0f / m.block_size;
+  float2* const slab0 = m.tsdf_slabs[0];
+
+  int first = 0, i = 0;
+  float t = 0.0f, guess = tp.trunc;
+  bool ok = false;
+  bool run = in_image && (i < tp.max_steps) && (t < tp.max_ray_length);
+  while (__any_sync(0xffffffffu, run)) {
+    // this lane's speculative sample position: t advanced by tl steps of the predicted length
+    float tj = t;
+#pragma unroll
+    for (int k = 0; k < G - 1; ++k)
+      if (k < tl) tj += guess;
+    // flags: 1 = has a voxel address, 2 = ray has left a closed world for good, 4 = block of observed free space
+    int flags = 0;
+    float2 val = make_float2(0.0f, 0.0f);
+    if (run && (i + tl < tp.max_steps) && (tj < tp.max_ray_length)) {
+      V3 p;
+      p.x = fmaf(tj, dl.x, ox);
+      p.y = fmaf(tj, dl.y, oy);
+      p.z = fmaf(tj, dl.z, oz);
+      I3 b, v;
+      b.x = floor_div_exact(p.x, bs, bs_inv);
+      b.y = floor_div_exact(p.y, bs, bs_inv);
+      b.z = floor_div_exact(p.z, bs, bs_inv);
+      v.x = min((int)(fmaf(-(float)b.x, bs, p.x) * m.voxel_size_inv), 7);
+      v.y = min((int)(fmaf(-(float)b.y, bs, p.y) * m.voxel_size_inv), 7);
+      v.z = min((int)(fmaf(-(float)b.z, bs, p.z) * m.voxel_size_inv), 7);
+      const int cell = ws_cell(m, b.x, b.y, b.z);
+      int slot = -1;
+      if (cell >= 0) {
+        slot = s_ws ? s_ws[cell] : m.ws_slot[cell];
+        if (s_ws && slot >= 0) {
+          if (slot & kNewFlag) flags |= 4;
+          slot &= kSlotMask;
+        }
+      } else if (!closed_world) {
+        slot = hash_find(m, b.x, b.y, b.z);
+      } else if ((b.x > ws_mx.x && dl.x >= 0.0f) || (b.x < m.ws_mn.x && dl.x <= 0.0f) ||
+                 (b.y > ws_mx.y && dl.y >= 0.0f) || (b.y < m.ws_mn.y && dl.y <= 0.0f) ||
+                 (b.z > ws_mx.z && dl.z >= 0.0f) || (b.z < m.ws_mn.z && dl.z <= 0.0f)) {
+        flags |= 2;
+      }
+      if (slot >= 0) {
+        flags |= 1;
+        if (flags & 4) {
+          val = make_float2(tp.free_dist, 1.0f);
+        } else {
+          const float2* addr =
+              ((slot < (1 << kTsdfSlabShift)) ? slab0 + (size_t)slot * kVoxelsPerBlock : tsdf_block(m, slot)) +
+              ((v.x * 8 + v.y) * 8 + v.z);
+          val = *addr;
+        }
+      }
+    }
+    // consume the samples in order (every lane of the team replays the same state machine)
+    bool open = run;           // samples of this round may still be consumed
+    float next_guess = guess;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const float tj_b = __shfl_sync(0xffffffffu, tj, j, G);
+      const float vx_b = __shfl_sync(0xffffffffu, val.x, j, G);
+      const float vy_b = __shfl_sync(0xffffffffu, val.y, j, G);
+      const int fl_b = __shfl_sync(0xffffffffu, flags, j, G);
+      if (open) {
+        if (__float_as_int(tj_b) != __float_as_int(t)) {
+          open = false;        // an earlier step was not of the predicted length: lanes >= j sampled elsewhere
+        } else if (!((i < tp.max_steps) && (t < tp.max_ray_length))) {
+          open = run = false;  // ran out of steps or length: fail
+        } else if (fl_b & 2) {
+          open = run = false;  // miss
+        } else {
+          const bool valid = (fl_b & 1) && (vy_b > 1e-4f);
+          float step = 0.0f;
+          if (!valid) {
+            if (first == 0) {
+              step = tp.trunc;
+            } else {
+              open = run = false;  // left observed space: fail
+            }
+          } else {
+            if (first == 0) first = (vx_b >= 0.0f) ? 1 : -1;
+            if (first == 1) {
+              if (vx_b < tp.eps) {
+                t += vx_b;
+                ok = true;
+                open = run = false;
+              } else {
+                step = vx_b;
+              }
+            } else {
+              if (vx_b > -tp.eps) {
+                t -= vx_b;
+                ok = true;
+                open = run = false;
+              } else {
+                step = -vx_b;
+              }
+            }
+          }
+          if (open) {
+            t += step;
+            ++i;
+            next_guess = step;
+          }
+        }
+      }
+    }
+    guess = next_guess;
+    if (run && !((i < tp.max_steps) && (t < tp.max_ray_length))) run = false;
+  }
+  if (in_image && tl == 0) image[(size_t)r * tp.cols + c] = ok ? t * dc.z : -1.0f;
+}
+
 // The two independent, latency-bound preparations of a feature frame in ONE launch: CTAs
 // [0, n_trace_ctas) sphere-trace 16x16 tiles of the synthetic depth image, the remaining CTAs run
 // band_select_tile.  Both only read the TSDF layer; they overlap instead of queueing.
@@ -873,6 +1017,14 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
         s_ws[i] = s;
       }
       __syncthreads();
+    }
+    if (tp.team) {  // 32 rays (8 x 4) per CTA, eight lanes per ray
+      const int ray = threadIdx.x >> 3;
+      const int tc = (blockIdx.x % trace_tiles_x) * 8 + (ray & 7);
+      const int tr = (blockIdx.x / trace_tiles_x) * 4 + (ray >> 3);
+      sphere_trace_team<8>(m, tp, tr, tc, tr < tp.rows && tc < tp.cols, image, stage_ws ? s_ws : nullptr);
+      PROF_END(kProfTrace);
+      return;
     }
     [[maybe_unused]] int n_steps = 0;
     if (r < tp.rows && c < tp.cols) n_steps = sphere_trace_ray<SPEC>(m, tp, r, c, image, stage_ws ? s_ws : nullptr);

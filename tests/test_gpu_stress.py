@@ -144,9 +144,10 @@ def test_stress_two_million_tsdf_blocks():
     lo = np.floor(np.asarray(WS_STRESS[0], np.float32) / bs)
     hi = np.floor(np.asarray(WS_STRESS[1], np.float32) / bs)
     assert (idx >= lo).all() and (idx <= hi).all()
-    # free space: 1 .. 4 m in front of the first populate camera, at (-5, -5, 1.5) looking along +x, above the floor
+    # free space: 2 .. 4 m in front of the first populate camera, at (-5, -5, 1.5) looking along +x (vertical field
+    # of view +-45 deg: z in [-0.5, 3.5] there), above the floor
     rng = np.random.default_rng(0)
-    q = np.stack([-5.0 + 1.0 + 3.0 * rng.random(4096), -5.0 + (rng.random(4096) - 0.5), 2.0 + rng.random(4096)], 1)
+    q = np.stack([-5.0 + 2.0 + 2.0 * rng.random(4096), -5.0 + (rng.random(4096) - 0.5), 2.0 + rng.random(4096)], 1)
     got = m.query_layer(QueryType.TSDF, torch.from_numpy(q.astype(np.float32)).cuda(), mapper_id=0).cpu().numpy()
     trunc = np.float32(4.0) * np.float32(0.01)
     assert (got[:, 1] > 0).mean() > 0.99 and np.all(got[got[:, 1] > 0, 0] == trunc)
