@@ -400,6 +400,16 @@ def run_ours(args, rank, world, local_rank):
         fused = fused_upsample_stage(sub, mapper, depths, poses, K_t, dev)
         mapper.set_pipelining(False)
         kms_alone = kernel_time_ms(args, mapper, depths, poses, feats, K_t)   # the same kernel with nothing beside it
+        # the same frames without frame pipelining (what a caller that frees / overwrites its frames right away gets)
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_np = min(args.steps, 256)
+        torch.cuda.synchronize()
+        ea.record()
+        for i in range(args.warmup, args.warmup + n_np):
+            step(i)
+        eb.record()
+        torch.cuda.synchronize()
+        value_no_pipe = n_np / (ea.elapsed_time(eb) / 1e3)
         mapper.set_pipelining(bool(args.pipelining))
         batched = batched_maps_stage(depths, poses, feats, K_t, local_rank)
         drill = drill_in_box_stage(lib, feats, h_feat, local_rank, peak)
@@ -455,7 +465,12 @@ def run_ours(args, rank, world, local_rank):
                       'per_kernel_us_in_pipeline': per_kernel, 'export_stage': export,
                       'fused_upsample': fused, 'batched_maps_one_gpu': batched, 'drill_in_box': drill,
                       'batched_64_maps': batched64, 'stress': stress, 'cold_start': cold,
-                      'pipelining': bool(args.pipelining),
+                      'pipelining': {'on': bool(args.pipelining),
+                                     'frames_per_s_without': value_no_pipe,
+                                     'note': 'value is measured with Mapper.set_pipelining(True): every frame of the '
+                                             'replay stays resident, so the gather of frame i may run under the depth '
+                                             'path of frame i + 1 (bit-identical map); frames_per_s_without is the '
+                                             'default mode of the drop-in (frames may be freed right after the call)'},
                       'counters_per_step': {k: v / args.steps for k, v in counters.items()
                                             if isinstance(v, (int, float))}},
         }
@@ -561,6 +576,21 @@ def drill_in_box_stage(lib, feats, h_feat, local_rank, peak):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     n_upd = mapper.counters(0)['feature_voxels_updated'] / (2 * n_timed)
+    # the same steps with frame pipelining (frames resident: the gather of one camera frame under the depth path of
+    # the next)
+    mapper.set_pipelining(True)
+    for i in range(n_warm, n_warm + 4):
+        step(i)
+    mapper.pipeline_join()
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(n_warm, n_warm + n_timed):
+        step(i)
+    mapper.pipeline_join()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_pipe = e0.elapsed_time(e1)
+    mapper.set_pipelining(False)
     lib.nvbx_set_kernel_timing(mapper._handle, 1)
     for i in range(n_warm, n_warm + n_timed):
         step(i)
@@ -575,7 +605,8 @@ def drill_in_box_stage(lib, feats, h_feat, local_rank, peak):
     b = 2 * C_FEAT * px + 2 * (C_FEAT + 1) * n_upd
     gbs = b / (kms * 1e-3) / 1e9 if kms else None
     return {'workload': 'drill_in_box: head (static) + wrist cam 512x512, C=768, 1 cm voxels', 'frames_per_s':
-            2 * n_timed / (ms / 1e3), 'ms_per_camera_frame': ms / (2 * n_timed), 'n_upd_per_frame': n_upd,
+            2 * n_timed / (ms / 1e3), 'ms_per_camera_frame': ms / (2 * n_timed),
+            'frames_per_s_pipelined': 2 * n_timed / (ms_pipe / 1e3), 'n_upd_per_frame': n_upd,
             'distinct_pixels_per_frame': px, 'gather_kernel_ms': kms, 'gather_algorithmic_bytes': b,
             'gather_GBps': gbs, 'gather_frac_of_measured_peak': (gbs / peak) if gbs else None,
             'feature_blocks': mapper.feature_layer_view(0).num_blocks(),
@@ -815,8 +846,8 @@ def cold_start_stage(depths, poses, feats, K_t, local_rank, n=8):
 
 def ncu_traffic_bytes():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary
-    (profiles/r01l_feature_gather.md: dram__bytes_read.sum + dram__bytes_write.sum, first capture)."""
-    path = os.path.join(ROOT, 'profiles', 'r01l_feature_gather.md')
+    (profiles/r02p_feature_gather.md: dram__bytes_read.sum + dram__bytes_write.sum, first capture)."""
+    path = os.path.join(ROOT, 'profiles', 'r02p_feature_gather.md')
     try:
         rd = wr = None
         for line in open(path):
@@ -826,7 +857,7 @@ def ncu_traffic_bytes():
             if len(cells) > 3 and cells[1] == 'dram__bytes_write.sum' and wr is None:
                 wr = float(cells[2]) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}[cells[3]]
         if rd is not None and wr is not None:
-            return rd + wr, 'profiles/r01l_feature_gather.md (ncu --set full, one launch of the same workload)'
+            return rd + wr, 'profiles/r02p_feature_gather.md (ncu --set full, one launch of the same workload)'
     except Exception:
         pass
     return None, None

@@ -60,18 +60,29 @@ struct LaunchRec {
   const char* name;
   cudaEvent_t a, b;
 };
-int g_timing_mode = 0;
+std::atomic<int> g_timing_mode{0};
+std::mutex g_launch_recs_mu;  // launches may come from the batch entry's worker threads
 std::vector<LaunchRec> g_launch_recs;
+thread_local long long t_last_rec = -1;  // index of the record this thread opened last
 inline void launch_rec_begin(const char* name, cudaStream_t stream) {
-  if (g_timing_mode < 2) return;
+  t_last_rec = -1;
+  if (g_timing_mode.load(std::memory_order_relaxed) < 2) return;
   LaunchRec r{name, nullptr, nullptr};
   if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
   cudaEventRecord(r.a, stream);
+  std::lock_guard<std::mutex> g(g_launch_recs_mu);
+  t_last_rec = (long long)g_launch_recs.size();
   g_launch_recs.push_back(r);
 }
 inline void launch_rec_end(cudaStream_t stream) {
-  if (g_timing_mode < 2 || g_launch_recs.empty()) return;
-  cudaEventRecord(g_launch_recs.back().b, stream);
+  if (t_last_rec < 0) return;
+  cudaEvent_t b = nullptr;
+  {
+    std::lock_guard<std::mutex> g(g_launch_recs_mu);
+    if (t_last_rec < (long long)g_launch_recs.size()) b = g_launch_recs[(size_t)t_last_rec].b;
+  }
+  if (b) cudaEventRecord(b, stream);
+  t_last_rec = -1;
 }
 
 // All kernels are launched with programmatic stream serialization (see pdl_prologue() in
@@ -183,6 +194,8 @@ struct Map {
   // slot table + hash (contiguous, re-allocated on growth)
   int slot_capacity = 0;
   int feat_capacity = 0;
+  long long stray_ub = 0;      // blocks requested OUTSIDE the workspace grid (allocate_block_at_index, load_from_file):
+                               // they live in the overflow hash and are not bounded by the workspace's cell count
   long long slot_used_ub = 0;  // host upper bounds of live ids (pessimistic between syncs)
   long long feat_used_ub = 0;
   std::vector<void*> tsdf_slabs, feat_slabs, color_slabs;
@@ -411,8 +424,11 @@ int grow_slots(nvbx_mapper* m, Map& mp, int new_cap, cudaStream_t stream) {
   // hash: next pow2 >= 4 * capacity
   unsigned hcap = 1024;
   while (hcap < 4u * (unsigned)new_cap) hcap <<= 1;
-  if (mp.dev.ws_cells > 0 && hcap > (1u << 16) && mp.slot_capacity <= mp.dev.ws_cells)
-    hcap = mp.dev.hash_mask ? mp.dev.hash_mask + 1 : (1u << 16);  // grid-indexed map: the hash only holds strays
+  if (mp.dev.ws_cells > 0) {  // grid-indexed map: the hash only holds strays -- sized from their number, load <= 0.25
+    hcap = 1u << 16;
+    while ((long long)hcap < 4 * mp.stray_ub) hcap <<= 1;
+    if (mp.dev.hash_mask && mp.dev.hash_mask + 1 > hcap) hcap = mp.dev.hash_mask + 1;  // never shrinks
+  }
   if (hcap != mp.dev.hash_mask + 1 || mp.dev.keys == nullptr) {
     if (mp.dev.keys) cudaFree(mp.dev.keys);
     if (mp.dev.vals) cudaFree(mp.dev.vals);
@@ -481,7 +497,8 @@ long long workspace_cells(const nvbx_mapper* m, const Map& mp) {
 // Make sure `need` more block indices can be allocated by the next kernel without the host knowing
 // how many really will be (see DESIGN.md "Arena sizing without read-backs").
 int ensure_slots(nvbx_mapper* m, Map& mp, long long need, cudaStream_t stream) {
-  const long long ws = workspace_cells(m, mp);
+  const long long ws0 = workspace_cells(m, mp);
+  const long long ws = ws0 >= 0 ? ws0 + mp.stray_ub : ws0;  // strays outside the box are extra
   auto bound = [&](long long v) { return ws >= 0 ? std::min(v, ws) : v; };
   if (bound(mp.slot_used_ub + need) <= mp.slot_capacity) {
     mp.slot_used_ub = bound(mp.slot_used_ub + need);
@@ -833,6 +850,7 @@ int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, 
       break;
     case 7: {  // the 48-register build on 4 CTAs / SM: leaves registers for two CTAs of the next frame's raycast
       static const int waves = std::max(1, env_int("NVBX_GATHER_WAVES", 1));  // tuning knob: grid = waves x resident CTAs
+      static const int pipe_ctas = std::min(4, std::max(1, env_int("NVBX_PIPE_GATHER_CTAS", 3)));  // tuning knob
       static const int pad = [] {  // tuning knob: dynamic shared memory per CTA (caps the resident CTAs per SM)
         const int v = std::max(0, env_int("NVBX_GATHER_SMEM_PAD", 0));
         if (v > 48 * 1024)
@@ -842,7 +860,7 @@ int launch_gather(nvbx_mapper* m, Map& mp, const FeatFrame& ff, int last_chunk, 
       // On its own stream (frame pipelining) the gather runs on THREE CTAs per SM: the 28 k registers it leaves free
       // hold one CTA of any kernel of the next frame's depth path (k_tsdf_update and k_trace_and_band need 20 k),
       // which is what lets those kernels run underneath it (25.7 k vs 24.2 k frames/s with four; r02 sweep).
-      LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, pipelined ? 3 : 4) * waves, 256, pad, stream, mp.dev, mp.items2[mp.dev.fp].p,
+      LAUNCH((k_feature_gather_dyn<CH, 256, 5>), persistent_grid(m, pipelined ? pipe_ctas : 4) * waves, 256, pad, stream, mp.dev, mp.items2[mp.dev.fp].p,
              (int)mp.items2[mp.dev.fp].cap, ff, last_chunk, gather_dyn_permille(), gather_ticket_units());
       break;
     }
@@ -1584,7 +1602,8 @@ int nvbx_integrate_frame_host(nvbx_mapper* m, int map_id, const float* depth_hos
                               float cy, void* stream_v) {
   int rc = check_map(m, map_id);
   if (rc) return rc;
-  if (!depth_host || !features_host) return fail(NVBX_ERR_INVALID_ARGUMENT, "null host frame");
+  if (!depth_host || !features_host || !T_L_C || height <= 0 || width <= 0)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "bad host frame (null buffer / pose or non-positive size)");
   cudaStream_t stream = (cudaStream_t)stream_v;
   Map& mp = *m->maps[map_id];
   const size_t px = (size_t)height * width;
@@ -1671,8 +1690,9 @@ int nvbx_integrate_frame_host_lowres(nvbx_mapper* m, int map_id, const float* de
                                      const float* T_L_C, float fx, float fy, float cx, float cy, void* stream_v) {
   int rc = check_map(m, map_id);
   if (rc) return rc;
-  if (!depth_host || !lowres_host || low_h <= 0 || low_w <= 0 || low_c <= 0 || dtype < 0 || dtype > 2)
-    return fail(NVBX_ERR_INVALID_ARGUMENT, "bad host frame");
+  if (!depth_host || !lowres_host || !T_L_C || low_h <= 0 || low_w <= 0 || low_c <= 0 || dtype < 0 || dtype > 2 ||
+      height <= 0 || width <= 0)
+    return fail(NVBX_ERR_INVALID_ARGUMENT, "bad host frame (null buffer / pose, bad dtype or non-positive size)");
   cudaStream_t stream = (cudaStream_t)stream_v;
   Map& mp = *m->maps[map_id];
   const size_t px = (size_t)height * width;
@@ -1751,6 +1771,7 @@ int nvbx_clear(nvbx_mapper* m, int map_id, void* stream_v) {
   LAUNCH(k_clear_all, persistent_grid(m, 4), 256, 0, stream, mp.dev);
   mp.slot_used_ub = 0;
   mp.feat_used_ub = 0;
+  mp.stray_ub = 0;
   mp.mesh_nv = 0;
   mp.mesh_nt = 0;
   mp.cmesh_nv = 0;
@@ -2078,6 +2099,17 @@ int nvbx_allocate_block(nvbx_mapper* m, int map_id, int layer, int x, int y, int
   Map& mp = *m->maps[map_id];
   cudaStream_t stream = (cudaStream_t)stream_v;
   if ((rc = pipeline_join(mp, stream))) return rc;
+  if (mp.dev.ws_cells > 0) {  // an index outside the workspace grid goes to the overflow hash: count it, keep the
+                              // table's load below 0.25 (re-hash through grow_slots when it would not be)
+    const I3 mn = mp.dev.ws_mn;
+    const bool inside = x >= mn.x && x < mn.x + mp.dev.ws_sx && y >= mn.y && y < mn.y + mp.dev.ws_sy && z >= mn.z &&
+                        z < mn.z + mp.dev.ws_sz;
+    if (!inside) {
+      ++mp.stray_ub;
+      if (4 * mp.stray_ub > (long long)mp.dev.hash_mask + 1 && mp.slot_capacity > 0)
+        if ((rc = grow_slots(m, mp, mp.slot_capacity, stream))) return rc;
+    }
+  }
   if ((rc = ensure_slots(m, mp, 1, stream))) return rc;
   ++mp.tsdf_version;
   if (layer == NVBX_LAYER_COLOR) {
@@ -2280,6 +2312,7 @@ int64_t nvbx_kernel_timing_report(nvbx_mapper* m, char* json, int64_t capacity) 
   if (!m || !json || capacity <= 2) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad timing report buffer");
   CUDA_TRY(cudaSetDevice(m->device));
   std::vector<std::pair<std::string, std::pair<double, long long>>> agg;
+  std::lock_guard<std::mutex> recs_guard(g_launch_recs_mu);
   for (auto& r : g_launch_recs) {
     float ms = 0.f;
     if (r.b && cudaEventSynchronize(r.b) == cudaSuccess) cudaEventElapsedTime(&ms, r.a, r.b);

@@ -179,18 +179,20 @@ __device__ __forceinline__ int hash_find(const MapDev& m, int x, int y, int z) {
   if (!key_in_range(x, y, z)) return -1;
   const unsigned long long key = pack_key(x, y, z);
   unsigned int h = mix_key(key) & m.hash_mask;
-  while (true) {
+  // bounded probe: a table without an empty key (a host sizing bug) must not hang the GPU
+  for (unsigned int n = 0; n <= m.hash_mask; ++n) {
     const unsigned long long k = m.keys[h];
     if (k == key) return m.vals[h];
     if (k == kEmptyKey) return -1;
     h = (h + 1) & m.hash_mask;
   }
+  return -1;
 }
 // Insert a key known to be absent and inserted by exactly one thread.
 __device__ __forceinline__ void hash_insert(const MapDev& m, int x, int y, int z, int slot) {
   const unsigned long long key = pack_key(x, y, z);
   unsigned int h = mix_key(key) & m.hash_mask;
-  while (true) {
+  for (unsigned int n = 0; n <= m.hash_mask; ++n) {
     const unsigned long long prev = atomicCAS(&m.keys[h], kEmptyKey, key);
     if (prev == kEmptyKey) {
       m.vals[h] = slot;
@@ -198,6 +200,7 @@ __device__ __forceinline__ void hash_insert(const MapDev& m, int x, int y, int z
     }
     h = (h + 1) & m.hash_mask;
   }
+  atomicExch(&m.ctrl->overflow, 1);  // table full: reported as an error by the next read_ctrl (never hangs)
 }
 
 // Cell of the workspace grid holding block (x, y, z), or -1 when the index lies outside the box (or the

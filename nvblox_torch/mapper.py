@@ -271,7 +271,13 @@ class Mapper:
                                   mapper_id: int = 0) -> None:
         """(ours) depth + feature frame from HOST tensors.  A pinned feature frame is fetched sparsely over PCIe
         (see `set_host_fetch_mode`) and must not be modified until the stream has passed this call."""
-        assert depth.dtype == torch.float32 and features.dtype == torch.float16 and not depth.is_cuda
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        _check_host_frame_inputs(depth, t_w_c, intrinsics, depth_mask, feature_mask)
+        assert features.dtype == torch.float16 and not features.is_cuda and features.dim() == 3 and \
+            features.is_contiguous(), 'Feature frame should be a contiguous [H, W, C] float16 CPU tensor.'
+        assert features.shape[0] == depth.shape[0] and features.shape[1] == depth.shape[1], \
+            'Feature frame size should match the depth frame.'
+        assert features.shape[2] == self._feature_channels, f'Feature should have {self._feature_channels} channels.'
         fx, fy, cx, cy = _fxfycxcy(intrinsics)
         _capi.check(self._lib.nvbx_integrate_frame_host(
             self._handle, mapper_id, depth.data_ptr(), features.data_ptr(), depth.shape[0], depth.shape[1],
@@ -328,7 +334,9 @@ class Mapper:
                                          feature_mask=None, mapper_id: int = 0) -> None:
         """(ours) depth + low-res feature map from HOST (ideally pinned) tensors: 2.5 MB of H2D per 512^2 x 768 frame
         instead of 385 MB."""
-        assert depth.dtype == torch.float32 and not depth.is_cuda and not features_bchw.is_cuda
+        assert 0 <= mapper_id < len(self._voxel_sizes)
+        _check_host_frame_inputs(depth, t_w_c, intrinsics, depth_mask, feature_mask)
+        assert not features_bchw.is_cuda, 'Low-res feature map should be on the CPU.'
         x, c, h, w, dtype, layout, kernel = lowres_descriptor(features_bchw)
         fx, fy, cx, cy = _fxfycxcy(intrinsics)
         _capi.check(self._lib.nvbx_integrate_frame_host_lowres(
@@ -519,6 +527,21 @@ class Mapper:
     def print_timing(self) -> str:
         from nvblox_torch.timer import timer_status_string
         return timer_status_string()
+
+
+def _check_host_frame_inputs(depth, t_w_c, intrinsics, depth_mask, feature_mask) -> None:
+    """Input contract of the host-frame entry points: the C side reads these buffers by raw pointer and size."""
+    assert depth.dtype == torch.float32 and not depth.is_cuda and depth.dim() == 2 and depth.is_contiguous(), \
+        'Depth frame should be a contiguous [H, W] float32 CPU tensor.'
+    for name, mask in (('Depth', depth_mask), ('Feature', feature_mask)):
+        if mask is not None:
+            assert mask.dtype == torch.uint8 and not mask.is_cuda and mask.is_contiguous() and \
+                tuple(mask.shape) == tuple(depth.shape), \
+                f'{name} mask should be a contiguous uint8 CPU tensor of the depth frame\'s size.'
+    assert t_w_c.is_cpu and t_w_c.dtype == torch.float32 and tuple(t_w_c.shape) == (4, 4), \
+        't_w_c should be a 4x4 float32 CPU tensor.'
+    assert intrinsics.is_cpu and intrinsics.dtype == torch.float32 and tuple(intrinsics.shape) == (3, 3), \
+        'intrinsics should be a 3x3 float32 CPU tensor.'
 
 
 def check_integrator_inputs(image: torch.Tensor,

@@ -106,6 +106,27 @@ def test_host_frame_rejects_wrong_channels():
     pair = Pair(0.02, 768, mp, op)
     K = S.intrinsics(64, 64)
     T = S.orbit_pose(0)
-    with pytest.raises(NvbxError):
+    # the Python surface rejects it (input contract, AssertionError like the device-frame integrators) ...
+    with pytest.raises(AssertionError):
         pair.gpu.integrate_frame_from_host(torch.zeros(64, 64), torch.zeros(64, 64, 512, dtype=torch.float16),
                                            torch.from_numpy(T), torch.from_numpy(K))
+    # ... and so does the C ABI itself when called directly
+    import ctypes as C
+    from nvblox_mindmap_b200 import _capi
+    d, f = torch.zeros(64, 64), torch.zeros(64, 64, 512, dtype=torch.float16)
+    Tt = torch.from_numpy(T).contiguous()
+    with pytest.raises(NvbxError):
+        _capi.check(_capi.load().nvbx_integrate_frame_host(
+            pair.gpu._handle, 0, d.data_ptr(), f.data_ptr(), 64, 64, 512, None, None, Tt.data_ptr(),
+            float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]), pair.gpu._stream()))
+    # non-contiguous / wrong-dtype / wrong-size host buffers never reach the C side
+    with pytest.raises(AssertionError):
+        pair.gpu.integrate_frame_from_host(torch.zeros(64, 128)[:, ::2], torch.zeros(64, 64, 768, dtype=torch.float16),
+                                           torch.from_numpy(T), torch.from_numpy(K))
+    with pytest.raises(AssertionError):
+        pair.gpu.integrate_frame_from_host(torch.zeros(64, 64), torch.zeros(64, 64, 768, dtype=torch.float16),
+                                           torch.from_numpy(T), torch.from_numpy(K),
+                                           depth_mask=torch.ones(32, 32, dtype=torch.uint8))
+    with pytest.raises(AssertionError):
+        pair.gpu.integrate_frame_from_host(torch.zeros(64, 64), torch.zeros(64, 64, 768, dtype=torch.float16),
+                                           torch.from_numpy(T).double(), torch.from_numpy(K))
