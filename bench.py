@@ -199,7 +199,7 @@ def run_ours(args, rank, world, local_rank):
     mapper = Mapper(voxel_sizes_m=VOXEL, mapper_parameters=mp, device=local_rank)
     # replay: every frame of the sequence stays resident and unmodified, which is the contract of frame pipelining
     # (the gather of frame i on the map's own stream, the depth path of frame i + 1 underneath it; same results)
-    mapper.set_pipelining(bool(args.pipelining))
+    mapper.set_pipelining(bool(args.pipelining), async_enqueue=(args.pipelining == 2))
 
     n_total = args.warmup + args.steps
     K, frames = poses_and_depths(max(n_total, 1))
@@ -234,11 +234,21 @@ def run_ours(args, rank, world, local_rank):
     launches0 = int(lib.nvbx_kernel_launch_count())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+
+    def pipe_waits():
+        a, b = C.c_int64(0), C.c_int64(0)
+        lib.nvbx_pipeline_wait_stats(C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    w0 = pipe_waits()
     e0.record()
     t_host = time.perf_counter()
     for i in range(args.warmup, n_total):
         step(i)
     t_host = time.perf_counter() - t_host      # host time to ENQUEUE the steps (no sync inside)
+    w1 = pipe_waits()
+    # how long the host sat waiting for a ring slot (device-bound) -- the rest of t_host is its own work
+    host_wait = {'waits_per_step': (w1[0] - w0[0]) / args.steps, 'wait_us_per_step': (w1[1] - w0[1]) / 1e3 / args.steps}
     mapper.pipeline_join()                     # the timed region ends when the last gather has finished
     e1.record()
     barrier()
@@ -292,7 +302,7 @@ def run_ours(args, rank, world, local_rank):
             kms = kernel_time_ms(args, mapper, depths, poses, feats, K_t)
             print(json.dumps({'per_kernel_us': per_kernel_us(args, mapper, depths, poses, feats, K_t)}), flush=True)
             print(json.dumps({'quick': True, 'value': value, 'ms_per_step': ms / args.steps, 'kernel_ms': kms,
-                              'host_enqueue_ms_per_step': 1000.0 * t_host / args.steps,
+                              'host_enqueue_ms_per_step': 1000.0 * t_host / args.steps, 'host_wait': host_wait,
                               'gpu_launches': launches, 'profile': counters.get('profile')}), flush=True)
         return
 
@@ -410,7 +420,7 @@ def run_ours(args, rank, world, local_rank):
         eb.record()
         torch.cuda.synchronize()
         value_no_pipe = n_np / (ea.elapsed_time(eb) / 1e3)
-        mapper.set_pipelining(bool(args.pipelining))
+        mapper.set_pipelining(bool(args.pipelining), async_enqueue=(args.pipelining == 2))
         batched = batched_maps_stage(depths, poses, feats, K_t, local_rank)
         drill = drill_in_box_stage(lib, feats, h_feat, local_rank, peak)
         cold = cold_start_stage(depths, poses, feats, K_t, local_rank)
@@ -461,7 +471,7 @@ def run_ours(args, rank, world, local_rank):
                              'sample': f"first {sample_mt['frames']} frames of the workload through the CPU oracle "
                                        f"(OpenMP over blocks, {n_cores} threads, {sample_mt['seconds']:.1f} s); "
                                        f"1 thread, first {sample['frames']} frames: {sample['fps']:.3f} frames/s"},
-            'extra': {'feature_call_ms': feat_call_ms, 'feature_call_ms_p10_p50_p90': feat_call_pct, 'host_enqueue_ms_per_step': 1000.0 * t_host / args.steps,
+            'extra': {'feature_call_ms': feat_call_ms, 'feature_call_ms_p10_p50_p90': feat_call_pct, 'host_enqueue_ms_per_step': 1000.0 * t_host / args.steps, 'host_wait_for_ring_slot': host_wait,
                       'per_kernel_us_in_pipeline': per_kernel, 'export_stage': export,
                       'fused_upsample': fused, 'batched_maps_one_gpu': batched, 'drill_in_box': drill,
                       'batched_64_maps': batched64, 'stress': stress, 'cold_start': cold,
@@ -978,14 +988,23 @@ def main():
     ap.add_argument('--warmup', type=int, default=64)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--sweep-gather', action='store_true', help='tuning aid: time every gather schedule')
+    ap.add_argument('--stream-priority', type=int, default=0,
+                    help='tuning aid: run the mapper on a torch stream of this priority (0 default, -1 .. -5 higher)')
     ap.add_argument('--quick', action='store_true', help='tuning aid: device-timed pass + kernel timing only')
-    ap.add_argument('--pipelining', type=int, default=1, help='frame pipelining (Mapper.set_pipelining) in the device-timed pass')
+    ap.add_argument('--pipelining', type=int, default=2,
+                    help='frame pipelining in the device-timed pass: 0 off, 1 on, 2 on + asynchronous enqueue (Mapper.set_pipelining)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
         run_reference(args, rank, world)
+        return
+    if args.stream_priority:
+        import torch
+        torch.cuda.set_device(local_rank)
+        with torch.cuda.stream(torch.cuda.Stream(device=local_rank, priority=args.stream_priority)):
+            run_ours(args, rank, world, local_rank)
         return
     run_ours(args, rank, world, local_rank)
 

@@ -270,14 +270,23 @@ int nvbx_clear(nvbx_mapper* m, int map_id, void* stream);
 int nvbx_mark_all_dirty(nvbx_mapper* m, int map_id, void* stream);
 
 /* ---- frame pipelining (ours) ------------------------------------------------------------------------------
- * nvbx_set_pipelining(m, 1): the memory-bound gather of feature frame i runs on a stream owned by the map, so that the
- * latency-bound depth path of frame i + 1 (raycast, TSDF update, sphere tracing + band selection, geometry), which the
- * caller enqueues next on ITS stream, runs underneath it instead of behind it.  Results are unchanged (bit for bit).
- * Contract while it is on: the FEATURE frame passed to nvbx_integrate_features must stay valid and unmodified until
- * the second-next nvbx_integrate_features call on that map returns, or until any call that reads or frees feature
- * data (decay, clear, mesh update, feature block views, feature queries, nvbx_pipeline_join) -- every such call first
- * orders its stream behind the gathers in flight.  Depth frames, masks and colour frames are consumed on the caller's
- * stream as before.  Off by default (the reference's callers free or overwrite a frame right after the call). */
+ * nvbx_set_pipelining(m, 1): the geometry kernel and the memory-bound gather of feature frame i run on two streams
+ * owned by the map, so that the latency-bound depth path of frame i + 1 (raycast, TSDF update, sphere tracing + band
+ * selection), which the caller enqueues next on ITS stream, runs underneath them instead of behind them.  Results are
+ * unchanged (bit for bit).
+ * Contract while it is on: the FEATURE frame (and its mask) passed to nvbx_integrate_features must stay valid and
+ * unmodified until four more nvbx_integrate_features calls on that map have returned (the per-frame lists live in a
+ * ring of four; the host waits for a slot's last gather before re-using it), or until any call that reads or frees
+ * feature data (decay, clear, mesh update, feature block views, feature queries, nvbx_pipeline_join) -- every such
+ * call first orders its stream behind the gathers in flight.  Depth frames, depth masks and colour frames are
+ * consumed on the caller's stream as before.  Off by default (the reference's callers free or overwrite a frame right
+ * after the call).
+ * nvbx_set_pipelining(m, 2): the same, plus ASYNCHRONOUS ENQUEUE -- nvbx_integrate_depth / nvbx_integrate_features
+ * validate their arguments, queue them (up to eight calls) and return; a worker thread owned by the mapper issues the
+ * CUDA work in call order on the stream each call named.  Every other entry point taking this handle first waits for
+ * the queue to be issued, and returns the error of a queued frame if there was one (frames queued behind a failed one
+ * are dropped).  Additional contract: EVERY input buffer of a queued call stays valid and unmodified until such a
+ * joining call, and work the caller itself enqueues on the stream is no longer ordered behind a queued frame. */
 int nvbx_set_pipelining(nvbx_mapper* m, int on);
 /* Order `stream` behind every gather in flight of map_id (-1: all maps). */
 int nvbx_pipeline_join(nvbx_mapper* m, int map_id, void* stream);
@@ -384,6 +393,10 @@ int nvbx_get_kernel_timing(nvbx_mapper* m, int which, double* total_ms, int64_t*
 int nvbx_set_gather_tuning(int variant, int dyn_permille, int ticket_units);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t nvbx_kernel_launch_count(void);
+/* Frame pipelining back-pressure (tuning aid): how often, and for how many nanoseconds in total, the HOST had to wait
+ * for a ring slot (the gather of four feature frames ago) since load.  Near zero: the host, not the device, sets the
+ * frame rate.  Either pointer may be null. */
+void nvbx_pipeline_wait_stats(int64_t* waits, int64_t* wait_ns);
 /* Debug / parity hooks: copy the last frame's intermediate products to HOST memory.
  *   which = 0: block indices handed to the last TSDF update   (int32 triples)
  *   which = 1: block indices handed to the last feature update (int32 triples)

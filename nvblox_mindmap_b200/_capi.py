@@ -24,7 +24,7 @@ API_SYMBOLS = [
     'nvbx_export_points', 'nvbx_gather_points', 'nvbx_num_blocks', 'nvbx_num_allocated_blocks',
     'nvbx_num_allocated_bytes', 'nvbx_voxel_size', 'nvbx_get_block_indices', 'nvbx_get_all_blocks', 'nvbx_get_block_ptr',
     'nvbx_allocate_block', 'nvbx_query_tsdf', 'nvbx_query_features', 'nvbx_get_counters',
-    'nvbx_reset_counters', 'nvbx_integrate_frames_batch', 'nvbx_set_gather_tuning', 'nvbx_set_kernel_timing', 'nvbx_get_kernel_timing', 'nvbx_kernel_timing_report', 'nvbx_kernel_launch_count', 'nvbx_debug_last_block_list', 'nvbx_debug_profile_stamps',
+    'nvbx_reset_counters', 'nvbx_integrate_frames_batch', 'nvbx_set_gather_tuning', 'nvbx_set_kernel_timing', 'nvbx_get_kernel_timing', 'nvbx_kernel_timing_report', 'nvbx_kernel_launch_count', 'nvbx_pipeline_wait_stats', 'nvbx_debug_last_block_list', 'nvbx_debug_profile_stamps',
     'nvbx_debug_last_synthetic_depth', 'nvbx_version',
 ]
 
@@ -107,6 +107,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         L.nvbx_kernel_timing_report.argtypes = [vp, C.c_char_p, C.c_int64]
         L.nvbx_kernel_timing_report.restype = C.c_int64
         L.nvbx_kernel_launch_count.restype = C.c_int64
+        L.nvbx_pipeline_wait_stats.argtypes = [i64p, i64p]
+        L.nvbx_pipeline_wait_stats.restype = None
         L.nvbx_debug_last_block_list.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64, vp]
         L.nvbx_debug_last_block_list.restype = C.c_int64
         L.nvbx_debug_last_synthetic_depth.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int),

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -211,8 +212,9 @@ struct Map {
   CacheEntry scratch_ray, scratch_planes;  // used when the cache is disabled
   DevBuf<unsigned> grid;   // view bitmap; all-zero between frames (k_view_compact_alloc cleans it)
   bool grid_dirty = false;  // a frame failed between marking and compaction
-  unsigned* small_grid[2] = {nullptr, nullptr};  // double-buffered bitmap of small views (2 x kFusedBitmapWords)
-  int small_cur = 0;
+  unsigned* small_grid[3] = {nullptr, nullptr, nullptr};  // triple-buffered bitmap of small views (3 x kFusedBitmapWords)
+  unsigned small_seq = 0;  // number of small-view depth frames enqueued (wraps); frame s marks small_grid[small_idx]
+  int small_idx = 0;       // = (number of small-view depth frames) mod 3
   bool small_dirty = false;
   DevBuf<int> view_slots, cband_slots;
   DevBuf<int> band_slots2[kFrameRing], newfeat_slots2[kFrameRing];  // per feature frame, ring slot MapDev::fp
@@ -223,6 +225,11 @@ struct Map {
   // frame's geometry kernel by `ev_trace`; `ev_gather[r]` marks the end of the last gather that used ring slot r (and
   // with it the last use of every buffer of that slot on `gstream`).
   cudaStream_t gstream = nullptr;
+  // NVBX_PIPE_GEOM=2: the geometry kernel of frame i on a third, high-priority stream (behind the frame's trace / band
+  // selection by `ev_trace`, ahead of its gather by `ev_geom`), so that the caller's stream goes straight on to frame
+  // i + 1's raycast / TSDF update
+  cudaStream_t cstream = nullptr;
+  cudaEvent_t ev_geom = nullptr;
   cudaEvent_t ev_trace = nullptr, ev_gather[kFrameRing] = {};
   bool gather_pending[kFrameRing] = {};
   DevBuf<float> synth2[kFrameRing];  // synthetic depth images, ring slot MapDev::fp
@@ -280,7 +287,70 @@ struct Map {
 
 }  // namespace
 
+// ---- asynchronous enqueue (nvbx_set_pipelining(m, 2)) -------------------------------------------------------
+// The five launches + six event operations of a pipelined frame cost the calling thread ~20 us -- with the Python
+// surface on top, more than the ~35 us the device needs per frame.  In this mode nvbx_integrate_depth /
+// nvbx_integrate_features validate their arguments, copy them into a small FIFO and return; one worker thread per
+// mapper issues the CUDA calls in order.  Every other entry point first waits until the FIFO has been issued (and
+// reports an error a queued frame ran into), so the library's own calls keep their stream order; what the caller
+// gives up is the order between a frame and the caller's OWN later work on the same stream (same contract as
+// pipelining: inputs stay alive and unmodified until the next joining call).
+struct AsyncJob {
+  int kind;  // 0: depth frame, 1: feature frame
+  int map_id;
+  const void* image;
+  int height, width, channels;
+  const void* mask;
+  float T[16];
+  float fx, fy, cx, cy;
+  void* stream;
+};
+class AsyncEnqueue {
+ public:
+  static constexpr int kCap = 8;  // frames the caller may run ahead of the worker
+  explicit AsyncEnqueue(nvbx_mapper* m) : m_(m), th_([this] { loop(); }) {}
+  ~AsyncEnqueue() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_ = true;
+    }
+    cv_work_.notify_all();
+    th_.join();
+  }
+  void push(const AsyncJob& j) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_room_.wait(lk, [this] { return (int)q_.size() < kCap; });
+    q_.push_back(j);
+    ++outstanding_;
+    lk.unlock();
+    cv_work_.notify_one();
+  }
+  // Returns when everything pushed so far has been issued; the first error of a queued frame is returned ONCE.
+  int flush(std::string* err) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [this] { return outstanding_ == 0; });
+    const int rc = rc_;
+    if (rc) *err = err_;
+    rc_ = 0;
+    err_.clear();
+    return rc;
+  }
+
+ private:
+  void loop();
+  nvbx_mapper* m_;
+  std::mutex mu_;
+  std::condition_variable cv_work_, cv_room_, cv_done_;
+  std::deque<AsyncJob> q_;
+  int outstanding_ = 0;  // queued + being issued
+  bool stop_ = false;
+  int rc_ = 0;
+  std::string err_;
+  std::thread th_;  // last member: started when everything above is constructed
+};
+
 struct nvbx_mapper {
+  std::unique_ptr<AsyncEnqueue> async;  // non-null while asynchronous enqueue is on
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events[2];
   int device = 0;
@@ -353,12 +423,16 @@ int grow_color_slabs(Map& mp, cudaStream_t stream) {
 // latency-bound and touch nothing the memory-bound gather reads or writes (Ctrl counters and the item list are
 // double-buffered by MapDev::fp, voxel weights are written by the geometry kernel).
 int env_int(const char* name, int dflt);
+std::atomic<long long> g_pipe_waits{0}, g_pipe_wait_ns{0};  // nvbx_pipeline_wait_stats
 int pipeline_init(Map& mp) {
   if (mp.gstream) return NVBX_OK;
   int lo = 0, hi = 0;
   CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   static const int prio = env_int("NVBX_PIPE_PRIO", 0);  // tuning knob: 0 lowest (the short kernels go first), 1 highest
   CUDA_TRY(cudaStreamCreateWithPriority(&mp.gstream, cudaStreamNonBlocking, prio ? hi : lo));
+  static const int gprio = env_int("NVBX_PIPE_GEOM_PRIO", 1);  // tuning knob: the geometry stream's priority
+  CUDA_TRY(cudaStreamCreateWithPriority(&mp.cstream, cudaStreamNonBlocking, gprio ? hi : lo));
+  CUDA_TRY(cudaEventCreateWithFlags(&mp.ev_geom, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&mp.ev_trace, cudaEventDisableTiming));
   for (int r = 0; r < kFrameRing; ++r) CUDA_TRY(cudaEventCreateWithFlags(&mp.ev_gather[r], cudaEventDisableTiming));
   return NVBX_OK;
@@ -388,7 +462,12 @@ int pipeline_slot_ready(Map& mp) {
   if (!mp.gather_pending[r]) return NVBX_OK;
   const cudaError_t q = cudaEventQuery(mp.ev_gather[r]);
   if (q == cudaErrorNotReady) {
+    const auto t0 = std::chrono::steady_clock::now();
     CUDA_TRY(cudaEventSynchronize(mp.ev_gather[r]));
+    g_pipe_waits.fetch_add(1, std::memory_order_relaxed);
+    g_pipe_wait_ns.fetch_add(
+        std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(),
+        std::memory_order_relaxed);
   } else if (q != cudaSuccess) {
     CUDA_TRY(q);
   }
@@ -610,8 +689,19 @@ int make_grid(const nvbx_mapper* m, const Map& mp, Aabb a, GridSpec* out) {
   return NVBX_OK;
 }
 
-int check_map(nvbx_mapper* m, int map_id) {
+thread_local bool t_async_worker = false;  // this thread is a mapper's enqueue worker: never wait for the FIFO
+// Wait until every asynchronously queued frame has been issued; report the error one of them ran into.
+int async_flush(nvbx_mapper* m) {
+  if (!m || !m->async || t_async_worker) return NVBX_OK;
+  std::string err;
+  const int rc = m->async->flush(&err);
+  if (rc) return fail(rc, "a frame queued by the asynchronous enqueue failed: %s", err.c_str());
+  return NVBX_OK;
+}
+int check_map(nvbx_mapper* m, int map_id, bool flush = true) {
   if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper handle");
+  if (flush)
+    if (int frc = async_flush(m)) return frc;
   if (map_id < 0 || map_id >= (int)m->maps.size())
     return fail(NVBX_ERR_INVALID_ARGUMENT, "mapper_id %d out of range [0, %d)", map_id, (int)m->maps.size());
   cudaError_t e = cudaSetDevice(m->device);
@@ -643,9 +733,10 @@ int init_map(nvbx_mapper* m, Map& mp, float voxel_size, cudaStream_t stream) {
   CUDA_TRY(cudaMalloc(&mp.d_tmp_ptr, sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc(&mp.d_exp_total, sizeof(long long)));
   CUDA_TRY(cudaMalloc(&mp.scratch_ray.d_count, sizeof(int)));
-  CUDA_TRY(cudaMalloc(&mp.small_grid[0], 2 * kFusedBitmapWords * sizeof(unsigned)));
-  CUDA_TRY(cudaMemsetAsync(mp.small_grid[0], 0, 2 * kFusedBitmapWords * sizeof(unsigned), stream));
+  CUDA_TRY(cudaMalloc(&mp.small_grid[0], 3 * kFusedBitmapWords * sizeof(unsigned)));
+  CUDA_TRY(cudaMemsetAsync(mp.small_grid[0], 0, 3 * kFusedBitmapWords * sizeof(unsigned), stream));
   mp.small_grid[1] = mp.small_grid[0] + kFusedBitmapWords;
+  mp.small_grid[2] = mp.small_grid[1] + kFusedBitmapWords;
   // level-1 index: direct-mapped grid over the workspace box (same rounding as make_grid)
   if (m->params.workspace_bounds_type == NVBX_WORKSPACE_BOUNDING_BOX) {
     Aabb a;
@@ -733,6 +824,9 @@ void destroy_map(Map& mp) {
   if (mp.gstream) {
     cudaStreamSynchronize(mp.gstream);
     cudaStreamDestroy(mp.gstream);
+    cudaStreamSynchronize(mp.cstream);
+    cudaStreamDestroy(mp.cstream);
+    cudaEventDestroy(mp.ev_geom);
     cudaEventDestroy(mp.ev_trace);
     for (int r = 0; r < kFrameRing; ++r) cudaEventDestroy(mp.ev_gather[r]);
     mp.gstream = nullptr;
@@ -910,6 +1004,10 @@ extern "C" {
 const char* nvbx_version(void) { return "nvbx 0.1.0 (sm_100a)"; }
 const char* nvbx_last_error(void) { return g_last_error.c_str(); }
 int64_t nvbx_kernel_launch_count(void) { return g_launches.load(); }
+void nvbx_pipeline_wait_stats(int64_t* waits, int64_t* wait_ns) {
+  if (waits) *waits = g_pipe_waits.load();
+  if (wait_ns) *wait_ns = g_pipe_wait_ns.load();
+}
 
 void nvbx_default_params(nvbx_params* p) {
   std::memset(p, 0, sizeof(*p));
@@ -1004,6 +1102,7 @@ int nvbx_create(int n_maps, const float* voxel_sizes_m, const nvbx_params* param
 void nvbx_destroy(nvbx_mapper* m) {
   if (!m) return;
   cudaSetDevice(m->device);
+  m->async.reset();  // issues what is still queued, then stops the worker
   for (auto& mp : m->maps) pipeline_drain(*mp);
   for (auto& mp : m->maps) destroy_map(*mp);
   delete m;
@@ -1024,9 +1123,15 @@ float nvbx_voxel_size(const nvbx_mapper* m, int map_id) {
 // ---- depth ---------------------------------------------------------------------------------------
 int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int height, int width, const void* mask,
                          const float* T_L_C_rm, float fx, float fy, float cx, float cy, void* stream_v) {
-  int rc = check_map(m, map_id);
+  int rc = check_map(m, map_id, /*flush=*/false);
   if (rc) return rc;
   if (!depth || !T_L_C_rm || height <= 0 || width <= 0) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad depth frame");
+  if (m->async && !t_async_worker) {  // asynchronous enqueue: the mapper's worker thread issues the launches
+    AsyncJob j{0, map_id, depth, height, width, 0, mask, {}, fx, fy, cx, cy, stream_v};
+    std::memcpy(j.T, T_L_C_rm, sizeof(j.T));
+    m->async->push(j);
+    return NVBX_OK;
+  }
   cudaStream_t stream = (cudaStream_t)stream_v;
   Map& mp = *m->maps[map_id];
   const nvbx_params& p = m->params;
@@ -1062,10 +1167,10 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
     unsigned* bits;
     if (fused) {
       if (mp.small_dirty) {
-        CUDA_TRY(cudaMemsetAsync(mp.small_grid[0], 0, 2 * kFusedBitmapWords * sizeof(unsigned), stream));
+        CUDA_TRY(cudaMemsetAsync(mp.small_grid[0], 0, 3 * kFusedBitmapWords * sizeof(unsigned), stream));
         mp.small_dirty = false;
       }
-      bits = mp.small_grid[mp.small_cur];
+      bits = mp.small_grid[mp.small_idx];
     } else {
       const unsigned* old_grid = mp.grid.p;
       if ((rc = mp.grid.ensure(n_words, stream))) return rc;
@@ -1105,11 +1210,14 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
                     (unsigned)(rf.start[2] - gs.g.mn.z) * (unsigned)gs.g.sx * (unsigned)gs.g.sy);
     rf.tiles_x = tiles_x;
     rf.n_tiles = n_tiles;
-    rf.ctrl = mp.d_ctrl;
+    rf.seq = mp.dev.seq;
     if (n_words <= (size_t)kRayBitmapWords) {
-      LAUNCH(k_raycast_mark<true>, rgrid, 256, n_words * sizeof(unsigned), stream, rf, bits, entry->d_count);
+      static const int early_flush = env_int("NVBX_RAYCAST_EARLY_FLUSH", 1);  // tuning knob
+      LAUNCH(k_raycast_mark<true>, rgrid, 256, n_words * sizeof(unsigned), stream, rf, bits, entry->d_count,
+             (fused && early_flush) ? 1 : 0, mp.small_seq, &mp.d_ctrl->bitmap_clean_seq);
     } else {
-      LAUNCH(k_raycast_mark<false>, rgrid, 256, 0, stream, rf, bits, entry->d_count);
+      LAUNCH(k_raycast_mark<false>, rgrid, 256, 0, stream, rf, bits, entry->d_count, 0, 0u,
+             &mp.d_ctrl->bitmap_clean_seq);
     }
     const int cgrid = std::max(1, std::min(persistent_grid(m, 4), (int)((n_words + 7) / 8)));  // warp per word
     if (!slots_fit(m, mp, (long long)n)) {
@@ -1127,7 +1235,8 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
     if (fused) {
       view_mode = kViewFromBitmap;
       vs.bits = bits;
-      vs.clean_bits = mp.small_grid[mp.small_cur ^ 1];
+      vs.clean_bits = mp.small_grid[(mp.small_idx + 2) % 3];
+      vs.clean_seq = mp.small_seq + 2u;
       vs.g = gs.g;
     } else {
       LAUNCH(k_view_compact_alloc, cgrid, 256, 0, stream, mp.dev, bits, gs.g, entry->idx.p, entry->d_count,
@@ -1158,7 +1267,8 @@ int nvbx_integrate_depth(nvbx_mapper* m, int map_id, const void* depth, int heig
   if ((rc = timing_begin(m, 1, stream))) return rc;
   if (view_mode == kViewFromBitmap) {
     LAUNCH(k_tsdf_update<kViewFromBitmap>, tgrid, 512, 0, stream, mp.dev, vs, f);
-    mp.small_cur ^= 1;  // the other half was cleared by the kernel
+    ++mp.small_seq;  // the third this frame marked is wiped by the next frame's kernel
+    mp.small_idx = (mp.small_idx + 1) % 3;
     mp.small_dirty = false;
   } else if (view_mode == kViewFromEntry) {
     LAUNCH(k_tsdf_update<kViewFromEntry>, tgrid, 512, 0, stream, mp.dev, vs, f);
@@ -1284,6 +1394,8 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
   // where every step depends on the value just read, so the extra lanes only add work.  Kept selectable.
   static const int team = env_int("NVBX_TRACE_TEAM", 0);
   tp.team = team;
+  static const int march = env_int("NVBX_TRACE_MARCH", 256);
+  tp.march = (march == 128 || march == 64 || march == 32) ? march : 256;
   // synthetic depth already rendered for exactly this pose / camera / TSDF state (the other appearance frame of
   // the same step): skip the sphere tracing, keep the band selection
   Map::SynthKey& key = mp.synth_key;
@@ -1299,8 +1411,9 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
     while (tile_cells < 256 && (entry->bound + tile_cells - 1) / tile_cells > 2 * m->sm_count) tile_cells <<= 1;
     const int n_tiles = (entry->bound + tile_cells - 1) / tile_cells;
     // trace CTAs: 8 x 4 rays with eight lanes per ray (team march), or 16 x 16 rays with one thread per ray
-    const int trace_tiles_x = tp.team ? (scols + 7) / 8 : (scols + 15) / 16;
-    const int n_trace = reuse ? 0 : trace_tiles_x * (tp.team ? (srows + 3) / 4 : (srows + 15) / 16);
+    const int tile_h = tp.team ? 4 : (tp.march < 256 ? tp.march / 8 : 16);
+    const int trace_tiles_x = (tp.team || tp.march < 256) ? (scols + 7) / 8 : (scols + 15) / 16;
+    const int n_trace = reuse ? 0 : trace_tiles_x * ((srows + tile_h - 1) / tile_h);
     const int n_band = std::max(1, std::min(n_tiles, persistent_grid(m, 4)));
     key.valid = false;  // a failed launch leaves no valid image behind
     static const int spec = env_int("NVBX_TRACE_SPEC", 1), ilp = env_int("NVBX_BAND_ILP", 2);
@@ -1441,12 +1554,18 @@ int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, co
     const int last = end >= cand_bound ? 1 : 0;
     if (begin > 0) CUDA_TRY(cudaMemsetAsync(&mp.d_ctrl->item_count[mp.dev.fp], 0, sizeof(int), stream));
     const int ggrid = persistent_grid(m, 2);  // full grid: new feature blocks are zero-filled by all CTAs
-    static const bool geom_on_gs = env_int("NVBX_PIPE_GEOM", 0) != 0;  // tuning knob: geometry on the gather stream (measured slower)
-    if (pipe && geom_on_gs) {  // geometry + gather of this frame on the map's own stream, behind its trace / band select
+    // tuning knob: where the geometry kernel of a pipelined frame runs -- 0: caller's stream, 1: the gather stream
+    // (measured slower), 2: its own high-priority stream
+    static const int geom_mode = env_int("NVBX_PIPE_GEOM", 2);
+    const bool geom_on_gs = geom_mode == 1, geom_own = geom_mode == 2;
+    cudaStream_t geo = stream;
+    if (pipe && geom_on_gs) geo = gs;
+    if (pipe && geom_own) geo = mp.cstream;
+    if (pipe && geo != stream) {  // behind this frame's trace / band selection
       CUDA_TRY(cudaEventRecord(mp.ev_trace, stream));
-      CUDA_TRY(cudaStreamWaitEvent(gs, mp.ev_trace, 0));
+      CUDA_TRY(cudaStreamWaitEvent(geo, mp.ev_trace, 0));
     }
-    LAUNCH(k_feature_geometry, ggrid, 512, 0, (pipe && !geom_on_gs) ? stream : gs, mp.dev, mp.band_slots2[mp.dev.fp].p, mp.newfeat_slots2[mp.dev.fp].p, ff,
+    LAUNCH(k_feature_geometry, ggrid, 512, 0, geo, mp.dev, mp.band_slots2[mp.dev.fp].p, mp.newfeat_slots2[mp.dev.fp].p, ff,
            mp.items2[mp.dev.fp].p, (int)begin, (int)end);
     const int ch = (m->C % 256 == 0 && m->C / 256 >= 1 && m->C / 256 <= 4) ? m->C / 256 : 0;
     if (hf) {
@@ -1469,9 +1588,12 @@ int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, co
       else
         rc = launch_gather_up<0>(m, mp, ff, *uf, up_mode, last, stream);
     } else {
-      if (pipe && !geom_on_gs) {
+      if (pipe && geo == stream) {
         CUDA_TRY(cudaEventRecord(mp.ev_trace, stream));
         CUDA_TRY(cudaStreamWaitEvent(gs, mp.ev_trace, 0));
+      } else if (pipe && geo == mp.cstream) {
+        CUDA_TRY(cudaEventRecord(mp.ev_geom, geo));
+        CUDA_TRY(cudaStreamWaitEvent(gs, mp.ev_geom, 0));
       }
       if (ch == 3)
         rc = launch_gather<3>(m, mp, ff, last, gs, pipe);
@@ -1492,6 +1614,7 @@ int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, co
   }
   mp.have_band_list = true;
   mp.dev.fp = (mp.dev.fp + 1) % kFrameRing;  // the next feature frame uses the next ring slot
+  ++mp.dev.seq;
   return NVBX_OK;
 }
 
@@ -1502,16 +1625,50 @@ extern "C" {
 int nvbx_integrate_features(nvbx_mapper* m, int map_id, const void* features, int height, int width, int channels,
                             const void* mask, const float* T_L_C_rm, float fx, float fy, float cx, float cy,
                             void* stream_v) {
-  int rc = check_map(m, map_id);
+  int rc = check_map(m, map_id, /*flush=*/false);
   if (rc) return rc;
   if (!features || !T_L_C_rm || height <= 0 || width <= 0) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad feature frame");
   if (channels != m->C)
     return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame has %d channels, the map was created with %d", channels,
                 m->C);
   if (((uintptr_t)features) & 15) return fail(NVBX_ERR_INVALID_ARGUMENT, "feature frame must be 16-byte aligned");
+  if (m->async && !t_async_worker) {
+    AsyncJob j{1, map_id, features, height, width, channels, mask, {}, fx, fy, cx, cy, stream_v};
+    std::memcpy(j.T, T_L_C_rm, sizeof(j.T));
+    m->async->push(j);
+    return NVBX_OK;
+  }
   return integrate_features_impl(m, map_id, features, nullptr, 0, height, width, mask, T_L_C_rm, fx, fy, cx, cy,
                                  stream_v);
 }
+
+}  // extern "C"
+void AsyncEnqueue::loop() {
+  t_async_worker = true;
+  std::unique_lock<std::mutex> lk(mu_);
+  for (;;) {
+    cv_work_.wait(lk, [this] { return stop_ || !q_.empty(); });
+    if (q_.empty()) return;  // stop requested and nothing left to issue
+    const AsyncJob j = q_.front();
+    q_.pop_front();
+    const bool skip = rc_ != 0;  // after a failure the frames behind it are dropped, the error is reported by flush()
+    lk.unlock();
+    cv_room_.notify_one();
+    int rc = NVBX_OK;
+    if (!skip)
+      rc = j.kind == 0 ? nvbx_integrate_depth(m_, j.map_id, j.image, j.height, j.width, j.mask, j.T, j.fx, j.fy, j.cx,
+                                              j.cy, j.stream)
+                       : nvbx_integrate_features(m_, j.map_id, j.image, j.height, j.width, j.channels, j.mask, j.T, j.fx,
+                                                 j.fy, j.cx, j.cy, j.stream);
+    lk.lock();
+    if (rc < 0 && rc_ == 0) {
+      rc_ = rc;
+      err_ = g_last_error;  // this thread's message
+    }
+    if (--outstanding_ == 0) cv_done_.notify_all();
+  }
+}
+extern "C" {
 
 int nvbx_integrate_features_lowres(nvbx_mapper* m, int map_id, const void* lowres, int low_h, int low_w, int low_c,
                                    int dtype, int layout, int kernel, int height, int width, const void* mask,
@@ -1653,17 +1810,22 @@ int nvbx_integrate_frame_host(nvbx_mapper* m, int map_id, const float* depth_hos
 
 int nvbx_set_pipelining(nvbx_mapper* m, int on) {
   if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper");
+  if (on < 0 || on > 2) return fail(NVBX_ERR_INVALID_ARGUMENT, "pipelining mode %d (0: off, 1: on, 2: on + asynchronous enqueue)", on);
+  if (int frc = async_flush(m)) return frc;
+  if (on != 2) m->async.reset();
   if (!on)
     for (auto& mp : m->maps) {
       int rc = pipeline_drain(*mp);
       if (rc) return rc;
-      mp->gather_pending[0] = mp->gather_pending[1] = false;
+      for (int r = 0; r < kFrameRing; ++r) mp->gather_pending[r] = false;
     }
   m->pipelining = on != 0;
+  if (on == 2 && !m->async) m->async.reset(new AsyncEnqueue(m));
   return NVBX_OK;
 }
 int nvbx_pipeline_join(nvbx_mapper* m, int map_id, void* stream_v) {
   if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper");
+  if (int frc = async_flush(m)) return frc;
   if (map_id < 0) {
     for (int i = 0; i < (int)m->maps.size(); ++i) {
       int rc = pipeline_join(*m->maps[i], (cudaStream_t)stream_v);
@@ -1740,6 +1902,7 @@ static int decay_one(nvbx_mapper* m, Map& mp, cudaStream_t stream) {
 
 int nvbx_decay(nvbx_mapper* m, int map_id, void* stream_v) {
   if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper handle");
+  if (int frc = async_flush(m)) return frc;
   if (map_id < 0) {
     for (int i = 0; i < (int)m->maps.size(); ++i) {
       int rc = nvbx_decay(m, i, stream_v);
@@ -1755,6 +1918,7 @@ int nvbx_decay(nvbx_mapper* m, int map_id, void* stream_v) {
 
 int nvbx_clear(nvbx_mapper* m, int map_id, void* stream_v) {
   if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper handle");
+  if (int frc = async_flush(m)) return frc;
   if (map_id < 0) {
     for (int i = 0; i < (int)m->maps.size(); ++i) {
       int rc = nvbx_clear(m, i, stream_v);
@@ -2184,6 +2348,7 @@ int nvbx_reset_counters(nvbx_mapper* m, int map_id, void* stream_v) {
   Map& mp = *m->maps[map_id];
   if ((rc = pipeline_join(mp, (cudaStream_t)stream_v))) return rc;
   CUDA_TRY(cudaMemsetAsync(mp.d_ctrl->counters, 0, sizeof(unsigned long long) * kCntNum, (cudaStream_t)stream_v));
+  mp.dev.seq = 0;  // the timeline stamps of profile builds are numbered from here
   return NVBX_OK;
 }
 
@@ -2303,6 +2468,7 @@ int nvbx_set_gather_tuning(int variant, int dyn_permille, int ticket_units) {
 
 int nvbx_set_kernel_timing(nvbx_mapper* m, int enabled) {
   if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper handle");
+  if (int frc = async_flush(m)) return frc;
   m->timing = enabled != 0;
   g_timing_mode = enabled;
   return NVBX_OK;
@@ -2310,6 +2476,7 @@ int nvbx_set_kernel_timing(nvbx_mapper* m, int enabled) {
 
 int64_t nvbx_kernel_timing_report(nvbx_mapper* m, char* json, int64_t capacity) {
   if (!m || !json || capacity <= 2) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad timing report buffer");
+  if (int frc = async_flush(m)) return frc;
   CUDA_TRY(cudaSetDevice(m->device));
   std::vector<std::pair<std::string, std::pair<double, long long>>> agg;
   std::lock_guard<std::mutex> recs_guard(g_launch_recs_mu);
@@ -2344,6 +2511,7 @@ int64_t nvbx_kernel_timing_report(nvbx_mapper* m, char* json, int64_t capacity) 
 }
 int nvbx_get_kernel_timing(nvbx_mapper* m, int which, double* total_ms, int64_t* launches) {
   if (!m || which < 0 || which > 1) return fail(NVBX_ERR_INVALID_ARGUMENT, "bad timing query");
+  if (int frc = async_flush(m)) return frc;
   CUDA_TRY(cudaSetDevice(m->device));
   double sum = 0.0;
   int64_t n = 0;
@@ -2403,11 +2571,25 @@ int64_t nvbx_debug_last_block_list(nvbx_mapper* m, int map_id, int which, int32_
 
 int nvbx_debug_profile_stamps(nvbx_mapper* m, uint64_t* out, int reset) {
   if (!m) return fail(NVBX_ERR_INVALID_ARGUMENT, "null mapper handle");
+  if (int frc = async_flush(m)) return frc;
 #ifdef NVBX_PROFILE_COUNTERS
   CUDA_TRY(cudaSetDevice(m->device));
   CUDA_TRY(cudaDeviceSynchronize());
   constexpr int n = 64 * 2 * kProfKernels;
   if (out) CUDA_TRY(cudaMemcpyFromSymbol(out, g_prof, n * sizeof(unsigned long long)));
+  if (out && getenv("NVBX_PROF_CTAS")) {  // per-CTA view of the raycast kernel of the last frames (stderr)
+    static unsigned long long cta[4][256][5];
+    CUDA_TRY(cudaMemcpyFromSymbol(cta, g_prof_cta, sizeof(cta)));
+    for (int fr = 0; fr < 4; ++fr) {
+      unsigned long long t0 = ~0ull;
+      for (int c = 0; c < 256; ++c)
+        if (cta[fr][c][0]) t0 = std::min(t0, cta[fr][c][0]);
+      for (int c = 0; c < 256; ++c)
+        if (cta[fr][c][0])
+          fprintf(stderr, "raycast frame%%4=%d cta %3d sm %3llu: entry %+7.2f marched %+7.2f wait-passed %+7.2f us\n", fr, c,
+                  cta[fr][c][4], (cta[fr][c][0] - t0) / 1e3, (cta[fr][c][1] - t0) / 1e3, (cta[fr][c][2] - t0) / 1e3);
+    }
+  }
   if (reset) {
     std::vector<unsigned long long> init(n);
     for (int i = 0; i < n; ++i) init[i] = (i & 1) ? 0ULL : ~0ULL;  // (min begin, max end) pairs

@@ -44,21 +44,18 @@ __device__ __forceinline__ void count_add(const MapDev& m, int id, unsigned long
 // ---- pipeline timeline (NVBX_PROFILE_COUNTERS builds; tools/pipeline_timeline.py) ------------------
 // Every kernel of a frame stamps %globaltimer when its first CTA passes griddepcontrol.wait and when its last
 // CTA ends, into g_prof[frame & 63][kernel]: what the PDL-chained pipeline really looks like in steady state,
-// which neither isolated event timings nor a serialising profiler can show.  The frame number is read from
-// counters that are stable while the stamping kernel runs (see prof_seq_*).
+// which neither isolated event timings nor a serialising profiler can show.  The frame number is the host's count
+// of feature frames enqueued so far (MapDev::seq / RaycastFrame::seq), so kernels of different frames that run
+// side by side on the pipelining streams stamp their own rows.
 enum { kProfRaycast = 0, kProfTsdf, kProfTrace, kProfGeometry, kProfGather, kProfRaycastPre, kProfKernels = 8 };
 #ifdef NVBX_PROFILE_COUNTERS
 __device__ unsigned long long g_prof[64 * 2 * kProfKernels];
+// per-CTA stamps of the raycast kernel (entry, march done, wait passed, exit) + SM id, frames mod 4 (NVBX_PROF_CTAS dump)
+__device__ unsigned long long g_prof_cta[4][256][5];
 __device__ __forceinline__ unsigned long long prof_now() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
-}
-__device__ __forceinline__ int prof_seq_early(const Ctrl* c) {  // raycast / tsdf / trace of frame i: i feature frames done
-  return (int)*reinterpret_cast<const volatile unsigned long long*>(&c->counters[kCntFeatureFrames]);
-}
-__device__ __forceinline__ int prof_seq_late(const Ctrl* c) {  // geometry / gather of frame i: i + 1 depth frames done
-  return (int)*reinterpret_cast<const volatile unsigned long long*>(&c->counters[kCntDepthFrames]) - 1;
 }
 __device__ __forceinline__ void prof_begin(int seq, int k, unsigned long long t) {
   atomicMin(&g_prof[((seq & 63) * kProfKernels + k) * 2], t);
@@ -128,11 +125,12 @@ struct RaycastFrame {
   float shifted[3];  // s - start
   int lin0;          // linear (aliased) grid index of the start block
   int tiles_x, n_tiles;
-  const Ctrl* ctrl;  // profile builds: frame number for the timeline stamps
+  int seq;           // profile builds: frame number for the timeline stamps (feature frames enqueued so far)
 };
 
 template <bool SMEM>
-__global__ void __launch_bounds__(256) k_raycast_mark(RaycastFrame f, unsigned* gbits, int* entry_count) {
+__global__ void __launch_bounds__(256) k_raycast_mark(RaycastFrame f, unsigned* gbits, int* entry_count,
+                                                      int flush_early, unsigned flush_seq, const unsigned* clean_seq) {
   // SMEM: the rays are marched BEFORE griddepcontrol.wait, i.e. while the previous kernels of the stream (the
   // last frame's feature gather) drain.  Until the wait this kernel reads only its arguments and the caller's
   // depth image and writes only shared memory; the depth image was produced by an operation that is not one of
@@ -208,10 +206,48 @@ __global__ void __launch_bounds__(256) k_raycast_mark(RaycastFrame f, unsigned* 
 #ifdef NVBX_PROFILE_COUNTERS
   const unsigned long long prof_marched = prof_now();
 #endif
+#ifdef NVBX_PROFILE_COUNTERS
+  if (threadIdx.x == 0 && blockIdx.x < 256) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* r = g_prof_cta[f.seq & 3][blockIdx.x];
+    r[0] = prof_entry;
+    r[1] = prof_marched;
+    r[4] = smid;
+  }
+#endif
   if (SMEM) {
+    // The marks go to one third of a triple-buffered bitmap (flush_early): this third was last read two depth
+    // frames ago and is wiped by the TSDF kernel of the PREVIOUS depth frame, which publishes Ctrl::bitmap_clean_seq
+    // when it is done.  If that has happened (practically always: the wipe is the first thing that kernel does) the
+    // marks are flushed right here, before the wait, under the tail of the preceding kernels; if not, after it.
+    __shared__ int s_early;
+    if (threadIdx.x == 0) {
+      int ok = 0;
+      if (flush_early) {  // wrap-safe: the counter runs for the life of the map
+        ok = (int)(*reinterpret_cast<const volatile unsigned*>(clean_seq) - flush_seq) >= 0;
+        __threadfence();
+      }
+      s_early = ok;
+    }
     __syncthreads();
+    const bool early = s_early != 0;
+    if (early) {
+      for (int w = threadIdx.x; w < n_words; w += 256) {
+        const unsigned v = s_bits[w];
+        if (v && (__ldcg(&gbits[w]) & v) != v) atomicOr(&gbits[w], v);
+      }
+      // This CTA is done.  Only CTA 0 stays to sit out the wait: the grid then still completes after its predecessor
+      // (the next kernel's own wait relies on that order), while every other CTA hands its registers and thread
+      // slots back at once instead of parking on them, and CTAs that did not fit on the machine at launch get
+      // their turn long before the wait is over.
+      if (blockIdx.x != 0) return;
+    }
     pdl_wait();
-    PROF_BEGIN(prof_seq_early(f.ctrl), kProfRaycast);
+#ifdef NVBX_PROFILE_COUNTERS
+    if (threadIdx.x == 0 && blockIdx.x < 256) g_prof_cta[f.seq & 3][blockIdx.x][2] = prof_now();
+#endif
+    PROF_BEGIN(f.seq, kProfRaycast);
 #ifdef NVBX_PROFILE_COUNTERS
     if (threadIdx.x == 0) {
       prof_begin(prof_seq_, kProfRaycastPre, prof_entry);
@@ -219,9 +255,11 @@ __global__ void __launch_bounds__(256) k_raycast_mark(RaycastFrame f, unsigned* 
     }
 #endif
     if (blockIdx.x == 0 && threadIdx.x == 0) *entry_count = 0;
-    for (int w = threadIdx.x; w < n_words; w += 256) {
-      const unsigned v = s_bits[w];
-      if (v && (__ldcg(&gbits[w]) & v) != v) atomicOr(&gbits[w], v);
+    if (!early) {
+      for (int w = threadIdx.x; w < n_words; w += 256) {
+        const unsigned v = s_bits[w];
+        if (v && (__ldcg(&gbits[w]) & v) != v) atomicOr(&gbits[w], v);
+      }
     }
     PROF_END(kProfRaycast);
   }
@@ -319,27 +357,47 @@ __device__ __forceinline__ bool project_voxel(const Cam& cam, const Pose& T_C_L,
   return true;
 }
 
-// One voxel of one block (thread t of the CTA); returns 1 if the voxel was fused with a measurement.  *is_free: the
-// voxel was written by this frame and now holds (+truncation distance, weight > 1e-4) -- observed free space.
-__device__ __forceinline__ unsigned tsdf_update_voxel(const MapDev& m, const DepthFrame& f, int slot, bool is_new,
-                                                      int t, bool* is_free) {
+// One voxel of one block (thread t of the CTA), in two steps so that the depth sample -- which only needs the
+// block's INDEX -- can be in flight while the block's slot is still being looked up or allocated:
+//   tsdf_measure : project the voxel centre, read the depth pixel (and mask) it falls on;
+//   tsdf_fuse    : blend with the stored voxel; returns 1 if the voxel was fused with a measurement.  *is_free: the
+//                  voxel was written by this frame and now holds (+truncation distance, weight > 1e-4).
+struct VoxMeas {
+  float meas, vd;
+  bool have;    // a depth sample (not NaN) was read
+  bool active;  // mask
+};
+__device__ __forceinline__ VoxMeas tsdf_measure(const DepthFrame& f, float block_size, const int3 b, int t) {
   const int vx = t >> 6, vy = (t >> 3) & 7, vz = t & 7;
-  const int3 b = m.blk_index[slot];
+  VoxMeas r;
+  r.meas = r.vd = 0.0f;
+  r.have = false;
+  r.active = true;
+  float u, v;
+  if (!project_voxel(f.cam, f.T_C_L, block_size, f.max_depth, b, vx, vy, vz, &u, &v, &r.vd)) return r;
+  const int ui = (int)floorf(u), vi = (int)floorf(v);
+  if (ui < 0 || vi < 0 || ui >= f.cols || vi >= f.rows) return r;
+  r.meas = __ldg(f.depth + (size_t)vi * f.cols + ui);
+  if (isnan(r.meas)) return r;
+  r.active = (f.mask == nullptr) || __ldg(f.mask + (size_t)vi * f.cols + ui);
+  r.have = true;
+  return r;
+}
+__device__ __forceinline__ unsigned tsdf_fuse(const MapDev& m, const DepthFrame& f, int slot, bool is_new, int t,
+                                              const VoxMeas& vm, bool* is_free) {
   float2* vox = tsdf_block(m, slot) + t;
   bool write = is_new;
   float2 out = make_float2(0.0f, 0.0f);
   unsigned updated = 0;
+  // the stored voxel travels while the measurement is being judged (an existing block's payload is always readable)
+  float2 cur = make_float2(0.0f, 0.0f);
+  if (vm.have && !is_new) cur = *vox;
   do {
-    float u, v, vd;
-    if (!project_voxel(f.cam, f.T_C_L, m.block_size, f.max_depth, b, vx, vy, vz, &u, &v, &vd)) break;
-    const int ui = (int)floorf(u), vi = (int)floorf(v);
-    if (ui < 0 || vi < 0 || ui >= f.cols || vi >= f.rows) break;
-    const float meas = __ldg(f.depth + (size_t)vi * f.cols + ui);
-    if (isnan(meas)) break;
-    const bool active = (f.mask == nullptr) || __ldg(f.mask + (size_t)vi * f.cols + ui);
+    if (!vm.have) break;
+    const float meas = vm.meas, vd = vm.vd;
     if (meas <= 0.0f) {
       if (f.invalid_decay >= 0.0f && !is_new) {
-        out = *vox;
+        out = cur;
         out.y *= f.invalid_decay;
         write = true;
       }
@@ -347,8 +405,7 @@ __device__ __forceinline__ unsigned tsdf_update_voxel(const MapDev& m, const Dep
     }
     const float sdf = meas - vd;
     if (sdf < -f.trunc) break;
-    if (!active && sdf < f.trunc) break;
-    const float2 cur = is_new ? make_float2(0.0f, 0.0f) : *vox;
+    if (!vm.active && sdf < f.trunc) break;
     const float w_m = weighting(f.weighting_mode, meas, vd, f.trunc);
     float fused = fmaf(cur.x, cur.y, sdf * w_m) / (w_m + cur.y);   // FMUL + FFMA in the reference
     if (fused > 0.0f)
@@ -363,6 +420,11 @@ __device__ __forceinline__ unsigned tsdf_update_voxel(const MapDev& m, const Dep
   *is_free = write && out.x == f.trunc && out.y > 1e-4f;
   return updated;
 }
+__device__ __forceinline__ unsigned tsdf_update_voxel(const MapDev& m, const DepthFrame& f, int slot, bool is_new,
+                                                      int t, bool* is_free) {
+  const VoxMeas vm = tsdf_measure(f, m.block_size, m.blk_index[slot], t);
+  return tsdf_fuse(m, f, slot, is_new, t, vm, is_free);
+}
 // All 512 voxels free -> kBlockFreeBit of the slot (one barrier; every thread of the CTA calls this).
 __device__ __forceinline__ void publish_block_free(const MapDev& m, int slot, bool voxel_free) {
   const int all = __syncthreads_and(voxel_free);
@@ -376,8 +438,8 @@ __device__ __forceinline__ void publish_block_free(const MapDev& m, int slot, bo
 //   kViewFromSlots  : slot list written by k_view_compact_alloc (views whose bitmap exceeds kFusedBitmapWords)
 //   kViewFromBitmap : the marked bitmap itself -- compaction, find-or-allocate and the viewpoint-cache entry
 //                     are folded into this kernel (every CTA ranks the <= 32 768 cells redundantly in shared
-//                     memory and serves ranks blockIdx.x, blockIdx.x + gridDim.x, ...); the OTHER bitmap of
-//                     the double buffer is cleared for the next frame.  One launch less per depth frame.
+//                     memory and serves ranks blockIdx.x, blockIdx.x + gridDim.x, ...); the bitmap the depth
+//                     frame after next will mark (triple buffer) is wiped.  One launch less per depth frame.
 //   kViewFromEntry  : viewpoint-cache hit, the cached index list (view_calculator.cu:256-265); blocks are
 //                     (re-)allocated where required (projective_integrator_impl.cuh:288-291)
 enum ViewMode { kViewFromSlots = 0, kViewFromBitmap = 1, kViewFromEntry = 2 };
@@ -388,17 +450,19 @@ struct ViewSource {
   int* entry_count;       // list length (read in kViewFromSlots / kViewFromEntry, written in kViewFromBitmap)
   int3* entry_idx;        // cache entry index list (written in kViewFromBitmap, read in kViewFromEntry)
   const unsigned* bits;   // kViewFromBitmap
-  unsigned* clean_bits;   // kViewFromBitmap: the other half of the double buffer
+  unsigned* clean_bits;   // kViewFromBitmap: the third of the triple buffer that the depth frame after next marks
+  unsigned clean_seq;     // kViewFromBitmap: value published in Ctrl::bitmap_clean_seq once clean_bits is wiped
   ViewGrid g;
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(512, 3) k_tsdf_update(MapDev m, ViewSource src, DepthFrame f) {
+__global__ void __launch_bounds__(512, 4) k_tsdf_update(MapDev m, ViewSource src, DepthFrame f) {
   pdl_prologue();
-  PROF_BEGIN(prof_seq_early(m.ctrl), kProfTsdf);
+  PROF_BEGIN(m.seq, kProfTsdf);
   __shared__ int s_off[513];
   __shared__ int s_warp[17];
   __shared__ int s_slot;
+  __shared__ int3 s_b;
   const int t = threadIdx.x;
   unsigned updated = 0;
   int n = 0;
@@ -421,7 +485,12 @@ __global__ void __launch_bounds__(512, 3) k_tsdf_update(MapDev m, ViewSource src
       const int n_words = (src.g.n_cells + 31) >> 5;
       if (2 * t < n_words) w0 = src.bits[2 * t];
       if (2 * t + 1 < n_words) w1 = src.bits[2 * t + 1];
-      for (int w = blockIdx.x * 512 + t; w < kFusedBitmapWords; w += gridDim.x * 512) src.clean_bits[w] = 0u;
+      if (blockIdx.x == 0) {  // wipe the bitmap of the depth frame after next, then say so (k_raycast_mark)
+        for (int w = t; w < kFusedBitmapWords; w += 512) src.clean_bits[w] = 0u;
+        __threadfence();
+        __syncthreads();
+        if (t == 0) *reinterpret_cast<volatile unsigned*>(&m.ctrl->bitmap_clean_seq) = src.clean_seq;
+      }
       const int c = __popc(w0) + __popc(w1);
       int inc = c;
       const int lane = t & 31, warp = t >> 5;
@@ -471,6 +540,11 @@ __global__ void __launch_bounds__(512, 3) k_tsdf_update(MapDev m, ViewSource src
           z = b.z;
         }
       }
+      if (owner) s_b = make_int3(x, y, z);
+      __syncthreads();
+      // every thread: the depth sample of its voxel (needs the block's index only) flies while the owner thread
+      // finds or allocates the block's slot
+      const VoxMeas vm = tsdf_measure(f, m.block_size, s_b, t);
       if (owner) {
         bool is_new;
         int slot = acquire_slot(m, x, y, z, &is_new);
@@ -487,10 +561,10 @@ __global__ void __launch_bounds__(512, 3) k_tsdf_update(MapDev m, ViewSource src
       const int raw = s_slot;
       if (raw >= 0) {  // uniform per CTA
         bool vfree;
-        updated += tsdf_update_voxel(m, f, raw & kSlotMask, (raw & kNewFlag) != 0, t, &vfree);
+        updated += tsdf_fuse(m, f, raw & kSlotMask, (raw & kNewFlag) != 0, t, vm, &vfree);
         publish_block_free(m, raw & kSlotMask, vfree);
       }
-      __syncthreads();  // s_slot is rewritten by the next rank
+      __syncthreads();  // s_slot / s_b are rewritten by the next rank
     }
   }
   // accounting: one atomic per warp
@@ -672,6 +746,8 @@ struct TraceParams {
   float free_dist;  // the TSDF truncation distance: what every voxel of a kBlockFreeBit block holds
   int use_free;     // tuning knob (NVBX_TRACE_FREE): consult kBlockFreeBit
   int team;         // 1: eight lanes per ray (sphere_trace_team), trace CTAs cover 8 x 4 rays; 0: one thread per ray
+  int march;        // marching threads per trace CTA: 256 (16 x 16 rays) or 128 / 64 / 32 (8 columns x march / 8 rows;
+                    // the CTA's other warps only help to stage the workspace table): spreads the rays over more SMs
 };
 
 // floor(p / block_size) exactly as block_index_from_position computes it, without the IEEE division on
@@ -1002,7 +1078,7 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
 #ifdef NVBX_PROFILE_COUNTERS
   const long long t0 = clock64();
 #endif
-  PROF_BEGIN(prof_seq_early(m.ctrl), kProfTrace);
+  PROF_BEGIN(m.seq, kProfTrace);
   // this ring slot's item list: last read by the gather of frame i - kFrameRing, complete before we were enqueued
   if (blockIdx.x == 0 && threadIdx.x == 0 && color_parity == -1) m.ctrl->item_count[m.fp] = 0;
   // n_trace_ctas == 0: the synthetic depth image of this pose / camera / TSDF state is already in `image`
@@ -1011,10 +1087,23 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
     const int r = (blockIdx.x / trace_tiles_x) * 16 + ((threadIdx.x >> 3) & 15);
     const bool stage_ws = m.ws_cells > 0 && m.ws_cells <= kTraceSmemCells;
     if (stage_ws) {
-      for (int i = threadIdx.x; i < m.ws_cells; i += 256) {
-        int s = m.ws_slot[i];
-        if (tp.use_free && s >= 0 && (m.blk_layers[s] & kBlockFreeBit)) s |= kNewFlag;  // bit 30: observed free space
-        s_ws[i] = s;
+      // four cells per thread and round: the slot loads of a round fly together, then the layer-byte loads that depend
+      // on them (two L2 round trips per round instead of two per cell)
+      for (int i0 = threadIdx.x; i0 < m.ws_cells; i0 += 4 * 256) {
+        int sl[4];
+        uint8_t ly[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k * 256;
+          sl[k] = i < m.ws_cells ? m.ws_slot[i] : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ly[k] = (tp.use_free && sl[k] >= 0) ? m.blk_layers[sl[k]] : (uint8_t)0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k * 256;
+          if (i < m.ws_cells) s_ws[i] = (ly[k] & kBlockFreeBit) ? (sl[k] | kNewFlag) : sl[k];  // bit 30: observed free space
+        }
       }
       __syncthreads();
     }
@@ -1027,7 +1116,12 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
       return;
     }
     [[maybe_unused]] int n_steps = 0;
-    if (r < tp.rows && c < tp.cols) n_steps = sphere_trace_ray<SPEC>(m, tp, r, c, image, stage_ws ? s_ws : nullptr);
+    if (tp.march < 256) {
+      if ((int)threadIdx.x >= tp.march) return;
+      const int tc = (blockIdx.x % trace_tiles_x) * 8 + (threadIdx.x & 7);
+      const int tr = (blockIdx.x / trace_tiles_x) * (tp.march >> 3) + (threadIdx.x >> 3);
+      if (tr < tp.rows && tc < tp.cols) n_steps = sphere_trace_ray<SPEC>(m, tp, tr, tc, image, stage_ws ? s_ws : nullptr);
+    } else if (r < tp.rows && c < tp.cols) n_steps = sphere_trace_ray<SPEC>(m, tp, r, c, image, stage_ws ? s_ws : nullptr);
 #ifdef NVBX_PROFILE_COUNTERS
     {  // tuning aid: steps (sum / max over rays) and the slowest warp's cycles, one atomic set per warp
       const long long dt = clock64() - t0;
@@ -1163,7 +1257,7 @@ __global__ void __launch_bounds__(512) k_feature_geometry(MapDev m, const int* _
   const int C = m.C;
   unsigned long long n_updated = 0;
   if (blockIdx.x == 0 && t == 0) m.ctrl->gather_ticket[m.fp] = 0;  // consumed by this frame's k_feature_gather_dyn
-  PROF_BEGIN(prof_seq_late(m.ctrl), kProfGeometry);
+  PROF_BEGIN(m.seq, kProfGeometry);
 
   // Zero-fill the feature blocks allocated by this frame (blox_impl.h:92-97), every CTA taking an equal
   // slice of each, so that a 794 KB block costs each SM a few KB; the gather kernel runs after us.
@@ -1262,7 +1356,7 @@ template <int CH, int U, int CTAS>  // U: units in flight per warp; CTAS: reside
 __global__ void __launch_bounds__(256, CTAS) k_feature_gather(MapDev m, const FeatItem* __restrict__ items,
                                                               FeatFrame f, int last_chunk) {
   pdl_prologue();
-  PROF_BEGIN(prof_seq_late(m.ctrl), kProfGather);
+  PROF_BEGIN(m.seq, kProfGather);
   const int n_items = m.ctrl->item_count[m.fp];
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
@@ -1336,7 +1430,7 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_feature_gather_dyn(MapDev m, 
                                                                       int items_cap, FeatFrame f, int last_chunk,
                                                                       int dyn_permille, int tk) {
   pdl_prologue();
-  PROF_BEGIN(prof_seq_late(m.ctrl), kProfGather);
+  PROF_BEGIN(m.seq, kProfGather);
   const int lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * (THREADS >> 5);
   const int warp = blockIdx.x * (THREADS >> 5) + (threadIdx.x >> 5);
@@ -1483,7 +1577,7 @@ __global__ void __launch_bounds__(kTmaWarps * 32, 1) k_feature_gather_tma(MapDev
   extern __shared__ __align__(128) unsigned char s_stage[];
   __shared__ __align__(8) unsigned long long s_bar[kTmaWarps][NST];
   pdl_prologue();
-  PROF_BEGIN(prof_seq_late(m.ctrl), kProfGather);
+  PROF_BEGIN(m.seq, kProfGather);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long warps_total = (long long)gridDim.x * kTmaWarps;
   const long long warp = (long long)blockIdx.x * kTmaWarps + wid;

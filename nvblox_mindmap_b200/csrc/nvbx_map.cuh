@@ -104,6 +104,7 @@ struct Ctrl {
                        // clears the other half, so no kernel both reads and resets the same counter)
   int last_cband_count;
   int gather_ticket[kFrameRing];  // k_feature_gather_dyn's work ticket; zeroed by k_feature_geometry
+  unsigned bitmap_clean_seq;  // small-view bitmaps (triple buffer): thirds of depth frames <= this number are wiped
   unsigned long long counters[kCntNum];
 };
 
@@ -141,6 +142,7 @@ struct MapDev {
   float voxel_size_inv;
   int C;    // feature channels
   int row;  // halves per feature voxel row (C + 8)
+  int seq;  // feature frames enqueued so far (host count; labels the timeline stamps of profile builds)
   int fp;   // ring slot of the current feature frame (frame number mod kFrameRing): which copy of the per-frame Ctrl
             // counters / lists it uses
 };

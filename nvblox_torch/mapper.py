@@ -6,6 +6,7 @@ wrapper; every method forwards to one C-ABI entry point of libnvbx.so (include/n
 run stream-ordered with the caller's torch work.  There is no CPU fallback: constructing a Mapper
 without a Blackwell GPU raises.
 """
+import collections
 import ctypes as C
 from enum import Enum
 from typing import List, Optional
@@ -20,6 +21,10 @@ from nvblox_torch.layer import ColorLayer, FeatureLayer, TsdfLayer
 from nvblox_torch.mapper_params import MapperParams
 from nvblox_torch.mesh import ColorMesh, FeatureMesh
 from nvblox_torch.projective_integrator_types import ProjectiveIntegratorType
+
+
+_HOLD_PIPELINED = 12   # input tensors kept alive per map while pipelining: (frame + mask) x (ring of 4 + 2)
+_HOLD_ASYNC = 48       # ... with asynchronous enqueue: (depth, mask, features, mask) x (ring of 4 + 8 queued)
 
 
 class QueryType(Enum):
@@ -121,7 +126,8 @@ class Mapper:
                                           C.byref(handle)))
         self._handle = handle
         self._pipelining = False
-        self._held_frames = {}    # mapper_id -> the last two feature frames (kept alive while pipelining)
+        self._async_enqueue = False
+        self._held_frames = {}    # mapper_id -> deque of input tensors kept alive while pipelining (see _hold)
 
     def __del__(self):
         h = getattr(self, '_handle', None)
@@ -169,6 +175,8 @@ class Mapper:
         _capi.check(self._lib.nvbx_integrate_depth(
             self._handle, mapper_id, depth_frame.data_ptr(), depth_frame.shape[0], depth_frame.shape[1], mask_ptr,
             _pose16(t_w_c), fx, fy, cx, cy, self._stream()))
+        if self._async_enqueue:
+            self._hold(mapper_id, depth_frame, mask_frame)
 
     def add_color_frame(self,
                         color_frame: torch.Tensor,
@@ -202,11 +210,7 @@ class Mapper:
             self._handle, mapper_id, feature_frame.data_ptr(), feature_frame.shape[0], feature_frame.shape[1],
             feature_frame.shape[2], mask_ptr, _pose16(t_w_c), fx, fy, cx, cy, self._stream()))
         if self._pipelining:
-            # the gather of this frame runs on the map's own stream and reads the frame until the second-next feature
-            # call has returned: keep the tensor alive so that the caching allocator cannot hand its memory out
-            held = self._held_frames.setdefault(mapper_id, [])
-            held.append(feature_frame)
-            del held[:-2]
+            self._hold(mapper_id, feature_frame, mask_frame)
 
     def integrate_frames(self, depth_frames, feature_frames, poses, intrinsics, mapper_id: int = 0,
                          depth_masks=None, feature_masks=None) -> None:
@@ -247,18 +251,42 @@ class Mapper:
             keep.append((d, f, dm, Tc))
         _capi.check(self._lib.nvbx_integrate_frames_batch(jobs, n, 1))
         if self._pipelining:
-            held = self._held_frames.setdefault(mapper_id, [])
-            held.extend(t[1] for t in keep if t[1] is not None)
-            del held[:-2]
+            for d, f, dm, _ in keep[-(_HOLD_ASYNC // 2):]:
+                self._hold(mapper_id, f, None if feature_masks is None else feature_masks[0])
+                if self._async_enqueue:
+                    self._hold(mapper_id, d, dm)
 
-    def set_pipelining(self, on: bool = True) -> None:
+    def _hold(self, mapper_id: int, *tensors) -> None:
+        """Keep input tensors alive while the library may still read them outside torch's stream order: the gather of
+        a feature frame runs on the map's own stream until up to four feature frames later (the ring depth of
+        nvbx_map.cuh), and with asynchronous enqueue up to eight more calls may still be waiting to be issued.  Without
+        this the caching allocator could hand the memory of a dropped tensor to a new one."""
+        held = self._held_frames.get(mapper_id)
+        n = _HOLD_ASYNC if self._async_enqueue else _HOLD_PIPELINED
+        if held is None or held.maxlen != n:
+            held = collections.deque(held or (), maxlen=n)
+            self._held_frames[mapper_id] = held
+        for t in tensors:
+            if t is not None:
+                held.append(t)
+
+    def set_pipelining(self, on: bool = True, async_enqueue: bool = False) -> None:
         """(ours) Overlap the memory-bound gather of feature frame i with the latency-bound depth path of frame i + 1
         (include/nvbx_c_api.h: nvbx_set_pipelining).  Results are bit-identical.  While it is on, a feature frame must
-        not be overwritten IN PLACE until two more feature frames have been added to that map, or until a call that
+        not be overwritten IN PLACE until four more feature frames have been added to that map, or until a call that
         reads the feature layer (decay / clear / mesh / block views / queries / `pipeline_join`); the frames
-        themselves are kept alive here.  Meant for replay / datagen loops that hold their frames."""
-        _capi.check(self._lib.nvbx_set_pipelining(self._handle, 1 if on else 0))
+        themselves are kept alive here.  Meant for replay / datagen loops that hold their frames.
+
+        `async_enqueue`: add_depth_frame / add_feature_frame only validate and queue their arguments; a worker thread
+        of the library issues the CUDA work in order (the ~20 us of launches per frame leave the calling thread, so a
+        Python loop keeps up with the ~35 us the device needs).  Every other method of the Mapper first waits for the
+        queue, so the map reads the same; but a frame is no longer ordered against the CALLER'S OWN later work on the
+        stream: depth frames and masks, too, must stay unmodified until the next joining call, and
+        `torch.cuda.synchronize()` alone does not wait for queued frames -- call `pipeline_join()` first.  An error in
+        a queued frame is raised by the next joining call."""
+        _capi.check(self._lib.nvbx_set_pipelining(self._handle, (2 if async_enqueue else 1) if on else 0))
         self._pipelining = bool(on)
+        self._async_enqueue = bool(on and async_enqueue)
         if not on:
             self._held_frames = {}
 

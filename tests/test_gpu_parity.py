@@ -411,16 +411,18 @@ def test_empty_and_degenerate_inputs():
     assert pair.check_tsdf() == 0 and pair.check_mesh() == 0
 
 
+@pytest.mark.parametrize('async_enqueue', [False, True])
 @pytest.mark.parametrize('alpha', [1.0, 0.8])
-def test_pipelined_frames_are_bit_identical(alpha):
+def test_pipelined_frames_are_bit_identical(alpha, async_enqueue):
     """Frame pipelining (Mapper.set_pipelining: the gather of frame i on the map's own stream, the depth path of
     frame i + 1 underneath it) changes nothing in the map: TSDF, features (alpha < 1 blends with what the previous
-    frames' gathers wrote), per-frame band lists, mesh, with decay / queries / block views joining in between."""
+    frames' gathers wrote), per-frame band lists, mesh, with decay / queries / block views joining in between.
+    async_enqueue: the frames are queued and issued by the mapper's worker thread (nvbx_set_pipelining(m, 2))."""
     import torch
     from nvblox_torch.mapper import QueryType
     mp, op = make_params(workspace=S.WS_CUBE_STACKING, alpha=alpha, strict=True)
     pair = Pair(0.02, 768, mp, op)
-    pair.gpu.set_pipelining(True)
+    pair.gpu.set_pipelining(True, async_enqueue=async_enqueue)
     H = W = 128
     K = S.intrinsics(W, H)
     frames = [S.feature_frame(H, W, 768, 900 + i) for i in range(3)]

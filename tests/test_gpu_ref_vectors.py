@@ -22,13 +22,13 @@ def _bits(a):
     return a.view(np.uint8).reshape(a.shape + (a.dtype.itemsize,)) if a.dtype.kind == 'f' else a
 
 
-@pytest.mark.parametrize('pipelining', [False, True])
+@pytest.mark.parametrize('pipelining', [False, True, 'async'])
 @pytest.mark.parametrize('name', list(RS.SCENARIOS))
 def test_product_reproduces_reference_kernels(name, pipelining):
     gold = np.load(os.path.join(GOLD, f'ref_nvcc_pipeline_{name}.npz'))
     sc = RS.SCENARIOS[name]
     be = RS.GpuBackend(sc, 16)
-    be.m.set_pipelining(pipelining)
+    be.m.set_pipelining(bool(pipelining), async_enqueue=(pipelining == 'async'))
     mine = RS.run_scenario(sc, 16, be)
     for k in mine:
         assert mine[k].shape == gold[k].shape, f'{name}/{k}: shape {mine[k].shape} vs reference {gold[k].shape}'

@@ -58,6 +58,36 @@ def main():
           f'add_depth_frame {t_py_d:.1f} (C ABI alone {t_c_d:.1f}), add_feature_frame {t_py_f:.1f} (C ABI alone {t_c_f:.1f}), '
           f'empty ctypes call {t_noop:.2f}')
 
+    # The whole replay in ONE C call (jobs marshalled beforehand): the device's own frame period, with the host
+    # enqueueing natively -- what the per-frame Python surface can at best approach.
+    from nvblox_mindmap_b200.params import NvbxFrameJob
+    n_seq = 512
+    jobs = (NvbxFrameJob * n_seq)()
+    for k in range(n_seq):
+        i = k % n
+        j = jobs[k]
+        j.mapper, j.map_id, j.stream = h.value, 0, s
+        j.height, j.width, j.channels = bench.H, bench.W, bench.C_FEAT
+        j.depth, j.features = dptr[i], fptr
+        C.memmove(j.T_L_C, poses[i].contiguous().data_ptr(), 64)
+        j.fx, j.fy, j.cx, j.cy = fx, fy, cx, cy
+    for pipe in (0, 1):
+        mapper.set_pipelining(bool(pipe))
+        best = (1e9, 0.0)
+        for _ in range(4):
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            t0 = time.perf_counter()
+            rc = lib.nvbx_integrate_frames_batch(jobs, n_seq, 1)
+            th = time.perf_counter() - t0
+            assert rc == 0
+            mapper.pipeline_join()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, (a.elapsed_time(b) * 1e3 / n_seq, th * 1e6 / n_seq))
+        print(f'one C call for {n_seq} frames, pipelining {pipe}: device {best[0]:.2f} us per frame, host {best[1]:.2f} us per frame')
+
 
 if __name__ == '__main__':
     main()

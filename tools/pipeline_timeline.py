@@ -29,7 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--frames', type=int, default=48)
     ap.add_argument('--out', default=None)
-    ap.add_argument('--pipelining', type=int, default=1)
+    ap.add_argument('--pipelining', type=int, default=1, help='0 off, 1 on, 2 on + asynchronous enqueue')
     args = ap.parse_args()
     import torch
     import bench
@@ -40,7 +40,7 @@ def main():
     constants.set_feature_array_num_elements(bench.C_FEAT)
     mp, _ = bench.mapper_params()
     mapper = Mapper(voxel_sizes_m=bench.VOXEL, mapper_parameters=mp, device=0)
-    mapper.set_pipelining(bool(args.pipelining))
+    mapper.set_pipelining(bool(args.pipelining), async_enqueue=(args.pipelining == 2))
     n_warm = 16
     n = n_warm + args.frames
     assert args.frames <= 56
