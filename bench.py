@@ -420,6 +420,19 @@ def run_ours(args, rank, world, local_rank):
         eb.record()
         torch.cuda.synchronize()
         value_no_pipe = n_np / (ea.elapsed_time(eb) / 1e3)
+        # ... and with pipelining but synchronous enqueue (the calling Python thread issues the CUDA work itself)
+        mapper.set_pipelining(True, async_enqueue=False)
+        for i in range(args.warmup):
+            step(i)
+        mapper.pipeline_join()
+        torch.cuda.synchronize()
+        ea.record()
+        for i in range(args.warmup, args.warmup + n_np):
+            step(i)
+        mapper.pipeline_join()
+        eb.record()
+        torch.cuda.synchronize()
+        value_sync_enqueue = n_np / (ea.elapsed_time(eb) / 1e3)
         mapper.set_pipelining(bool(args.pipelining), async_enqueue=(args.pipelining == 2))
         batched = batched_maps_stage(depths, poses, feats, K_t, local_rank)
         drill = drill_in_box_stage(lib, feats, h_feat, local_rank, peak)
@@ -475,11 +488,16 @@ def run_ours(args, rank, world, local_rank):
                       'per_kernel_us_in_pipeline': per_kernel, 'export_stage': export,
                       'fused_upsample': fused, 'batched_maps_one_gpu': batched, 'drill_in_box': drill,
                       'batched_64_maps': batched64, 'stress': stress, 'cold_start': cold,
-                      'pipelining': {'on': bool(args.pipelining),
+                      'pipelining': {'mode': int(args.pipelining),
                                      'frames_per_s_without': value_no_pipe,
-                                     'note': 'value is measured with Mapper.set_pipelining(True): every frame of the '
-                                             'replay stays resident, so the gather of frame i may run under the depth '
-                                             'path of frame i + 1 (bit-identical map); frames_per_s_without is the '
+                                     'frames_per_s_synchronous_enqueue': value_sync_enqueue,
+                                     'host_wait_for_ring_slot': host_wait,
+                                     'note': 'value is measured with Mapper.set_pipelining(True, async_enqueue=True) '
+                                             '(mode 2): every frame of the replay stays resident and unmodified, so '
+                                             'geometry + gather of frame i run on the map\'s own streams above the depth '
+                                             'path of frame i + 1, and the CUDA calls are issued by the mapper\'s worker '
+                                             'thread (bit-identical map); frames_per_s_synchronous_enqueue = mode 1 (the '
+                                             'Python thread issues them itself: host-bound); frames_per_s_without = the '
                                              'default mode of the drop-in (frames may be freed right after the call)'},
                       'counters_per_step': {k: v / args.steps for k, v in counters.items()
                                             if isinstance(v, (int, float))}},
@@ -856,8 +874,8 @@ def cold_start_stage(depths, poses, feats, K_t, local_rank, n=8):
 
 def ncu_traffic_bytes():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary
-    (profiles/r02p_feature_gather.md: dram__bytes_read.sum + dram__bytes_write.sum, first capture)."""
-    path = os.path.join(ROOT, 'profiles', 'r02p_feature_gather.md')
+    (profiles/r02z_feature_gather.md: dram__bytes_read.sum + dram__bytes_write.sum, first capture)."""
+    path = os.path.join(ROOT, 'profiles', 'r02z_feature_gather.md')
     try:
         rd = wr = None
         for line in open(path):
@@ -867,7 +885,7 @@ def ncu_traffic_bytes():
             if len(cells) > 3 and cells[1] == 'dram__bytes_write.sum' and wr is None:
                 wr = float(cells[2]) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}[cells[3]]
         if rd is not None and wr is not None:
-            return rd + wr, 'profiles/r02p_feature_gather.md (ncu --set full, one launch of the same workload)'
+            return rd + wr, 'profiles/r02z_feature_gather.md (ncu --set full, one launch of the same workload)'
     except Exception:
         pass
     return None, None

@@ -241,6 +241,12 @@ __global__ void __launch_bounds__(256) k_raycast_mark(RaycastFrame f, unsigned* 
       // (the next kernel's own wait relies on that order), while every other CTA hands its registers and thread
       // slots back at once instead of parking on them, and CTAs that did not fit on the machine at launch get
       // their turn long before the wait is over.
+#ifdef NVBX_PROFILE_COUNTERS
+      if (threadIdx.x == 0) {  // pre-wait row of the timeline: first entry .. last flush over ALL CTAs
+        prof_begin(f.seq, kProfRaycastPre, prof_entry);
+        prof_end(f.seq, kProfRaycastPre, prof_now());
+      }
+#endif
       if (blockIdx.x != 0) return;
     }
     pdl_wait();

@@ -21,8 +21,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ.setdefault('NVBX_PROFILE', '1')
 
-NAMES = ['raycast (post-wait: bitmap flush)', 'tsdf_update', 'trace_and_band', 'feature_geometry', 'feature_gather',
-         'raycast (pre-wait: ray march)']
+NAMES = ['raycast (post-wait: CTA 0 only once the marks are flushed early)', 'tsdf_update', 'trace_and_band', 'feature_geometry', 'feature_gather',
+         'raycast (pre-wait: ray march + early flush, all CTAs)']
 
 
 def main():
