@@ -189,6 +189,20 @@ SCENARIOS = {
                                                  ((0.3, -0.5, 1.2), (0.3, 0.1, 0.0)), ((2.5, 2.0, 3.5), (0.3, 0.1, 0.0))])],
                             alpha=0.3, max_dist=3.0, raycast_sub=4, decay=0.9, weighting='kInverseSquareDropoffWeight',
                             color=True, mask_every=3, invalid_decay=0.5, holes=True),
+    # stick-in-bin shape (MM/mapping/nvblox_mapper_constants.py:72-80): a workspace 4-5 m AWAY from the origin (block
+    # indices 23..34: the float arithmetic of block / voxel indexing runs in another binade), 2 cm, orbit + fixed camera
+    'stick_in_bin': dict(voxel_size=0.02, workspace=((3.7, 1.5, 0.44), (5.5, 3.2, 1.25)),
+                         scene=dict(plane_z=0.5, spheres=[(4.6, 2.35, 0.6, 0.11)]), W=48, H=48, steps=3,
+                         cameras=[dict(orbit=dict(stride=9, radius=0.42, height=1.02, center=(4.6, 2.35, 0.58))),
+                                  dict(fixed=((4.05, 1.9, 1.15), (4.6, 2.35, 0.55)))],
+                         alpha=1.0, max_dist=5.0, raycast_sub=1, decay=0.98, weighting='kInverseSquareWeight',
+                         color=True, mask_every=0, invalid_decay=-1.0),
+    # mug-in-drawer shape (nvblox_mapper_constants.py:45-53): tall workspace, decay 0.999, non-square frames, raycast
+    # subsampling 2, constant weighting, masks every step
+    'mug_in_drawer': dict(voxel_size=0.02, workspace=((-0.2, -0.8, -0.2), (0.9, 0.8, 1.0)), scene=S.S_TABLE, W=64, H=48,
+                          steps=4, cameras=[dict(orbit=dict(stride=11, radius=0.5, height=0.62))],
+                          alpha=1.0, max_dist=5.0, raycast_sub=2, decay=0.999, weighting='kConstantWeight',
+                          color=False, mask_every=1, invalid_decay=-1.0),
 }
 
 

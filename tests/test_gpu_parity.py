@@ -442,7 +442,12 @@ def test_pipelined_frames_are_bit_identical(alpha, async_enqueue):
     assert pair.check_tsdf() > 0
     assert pair.check_features(max_ulp=0) > 0
     assert pair.check_mesh() > 0
-    # switching it off drains the gather stream; further frames keep matching
+    import ctypes as C
+    from nvblox_mindmap_b200 import _capi
+    waits, wait_ns = C.c_int64(-1), C.c_int64(-1)
+    _capi.load().nvbx_pipeline_wait_stats(C.byref(waits), C.byref(wait_ns))
+    assert waits.value >= 0 and wait_ns.value >= 0     # (how often the host had to wait for a ring slot: tuning aid)
+    # switching it off drains the queue and the map's streams; further frames keep matching
     pair.gpu.set_pipelining(False)
     T = S.orbit_pose(40)
     pair.depth(S.render_depth(K, H, W, T, **S.S_TABLE), T, K)
