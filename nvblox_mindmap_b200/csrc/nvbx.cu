@@ -1394,8 +1394,10 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
   // where every step depends on the value just read, so the extra lanes only add work.  Kept selectable.
   static const int team = env_int("NVBX_TRACE_TEAM", 0);
   tp.team = team;
+  static const int cache_blocks = env_int("NVBX_TRACE_CACHE", 0);  // tuning knob: 0 scalar march, 2 / 4 blocks per warp in smem
+  tp.cache_blocks = (!tp.team && (cache_blocks == 2 || cache_blocks == 4)) ? cache_blocks : 0;
   static const int march = env_int("NVBX_TRACE_MARCH", 256);
-  tp.march = (march == 128 || march == 64 || march == 32) ? march : 256;
+  tp.march = (!tp.cache_blocks && (march == 128 || march == 64 || march == 32)) ? march : 256;
   // synthetic depth already rendered for exactly this pose / camera / TSDF state (the other appearance frame of
   // the same step): skip the sphere tracing, keep the band selection
   Map::SynthKey& key = mp.synth_key;
@@ -1417,9 +1419,18 @@ int appearance_prepare(nvbx_mapper* m, Map& mp, ViewCache& cache, int height, in
     const int n_band = std::max(1, std::min(n_tiles, persistent_grid(m, 4)));
     key.valid = false;  // a failed launch leaves no valid image behind
     static const int spec = env_int("NVBX_TRACE_SPEC", 1), ilp = env_int("NVBX_BAND_ILP", 2);
+    const size_t tb_smem = tp.cache_blocks ? (size_t)8 * tp.cache_blocks * (kVoxelsPerBlock * sizeof(float2) + sizeof(int)) : 0;
 #define NVBX_TB(S, I)                                                                                                \
-  LAUNCH((k_trace_and_band<S, I>), n_trace + n_band, 256, 0, stream, mp.dev, tp, mp.synth2[mp.dev.fp].p, trace_tiles_x, \
-         n_trace, pv, trunc, band_list, mp.newfeat_slots2[mp.dev.fp].p, tile_cells, n_tiles, color_parity)
+  do {                                                                                                               \
+    static const bool big_smem_ok = [] {                                                                             \
+      return cudaFuncSetAttribute(k_trace_and_band<S, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == \
+             cudaSuccess;                                                                                            \
+    }();                                                                                                             \
+    if (tb_smem > 48 * 1024 && !big_smem_ok) return fail(NVBX_ERR_CUDA, "cannot raise the tracer's shared memory");  \
+    LAUNCH((k_trace_and_band<S, I>), n_trace + n_band, 256, tb_smem, stream, mp.dev, tp, mp.synth2[mp.dev.fp].p,     \
+           trace_tiles_x, n_trace, pv, trunc, band_list, mp.newfeat_slots2[mp.dev.fp].p, tile_cells, n_tiles,        \
+           color_parity);                                                                                            \
+  } while (0)
     if (spec == 1 && ilp == 1) {
       NVBX_TB(1, 1);
     } else if (spec == 1) {

@@ -752,6 +752,8 @@ struct TraceParams {
   float free_dist;  // the TSDF truncation distance: what every voxel of a kBlockFreeBit block holds
   int use_free;     // tuning knob (NVBX_TRACE_FREE): consult kBlockFreeBit
   int team;         // 1: eight lanes per ray (sphere_trace_team), trace CTAs cover 8 x 4 rays; 0: one thread per ray
+  int cache_blocks; // 0: scalar march; 2 / 4: sphere_trace_ray_cached with that many TSDF blocks per warp in (dynamic)
+                    // shared memory (8 warps x cache_blocks x 4 KB + tags)
   int march;        // marching threads per trace CTA: 256 (16 x 16 rays) or 128 / 64 / 32 (8 columns x march / 8 rows;
                     // the CTA's other warps only help to stage the workspace table): spreads the rays over more SMs
 };
@@ -924,6 +926,184 @@ __device__ __forceinline__ int sphere_trace_ray(const MapDev& m, const TracePara
   }
   image[(size_t)r * tp.cols + c] = ok ? t * dc.z : -1.0f;
   return n_steps;
+}
+
+// ---- cached march: the TSDF blocks a warp's rays cross are staged in shared memory ------------------------------
+// The scalar march above pays one L2 round trip per sample that falls into a block near the surface, and those are
+// the samples of the slow rays (the step shrinks with the distance, 10 .. 24 dependent round trips, each ~1 us while
+// the previous frame's gather saturates the memory system).  The 32 rays of a warp (an 8 x 4 patch of the synthetic
+// image) cross the same one or two blocks there.  Here every warp keeps E whole TSDF blocks (4 KB each) in shared
+// memory.  A block is staged when a lane samples it twice in a row (the ray lingers: it is near the surface), by
+// cp.async in the background of that step's ordinary loads, so staging never adds a round trip; every later sample of
+// any lane into that block is a shared-memory read, and a step in which all lanes hit costs no round trip at all.
+// Same positions, same values, same decisions as the scalar march: only where a voxel is read from changes.
+// Warp-synchronous (no CTA barrier): all 32 lanes stay in the loop until the last ray of the warp is done.
+template <int E>
+__device__ __forceinline__ void sphere_trace_ray_cached(const MapDev& m, const TraceParams& tp, int r, int c,
+                                                        bool in_image, float* __restrict__ image, const int* s_ws,
+                                                        float2* cache, int* tags) {
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const float pu = (float)(c * tp.sub) + 0.5f * (float)tp.sub * 1.0f;
+  const float pv = (float)(r * tp.sub) + 0.5f * (float)tp.sub * 1.0f;
+  const V3 ray = ray_from_image_plane(tp.cam, pu, pv);
+  const float sq = fmaf(ray.x, ray.x, fmaf(ray.y, ray.y, ray.z * ray.z));
+  V3 dc = ray;
+  if (sq > 0.0f) {
+    const float nrm = sqrtf(sq);
+    dc.x = ray.x / nrm;
+    dc.y = ray.y / nrm;
+    dc.z = ray.z / nrm;
+  }
+  const V3 dl = dev_rotate(tp.T_L_C, dc);
+  const float ox = tp.T_L_C.t[0], oy = tp.T_L_C.t[1], oz = tp.T_L_C.t[2];
+  const bool closed_world = (m.ws_sx > 0) && (m.ctrl->n_hash == 0);
+  const I3 ws_mx = {m.ws_mn.x + m.ws_sx - 1, m.ws_mn.y + m.ws_sy - 1, m.ws_mn.z + m.ws_sz - 1};
+  const float bs = m.block_size, bs_inv = 1.0f / m.block_size;
+
+  if (lane < E) tags[lane] = -1;
+  __syncwarp();
+  int victim = 0;      // round-robin replacement (warp-uniform)
+  int prev_slot = -1;  // the block this lane's previous sample fell into
+
+  int first = 0;
+  float t = 0.0f;
+  bool ok = false;
+  int i = 0;
+  bool run = in_image && (i < tp.max_steps) && (t < tp.max_ray_length);
+  while (__any_sync(kFull, run)) {
+    // which voxel does o + t * d read?  (getBlockAndVoxelIndexFromPositionInLayer, indexing_impl.h:37-49)
+    int slot = -1, vox = 0;
+    bool gone = false, free_blk = false;
+    if (run) {
+      V3 p;
+      p.x = fmaf(t, dl.x, ox);
+      p.y = fmaf(t, dl.y, oy);
+      p.z = fmaf(t, dl.z, oz);
+      I3 b, v;
+      b.x = floor_div_exact(p.x, bs, bs_inv);
+      b.y = floor_div_exact(p.y, bs, bs_inv);
+      b.z = floor_div_exact(p.z, bs, bs_inv);
+      v.x = min((int)(fmaf(-(float)b.x, bs, p.x) * m.voxel_size_inv), 7);
+      v.y = min((int)(fmaf(-(float)b.y, bs, p.y) * m.voxel_size_inv), 7);
+      v.z = min((int)(fmaf(-(float)b.z, bs, p.z) * m.voxel_size_inv), 7);
+      vox = (v.x * 8 + v.y) * 8 + v.z;
+      const int cell = ws_cell(m, b.x, b.y, b.z);
+      if (cell >= 0) {
+        slot = s_ws ? s_ws[cell] : m.ws_slot[cell];
+        if (s_ws && slot >= 0) {
+          free_blk = (slot & kNewFlag) != 0;
+          slot &= kSlotMask;
+        }
+      } else if (!closed_world) {
+        slot = hash_find(m, b.x, b.y, b.z);
+      } else {
+        gone = (b.x > ws_mx.x && dl.x >= 0.0f) || (b.x < m.ws_mn.x && dl.x <= 0.0f) ||
+               (b.y > ws_mx.y && dl.y >= 0.0f) || (b.y < m.ws_mn.y && dl.y <= 0.0f) ||
+               (b.z > ws_mx.z && dl.z >= 0.0f) || (b.z < m.ws_mn.z && dl.z <= 0.0f);
+      }
+    }
+    // The voxel's value.  A block already staged for this warp is read from shared memory; any other voxel is loaded
+    // straight from global memory exactly like the scalar march does (all lanes' loads in one round trip), and a block
+    // a lane samples for the SECOND time in a row -- the ray lingers there: it is close to the surface -- is staged in
+    // the background (cp.async, in flight together with those loads) for the samples still to come.
+    const bool need = run && slot >= 0 && !free_blk;
+    float2 q = make_float2(0.0f, 0.0f);
+    int hit = -1;
+    if (need) {
+#pragma unroll
+      for (int k = 0; k < E; ++k)
+        if (tags[k] == slot) hit = k;
+    }
+    const float2* gaddr = nullptr;
+    if (need) {
+      if (hit >= 0)
+        q = cache[(size_t)hit * kVoxelsPerBlock + vox];
+      else
+        gaddr = tsdf_block(m, slot) + vox;
+    }
+    __syncwarp();  // the staged entries have been read: they may be replaced now
+    unsigned want = __ballot_sync(kFull, need && hit < 0 && slot == prev_slot);
+    bool staged_any = false;
+    int n_staged = 0;  // at most E blocks per step: two copies in flight must never target the same entry
+    while (want && n_staged < E) {
+      const int s = __shfl_sync(kFull, slot, __ffs(want) - 1);
+      bool present = false;
+#pragma unroll
+      for (int k = 0; k < E; ++k) present |= (tags[k] == s);
+      if (!present) {
+        const int e = victim;
+        victim = (victim + 1 == E) ? 0 : victim + 1;
+        const uint4* src = reinterpret_cast<const uint4*>(tsdf_block(m, s));
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(cache + (size_t)e * kVoxelsPerBlock);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)(lane + 32 * j) * 16u),
+                       "l"(src + lane + 32 * j));
+        __syncwarp();
+        if (lane == 0) tags[e] = s;
+        staged_any = true;
+        ++n_staged;
+      }
+      want &= ~__ballot_sync(kFull, need && slot == s);
+      __syncwarp();
+    }
+    if (gaddr) q = *gaddr;
+    prev_slot = run ? slot : -1;
+    if (staged_any) {  // warp-uniform
+      asm volatile("cp.async.commit_group;");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    if (run) {  // sphereTracingKernel's step (sphere_tracer.cu:31-131), exactly as in sphere_trace_ray
+      if (gone) {
+        run = false;
+      } else {
+        bool valid = false;
+        float dist = 0.0f;
+        if (slot >= 0) {
+          if (free_blk) q = make_float2(tp.free_dist, 1.0f);
+          if (q.y > 1e-4f) {
+            valid = true;
+            dist = q.x;
+          }
+        }
+        float step = 0.0f;
+        if (!valid) {
+          if (first == 0) {
+            step = tp.trunc;
+          } else {
+            run = false;  // left observed space: fail
+          }
+        } else {
+          if (first == 0) first = (dist >= 0.0f) ? 1 : -1;
+          if (first == 1) {
+            if (dist < tp.eps) {
+              t += dist;
+              ok = true;
+              run = false;
+            } else {
+              step = dist;
+            }
+          } else {
+            if (dist > -tp.eps) {
+              t -= dist;
+              ok = true;
+              run = false;
+            } else {
+              step = -dist;
+            }
+          }
+        }
+        if (run) {
+          t += step;
+          ++i;
+          if (!((i < tp.max_steps) && (t < tp.max_ray_length))) run = false;
+        }
+      }
+    }
+  }
+  if (in_image) image[(size_t)r * tp.cols + c] = ok ? t * dc.z : -1.0f;
 }
 
 // ---- team march: G lanes share one ray ---------------------------------------------------------------------
@@ -1118,6 +1298,19 @@ __global__ void __launch_bounds__(256) k_trace_and_band(MapDev m, TraceParams tp
       const int tc = (blockIdx.x % trace_tiles_x) * 8 + (ray & 7);
       const int tr = (blockIdx.x / trace_tiles_x) * 4 + (ray >> 3);
       sphere_trace_team<8>(m, tp, tr, tc, tr < tp.rows && tc < tp.cols, image, stage_ws ? s_ws : nullptr);
+      PROF_END(kProfTrace);
+      return;
+    }
+    if (tp.cache_blocks) {  // whole TSDF blocks staged per warp (dynamic shared memory)
+      extern __shared__ uint4 s_dyn[];
+      const int warp = threadIdx.x >> 5, nb = tp.cache_blocks;
+      float2* cache = reinterpret_cast<float2*>(s_dyn) + (size_t)warp * nb * kVoxelsPerBlock;
+      int* tags = reinterpret_cast<int*>(reinterpret_cast<float2*>(s_dyn) + (size_t)8 * nb * kVoxelsPerBlock) + warp * nb;
+      const bool in_image = r < tp.rows && c < tp.cols;
+      if (nb == 4)
+        sphere_trace_ray_cached<4>(m, tp, r, c, in_image, image, stage_ws ? s_ws : nullptr, cache, tags);
+      else
+        sphere_trace_ray_cached<2>(m, tp, r, c, in_image, image, stage_ws ? s_ws : nullptr, cache, tags);
       PROF_END(kProfTrace);
       return;
     }

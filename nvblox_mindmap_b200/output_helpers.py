@@ -71,18 +71,55 @@ def _owned(tensors, zero_copy: bool):
 def sample_to_n_vertices(vertices: torch.Tensor, features: torch.Tensor, desired_num_vertices: int, method,
                          seed: Optional[int] = None, mapper=None, mapper_id: int = 0, zero_copy: bool = False
                          ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """vertex_sampling.py:29-81.  `vertices` / `features` are CUDA tensors; they are staged through the mapper's
-    export arena (identity filter).  Returns tensors that own their memory unless `zero_copy=True` (then they are
-    views of the mapper's arenas, valid until its next export / gather / mesh update)."""
+    """vertex_sampling.py:29-81.  fp16 CUDA rows are staged through the mapper's export arena (identity filter; skipped
+    when they already ARE the mapper's last export) and sampled by one gather kernel; anything else takes the
+    reference's torch path and keeps its dtype.  Returns tensors that own their memory unless `zero_copy=True` (then
+    they are views of the mapper's arenas, valid until its next export / gather / mesh update)."""
     assert vertices.dim() == 2
     assert features.dim() == 2
     assert vertices.shape[0] == features.shape[0]
+    if features.dtype != torch.float16 or not vertices.is_cuda:
+        # The device path moves fp16 rows; any other input (the reference keeps whatever dtype it is given) goes through
+        # the same torch calls the reference makes, so nothing is down-cast behind the caller's back.
+        return _sample_with_torch(vertices, features, desired_num_vertices, method, seed)
     if mapper is None:
         raise ValueError('sample_to_n_vertices needs the mapper whose export arena holds the points')
-    big = 3.0e38
-    ev, ef = mapper.export_points(mapper_id, (-big,) * 3, (big,) * 3, 0, False, vertices=vertices,
-                                  features=features.to(torch.float16))
+    last = getattr(mapper, '_last_export', {}).get(mapper_id)
+    if last is not None and last == (vertices.data_ptr(), features.data_ptr(), vertices.shape[0], features.shape[1]):
+        ev, ef = vertices, features         # already the arena's own views (export_points output): nothing to stage
+    else:
+        big = 3.0e38
+        ev, ef = mapper.export_points(mapper_id, (-big,) * 3, (big,) * 3, 0, False, vertices=vertices, features=features)
     return _owned(_sample_exported(mapper, mapper_id, ev, ef, desired_num_vertices, method, seed, None), zero_copy)
+
+
+def _sample_with_torch(vertices, features, desired, method, seed):
+    """vertex_sampling.py:29-176 with plain torch indexing (inputs that are not fp16 CUDA rows)."""
+    n = features.shape[0]
+    m = _method_value(method)
+    if m == 'none' or n == desired:
+        return vertices, features, torch.ones(n, device=vertices.device, dtype=torch.bool)
+    if n > desired:
+        if m == 'random_without_replacement':
+            if seed is not None:
+                torch.manual_seed(seed)
+            idx = torch.randperm(n)[:desired]
+        elif m == 'random_with_replacement':
+            if seed is not None:
+                torch.manual_seed(seed)
+            idx = torch.randint(0, n, (desired,))
+        elif m == 'lowest':
+            idx = torch.from_numpy(np.argsort(-vertices[:, 2].cpu().numpy())[:desired].astype(np.int64))
+        else:
+            raise ValueError(f'Vertex sampling method {method} is not yet implemented.')
+        idx = idx.to(vertices.device)
+        return vertices[idx, :], features[idx, :], torch.ones(desired, device=vertices.device, dtype=torch.bool)
+    pad = desired - n
+    features = torch.cat([features, torch.zeros((pad, features.shape[1]), device=features.device)], dim=0)
+    vertices = torch.cat([vertices, torch.zeros((pad, vertices.shape[1]), device=vertices.device)], dim=0)
+    valid = torch.ones(desired, device=vertices.device, dtype=torch.bool)
+    valid[n:] = False
+    return vertices, features, valid
 
 
 def get_vertices_and_features(mapper, mapper_id: int, nvblox_mapping_config, remove_zero_features: bool,

@@ -127,6 +127,7 @@ class Mapper:
         self._handle = handle
         self._pipelining = False
         self._async_enqueue = False
+        self._last_export = {}    # mapper_id -> (vertices ptr, features ptr, rows, channels) of the last export_points
         self._held_frames = {}    # mapper_id -> deque of input tensors kept alive while pipelining (see _hold)
 
     def __del__(self):
@@ -448,6 +449,7 @@ class Mapper:
             C.byref(ov), C.byref(of), self._stream()))
         keep = ch - int(num_excess_features)
         d = self._device
+        self._last_export[mapper_id] = (ov.value, of.value, count, keep)   # output_helpers.sample_to_n_vertices
         return (device_view(ov.value, (count, 3), torch.float32, d, owner=self),
                 device_view(of.value, (count, keep), torch.float16, d, owner=self))
 
