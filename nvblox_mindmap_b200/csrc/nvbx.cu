@@ -689,6 +689,7 @@ int make_grid(const nvbx_mapper* m, const Map& mp, Aabb a, GridSpec* out) {
   return NVBX_OK;
 }
 
+thread_local bool t_multi_map_batch = false;  // this thread is issuing one map's share of a multi-map batch
 thread_local bool t_async_worker = false;  // this thread is a mapper's enqueue worker: never wait for the FIFO
 // Wait until every asynchronously queued frame has been issued; report the error one of them ran into.
 int async_flush(nvbx_mapper* m) {
@@ -1554,6 +1555,15 @@ int integrate_features_impl(nvbx_mapper* m, int map_id, const void* features, co
     std::memcpy(&ff.h_w2, &h2, 2);
   }
   ff.read_old = (p.strict_blend || ff.alpha != 1.0f) ? 1 : 0;
+  // Pixel rows loaded without allocating in L1 (ldg_nc_stream)?  Measured on the B200 (profiles/r02_pipelining.md):
+  // a single map with voxels that project to several pixels (cube stacking 2 cm, the 1024^2 stress rig) gains
+  // (gather alone 24.8 -> 23.3 us, stress step +11 %): the rows are used once and the L1 is better left to the depth
+  // path; with voxels denser than the pixels (drill in box, 1 cm at 512^2: 1.6 distinct pixels per voxel) the L1 is what
+  // merges the neighbours' repeated rows (0.67 -> 0.52 of the roofline without it), and with several maps on one GPU
+  // the L2 is the bound and the merging helps too (-10 % without it).  Hence: stream when a voxel at 1 m covers at
+  // least four pixels (fx x voxel size) and the frame does not come from a multi-map batch.  NVBX_GATHER_STREAM_LOADS=0 / 1 forces it.
+  static const int stream_loads = env_int("NVBX_GATHER_STREAM_LOADS", -1);
+  ff.stream_loads = stream_loads >= 0 ? (stream_loads != 0) : (fx * mp.voxel_size >= 4.0f && !t_multi_map_batch);
   if (pipe && cand_bound > chunk_blocks) {  // several geometry / gather passes share one item list: not pipelined
     pipe = false;
     if ((rc = pipeline_join(mp, stream))) return rc;
@@ -2441,6 +2451,7 @@ int nvbx_integrate_frames_batch(nvbx_frame_job* jobs, int n_jobs, int n_threads)
   std::string first_error;
   int first_rc = NVBX_OK, first_job = n_jobs;
   auto work = [&](int w) {
+    t_multi_map_batch = handles.size() > 1;
     for (int i = 0; i < n_jobs; ++i) {
       if (owner[i] % n_workers != w) continue;
       nvbx_frame_job& j = jobs[i];
@@ -2459,6 +2470,7 @@ int nvbx_integrate_frames_batch(nvbx_frame_job* jobs, int n_jobs, int n_threads)
         }
       }
     }
+    t_multi_map_batch = false;
   };
   {
     std::lock_guard<std::mutex> g(g_batch_mu);

@@ -1400,6 +1400,7 @@ struct FeatFrame {
   float max_weight;
   unsigned short h_w1, h_w2;  // half bits of (1-alpha)/(total), alpha/(total)
   int read_old;               // 1: blend with the stored feature (alpha < 1 or strict mode)
+  int stream_loads;           // 1: pixel rows are loaded without allocating in L1 (k_feature_gather_dyn)
 };
 
 __device__ __forceinline__ __half2 interp_h2(__half2 x, __half2 y, __half2 xy, __half2 f00, __half2 f01, __half2 f10,
@@ -1432,6 +1433,16 @@ __device__ __forceinline__ uint4 blend_vec(uint4 oldv, uint4 meas, __half2 w1, _
   return o;
 }
 __device__ __forceinline__ uint4 ldg_nc(const uint4* p) { return __ldg(p); }
+// The same read-only load without allocating the line in L1: the gather streams every pixel row through once, and while
+// it shares the SMs with the next frame's depth path (frame pipelining) those lines only push that path's TSDF / table
+// lines out of L1.
+__device__ __forceinline__ uint4 ldg_nc_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
 
 // One voxel to update (16 bytes, moved as one uint4).
 struct __align__(16) FeatItem {
@@ -1680,10 +1691,17 @@ __global__ void __launch_bounds__(THREADS, CTAS) k_feature_gather_dyn(MapDev m, 
     if (live) {
       const uint4* p00 = reinterpret_cast<const uint4*>(f.img + (size_t)cur.pix * C) + cvec;
       const uint4* p01 = p00 + (size_t)f.cols * nvec;
-      a00 = ldg_nc(p00);
-      a10 = ldg_nc(p00 + nvec);
-      a01 = ldg_nc(p01);
-      a11 = ldg_nc(p01 + nvec);
+      if (f.stream_loads) {  // warp-uniform
+        a00 = ldg_nc_stream(p00);
+        a10 = ldg_nc_stream(p00 + nvec);
+        a01 = ldg_nc_stream(p01);
+        a11 = ldg_nc_stream(p01 + nvec);
+      } else {
+        a00 = ldg_nc(p00);
+        a10 = ldg_nc(p00 + nvec);
+        a01 = ldg_nc(p01);
+        a11 = ldg_nc(p01 + nvec);
+      }
     }
     // next unit (and its item) while the pixel loads fly
     long long qn;
