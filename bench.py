@@ -874,8 +874,8 @@ def cold_start_stage(depths, poses, feats, K_t, local_rank, n=8):
 
 def ncu_traffic_bytes():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` summary
-    (profiles/r02z_feature_gather.md: dram__bytes_read.sum + dram__bytes_write.sum, first capture)."""
-    path = os.path.join(ROOT, 'profiles', 'r02z_feature_gather.md')
+    (profiles/r02am_feature_gather.md: dram__bytes_read.sum + dram__bytes_write.sum, first capture)."""
+    path = os.path.join(ROOT, 'profiles', 'r02am_feature_gather.md')
     try:
         rd = wr = None
         for line in open(path):
@@ -885,7 +885,7 @@ def ncu_traffic_bytes():
             if len(cells) > 3 and cells[1] == 'dram__bytes_write.sum' and wr is None:
                 wr = float(cells[2]) * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1.0}[cells[3]]
         if rd is not None and wr is not None:
-            return rd + wr, 'profiles/r02z_feature_gather.md (ncu --set full, one launch of the same workload)'
+            return rd + wr, 'profiles/r02am_feature_gather.md (ncu --set full, one launch of the same workload)'
     except Exception:
         pass
     return None, None
