@@ -8,6 +8,7 @@ without a Blackwell GPU raises.
 """
 import collections
 import ctypes as C
+import os
 from enum import Enum
 from typing import List, Optional
 
@@ -129,6 +130,14 @@ class Mapper:
         self._async_enqueue = False
         self._last_export = {}    # mapper_id -> (vertices ptr, features ptr, rows, channels) of the last export_points
         self._held_frames = {}    # mapper_id -> deque of input tensors kept alive while pipelining (see _hold)
+        # Opt-in without touching the caller's code (a drop-in under mindmap's own loop): NVBX_PIPELINING=1 turns frame
+        # pipelining on for every Mapper of the process, =2 adds asynchronous enqueue.  The caller then promises what
+        # set_pipelining's contract says: frames are not modified in place after they were handed over.
+        mode = os.environ.get('NVBX_PIPELINING', '0').strip()
+        if mode in ('1', '2'):
+            self.set_pipelining(True, async_enqueue=(mode == '2'))
+        elif mode not in ('', '0'):
+            raise ValueError(f'NVBX_PIPELINING={mode!r}: expected 0, 1 or 2')
 
     def __del__(self):
         h = getattr(self, '_handle', None)
