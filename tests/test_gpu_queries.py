@@ -115,6 +115,7 @@ def test_get_all_blocks_single_pass():
     from nvblox_mindmap_b200 import _capi
     pair = _pair(n_frames=2)
     L = _capi.load()
+    pair.gpu.pipeline_join()   # (NVBX_PIPELINING=2: frames still queued would be issued -- and counted -- inside the call)
     for view, layer_id in ((pair.gpu.tsdf_layer_view(0), 0), (pair.gpu.feature_layer_view(0), 1)):
         before = int(L.nvbx_kernel_launch_count())
         blocks, indices = view.get_all_blocks()

@@ -39,3 +39,20 @@ def test_variant_reproduces_reference_kernels(knobs):
     tail = (r.stdout or '')[-1500:] + (r.stderr or '')[-500:]
     assert r.returncode == 0, tail
     assert ' passed' in r.stdout and 'failed' not in r.stdout, tail
+
+
+@pytest.mark.parametrize('mode', ['1', '2'])
+def test_whole_parity_suite_under_env_opt_in(mode):
+    """NVBX_PIPELINING=1 / 2 (every Mapper of the process pipelines, 2: with asynchronous enqueue) under callers that
+    know nothing about it: the whole CUDA-vs-oracle parity file (decay, clear, masks, colour frames, queries, block
+    views, meshes, viewpoint cache, several maps per mapper ... in between frames) and mindmap's own mapping helpers
+    still produce the oracle's bits -- every entry point orders itself behind what is queued or in flight."""
+    env = dict(os.environ)
+    env['NVBX_PIPELINING'] = mode
+    r = subprocess.run([sys.executable, '-m', 'pytest', 'tests/test_gpu_parity.py', 'tests/test_gpu_queries.py',
+                        'tests/test_gpu_reference_suite.py::test_mindmap_mapping_helpers_drive_the_drop_in',
+                        '-q', '-x', '--no-header', '-m', 'gpu', '-p', 'no:cacheprovider'],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    tail = (r.stdout or '')[-2500:] + (r.stderr or '')[-500:]
+    assert r.returncode == 0, tail
+    assert ' passed' in r.stdout and 'failed' not in r.stdout, tail
