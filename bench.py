@@ -451,7 +451,11 @@ def run_ours(args, rank, world, local_rank):
                     'transfer': 'depth by cudaMemcpyAsync; pinned feature frame read sparsely through its device '
                                 f'mapping ({e2e_px:.0f} of {H * W} pixels per step cross PCIe, each once)',
                     'dense_copy': {'value': dense_value, 'unit': 'frames/s',
-                                   'h2d_bytes_per_step': H * W * 4 + H * W * C_FEAT * 2}},
+                                   'h2d_bytes_per_step': H * W * 4 + H * W * C_FEAT * 2},
+                    # what the host's memory system has to deliver for this figure (all ranks read pinned host memory
+                    # through the same root complex / NUMA node: the aggregate is what saturates at N = 4 .. 8)
+                    'host_read_GBps_aggregate': e2e_value * e2e_h2d / 1e9,
+                    'host_read_GBps_per_rank': e2e_value * e2e_h2d / 1e9 / world},
             'gpu_launches': launches,
             'clocks': clocks,
             'e2e_lowres': {'value': e2e_lowres_value, 'unit': 'frames/s', 'h2d_bytes_per_step': e2e_lowres_h2d,
