@@ -153,7 +153,8 @@ class Mapper:
         return current_stream_ptr(self._device)
 
     @staticmethod
-    def _mask_ptr(mask_frame: Optional[torch.Tensor], image: torch.Tensor) -> Optional[int]:
+    def _mask_tensor(mask_frame: Optional[torch.Tensor], image: torch.Tensor) -> Optional[torch.Tensor]:
+        """The mask as the C ABI reads it (contiguous uint8 on the device), or None."""
         if mask_frame is None:
             return None
         # py_mapper.cu:90-99: not-on-GPU / size mismatch are logged and the frame is skipped there;
@@ -162,9 +163,12 @@ class Mapper:
         assert mask_frame.dtype == torch.uint8, 'Mask frame should have type torch.uint8.'
         assert mask_frame.shape[0] == image.shape[0] and mask_frame.shape[1] == image.shape[1], \
             'Mask frame size should match the image.'
-        if not mask_frame.is_contiguous():
-            mask_frame = mask_frame.contiguous()
-        return mask_frame.data_ptr()
+        return mask_frame if mask_frame.is_contiguous() else mask_frame.contiguous()
+
+    @staticmethod
+    def _mask_ptr(mask_frame: Optional[torch.Tensor], image: torch.Tensor) -> Optional[int]:
+        m = Mapper._mask_tensor(mask_frame, image)
+        return None if m is None else m.data_ptr()
 
     def params(self) -> MapperParams:
         return MapperParams(self._params)
@@ -180,7 +184,8 @@ class Mapper:
         assert 0 <= mapper_id < len(self._voxel_sizes)
         check_integrator_inputs(depth_frame, t_w_c, intrinsics, 'Depth', 2, torch.float32)
         depth_frame = depth_frame if depth_frame.is_contiguous() else depth_frame.contiguous()
-        mask_ptr = self._mask_ptr(mask_frame, depth_frame)
+        mask_frame = self._mask_tensor(mask_frame, depth_frame)   # (a contiguous copy, if one was needed, is what is held)
+        mask_ptr = None if mask_frame is None else mask_frame.data_ptr()
         fx, fy, cx, cy = _fxfycxcy(intrinsics)
         _capi.check(self._lib.nvbx_integrate_depth(
             self._handle, mapper_id, depth_frame.data_ptr(), depth_frame.shape[0], depth_frame.shape[1], mask_ptr,
@@ -214,7 +219,8 @@ class Mapper:
         assert 0 <= mapper_id < len(self._voxel_sizes)
         check_integrator_inputs(feature_frame, t_w_c, intrinsics, 'Feature', 3, torch.float16, self._feature_channels)
         feature_frame = feature_frame if feature_frame.is_contiguous() else feature_frame.contiguous()
-        mask_ptr = self._mask_ptr(mask_frame, feature_frame)
+        mask_frame = self._mask_tensor(mask_frame, feature_frame)
+        mask_ptr = None if mask_frame is None else mask_frame.data_ptr()
         fx, fy, cx, cy = _fxfycxcy(intrinsics)
         _capi.check(self._lib.nvbx_integrate_features(
             self._handle, mapper_id, feature_frame.data_ptr(), feature_frame.shape[0], feature_frame.shape[1],
@@ -245,24 +251,25 @@ class Mapper:
             j.mapper, j.map_id, j.stream = self._handle.value, mapper_id, stream
             j.height, j.width = int(d.shape[0]), int(d.shape[1])
             j.depth = d.data_ptr()
-            dm = None if depth_masks is None else depth_masks[k]
-            j.depth_mask = self._mask_ptr(dm, d)
+            dm = self._mask_tensor(None if depth_masks is None else depth_masks[k], d)
+            j.depth_mask = None if dm is None else dm.data_ptr()
+            fm = None
             if f is not None:
                 check_integrator_inputs(f, T, K, 'Feature', 3, torch.float16, self._feature_channels)
                 assert f.shape[0] == d.shape[0] and f.shape[1] == d.shape[1], 'Feature frame size should match the depth frame.'
                 f = f if f.is_contiguous() else f.contiguous()
                 j.channels = int(f.shape[2])
                 j.features = f.data_ptr()
-                fm = None if feature_masks is None else feature_masks[k]
-                j.feature_mask = self._mask_ptr(fm, f)
+                fm = self._mask_tensor(None if feature_masks is None else feature_masks[k], f)
+                j.feature_mask = None if fm is None else fm.data_ptr()
             Tc = T if T.is_contiguous() else T.contiguous()
             C.memmove(j.T_L_C, Tc.data_ptr(), 64)
             j.fx, j.fy, j.cx, j.cy = _fxfycxcy(K)
-            keep.append((d, f, dm, Tc))
+            keep.append((d, f, dm, fm, Tc))
         _capi.check(self._lib.nvbx_integrate_frames_batch(jobs, n, 1))
         if self._pipelining:
-            for d, f, dm, _ in keep[-(_HOLD_ASYNC // 2):]:
-                self._hold(mapper_id, f, None if feature_masks is None else feature_masks[0])
+            for d, f, dm, fm, _ in keep[-(_HOLD_ASYNC // 4):]:
+                self._hold(mapper_id, f, fm)
                 if self._async_enqueue:
                     self._hold(mapper_id, d, dm)
 
